@@ -1,0 +1,139 @@
+/* k4b_hamm.h - C ABI of the B200-native K-mer Hamming-distance engine.
+ *
+ * This is the drop-in boundary for the `ngskit4b hammings` hot path.  The reference has no
+ * FFI seam of its own; the seam sits exactly where the reference hands its concatenated
+ * genome and result array to the worker pool:
+ *   - exhaustive (-m1/-m2): ngskit4b/hammings.cpp:2740-2867 (thread params, ThreadedGHamDist,
+ *     GHamDistWatson :3183-3287, GHamDistCrick :3300-3489, per-thread min-merge :2855-2867)
+ *   - targeted  (-m0 -I):   ngskit4b/hammings.cpp:1691-1694 (RestrictedHammingThread calling
+ *     CSfxArray::LocateHammings, libkit4b/SfxArray.cpp:4227-4331)
+ * Plain pointers and sizes only; caller owns every host buffer; the library copies what it
+ * needs to the device.  All entry points return 0 (eBSFSuccess, libkit4b/ErrorCodes.h:16) on
+ * success or a negative teBSFrsltCodes-style value; they never throw and never exit().
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * K4B_ERR_NODEVICE.
+ */
+#ifndef K4B_HAMM_H
+#define K4B_HAMM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* result codes: values follow libkit4b/ErrorCodes.h:15-30 where a counterpart exists */
+#define K4B_OK 0
+#define K4B_ERR_PARAMS (-100)   /* eBSFerrParams */
+#define K4B_ERR_MEM (-95)       /* eBSFerrMem */
+#define K4B_ERR_NODEVICE (-1000) /* no usable CUDA device / library built without a device */
+#define K4B_ERR_CUDA (-1001)    /* a CUDA runtime call failed; see k4b_last_error() */
+#define K4B_ERR_NCCL (-1002)    /* a NCCL call failed; see k4b_last_error() */
+#define K4B_ERR_UNSUPPORTED (-1003)
+
+/* base codes of the concatenated arrays: libkit4b/commdefs.h:76-91 */
+#define K4B_BASE_EOS 7u
+#define K4B_BASE_EOG 0x0fu
+#define K4B_RPT_MASK 0x08u
+
+/* Limits mirrored from the reference CLI: ngskit4b/hammings.cpp:36-42 */
+#define K4B_MIN_K 10u
+#define K4B_MAX_K 5000u
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+
+/* Creates contexts and streams on n_gpus devices (0 = all visible) and, when more than one
+ * device is used, a single-process NCCL communicator for the one-off broadcast of the packed
+ * target set.  Replaces the reference's pthread pool set-up (hammings.cpp:2752-2780). */
+int k4b_gpu_init(int n_gpus, const int *device_ids /* nullable */);
+void k4b_gpu_shutdown(void);
+/* number of devices in use after k4b_gpu_init (0 before) */
+int k4b_gpu_count(void);
+/* thread-local, never NULL */
+const char *k4b_last_error(void);
+
+/* ---- exhaustive all-vs-all (-m1) --------------------------------------------------------- */
+
+/* Replaces ThreadedGHamDist + GHamDistWatson/Crick + merge (hammings.cpp:883-939, 3183-3489,
+ * 2855-2867).
+ *   concat       == &m_pGenomeSeq[1] (hammings.cpp:924): codes 0..6, eBaseEOS (7) between
+ *                   chromosomes, no leading/trailing EOG; soft-mask bit already cleared
+ *   concat_len   == m_GenomeLen-2
+ *   K            10..5000
+ *   both_strands -c
+ *   sweep_start/sweep_end  SSeqStart/SSeqEnd after clamping (hammings.cpp:2690-2706);
+ *                   defaults 1 and m_GenomeLen (= concat_len+2) select every pair
+ *   out_min      concat_len entries PRE-FILLED by the caller (K+1, hammings.cpp:3120-3122);
+ *                   lowered (min) at valid K-mer start positions only
+ * Queries are sharded over all initialised GPUs; minima are gathered on the host. */
+int k4b_hamm_exhaustive(const uint8_t *concat, uint32_t concat_len, uint32_t K, int both_strands,
+                        uint32_t sweep_start, uint32_t sweep_end, uint16_t *out_min);
+
+/* Same computation restricted to the query K-mers whose flat start position lies in
+ * [q_begin, q_end): the multi-GPU / multi-process shard unit (one process per GPU under
+ * torchrun calls this with its own range; targets are always the whole concat). Runs on the
+ * first initialised device of this process. */
+int k4b_hamm_exhaustive_shard(const uint8_t *concat, uint32_t concat_len, uint32_t K,
+                              int both_strands, uint32_t q_begin, uint32_t q_end,
+                              uint16_t *out_min);
+
+/* ---- targeted probes-vs-assembly (-m0 -I) -------------------------------------------------- */
+
+/* Replaces RestrictedHammingThread + CSfxArray::LocateHammings (hammings.cpp:1593-1708,
+ * SfxArray.cpp:4227-4627) by exact brute force on the GPU.
+ *   target_concat/target_len  the .sfx sequence area: each entry's bases followed by EOS
+ *                             (SfxArray.cpp:1746-1750)
+ *   probe_concat/probe_len    probes in the LoadGenome layout (hammings.cpp:2201-2310)
+ *   K 10..500, R 1..10; result per probe K-mer start = min(true both-strand minimum,
+ *   K/(K/(R+1))) i.e. the reference's "not found" value (SfxArray.cpp:4462-4463)
+ *   out_h  probe_len entries PRE-FILLED 0xFF; written at valid probe K-mer starts */
+int k4b_hamm_targeted(const uint8_t *target_concat, uint64_t target_len,
+                      const uint8_t *probe_concat, uint32_t probe_len, uint32_t K, int R,
+                      int both_strands, uint32_t q_begin, uint32_t q_end, uint8_t *out_h);
+
+/* ---- device-resident API (inputs already in HBM; used by bench.py and by ranks that receive
+ *      the packed target set over NCCL instead of packing it themselves) --------------------- */
+
+typedef struct k4b_packed k4b_packed; /* opaque: bit-plane packed sequence set on one device */
+
+/* bytes of one device-resident packed image for a concat of this length (for NCCL broadcast) */
+size_t k4b_packed_image_bytes(uint32_t concat_len);
+/* Packs a HOST concat (H2D copy + pack kernel on the current device of this process). */
+int k4b_pack_host(const uint8_t *concat, uint32_t concat_len, uint32_t K, k4b_packed **out);
+/* Packs a DEVICE-resident concat (16-byte aligned; pack + valid-start kernels only). */
+int k4b_pack_device(const void *d_concat, uint32_t concat_len, uint32_t K, void *stream,
+                    k4b_packed **out);
+/* device pointer + size of the packed image (planes+valid bits), e.g. for ncclBroadcast */
+void *k4b_packed_image_ptr(k4b_packed *p);
+size_t k4b_packed_image_size(k4b_packed *p);
+/* Rebuilds a handle around an image received from another rank (image stays owned by caller).*/
+int k4b_packed_from_image(void *d_image, size_t image_bytes, uint32_t concat_len, uint32_t K,
+                          int has_non_acgt, k4b_packed **out);
+int k4b_packed_has_non_acgt(k4b_packed *p);
+uint64_t k4b_packed_num_kmers(k4b_packed *p);
+void k4b_packed_free(k4b_packed *p);
+
+/* All-pairs minimum on device-resident data: queries = K-mers of `queries` starting in
+ * [q_begin,q_end), targets = all K-mers of `targets`.  self_exclude!=0 skips the pair
+ * (query position == target position) on the forward strand (Watson offsets start at 1,
+ * hammings.cpp:2692; the reverse-complement self pair is kept, :3300-3489).
+ * d_out_min: DEVICE uint16[q_end-q_begin]; positions that are not valid K-mer starts get
+ * K+1.  clamp>0 caps results at clamp (targeted mode).  Asynchronous on `stream`.
+ * *launches (nullable) receives the number of kernels enqueued. */
+int k4b_allpairs_min_device(k4b_packed *queries, k4b_packed *targets, int both_strands,
+                            int self_exclude, uint32_t q_begin, uint32_t q_end, uint32_t clamp,
+                            uint16_t *d_out_min, void *stream, int *launches);
+/* duration in ms of the most recent allpairs kernel enqueued by this thread, measured with
+ * CUDA events on the launching stream (blocks until that kernel has finished) */
+float k4b_last_kernel_ms(void);
+
+/* ---- integer-pipe roofline microbenchmark ----------------------------------- */
+/* which: 0 POPC only, 1 LOP3 only, 2 engine mix (2 LOP3 + 1 POPC + min), 3 IADD3 only.
+ * Returns giga warp-lane-ops per second (ops/s / 1e9) on the current device in *gops. */
+int k4b_microbench_intpipe(int which, int iters, double *gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* K4B_HAMM_H */

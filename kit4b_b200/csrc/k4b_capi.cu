@@ -1,0 +1,597 @@
+// k4b_capi.cu - extern "C" boundary of the engine (include/k4b_hamm.h): device management,
+// packing, query sharding over the GPUs of one box, NCCL broadcast of the packed target set,
+// gather of per-GPU minima.  Host orchestration only; the arithmetic is in k4b_kernels.cu.
+// There is deliberately no CPU implementation behind any entry point.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "../../include/k4b_hamm.h"
+#include "k4b_kernels.cuh"
+
+using namespace k4b;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int cuda_code(cudaError_t e) {
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? K4B_ERR_NODEVICE
+           : (e == cudaErrorMemoryAllocation)                           ? K4B_ERR_MEM
+                                                                        : K4B_ERR_CUDA;
+}
+#define CU(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(cuda_code(e_), "%s:%d %s: %s", __FILE__, __LINE__, #call,              \
+                        cudaGetErrorString(e_));                                               \
+    } while (0)
+#define RC(call)              \
+    do {                      \
+        int rc_ = (call);     \
+        if (rc_) return rc_;  \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen (only needed when ONE process drives several GPUs; under torchrun the
+// broadcast is issued by torch.distributed on the image pointer instead)
+// ------------------------------------------------------------------------------------------
+typedef struct ncclComm *ncclComm_t;
+struct NcclApi {
+    void *h = nullptr;
+    int (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int /*ncclDataType_t*/, int /*root*/,
+                     ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+constexpr int kNcclUint8 = 1;  // ncclUint8 in nccl.h
+
+struct Engine {
+    std::vector<int> devs;
+    std::vector<cudaStream_t> streams;
+    std::vector<ncclComm_t> comms;
+    NcclApi nccl;
+    bool inited = false;
+};
+static Engine g_eng;
+static std::mutex g_mu;
+
+static int load_nccl(NcclApi &n) {
+    if (n.h) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        n.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (n.h) break;
+    }
+    if (!n.h) return fail(K4B_ERR_NCCL, "dlopen libnccl.so.2 failed: %s", dlerror());
+#define SYM(field, name)                     \
+    *(void **)(&n.field) = dlsym(n.h, name); \
+    if (!n.field) return fail(K4B_ERR_NCCL, "libnccl lacks symbol %s", name)
+    SYM(CommInitAll, "ncclCommInitAll");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(Broadcast, "ncclBroadcast");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return 0;
+}
+
+extern "C" int k4b_gpu_init(int n_gpus, const int *device_ids) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_eng.inited) return K4B_OK;
+    int avail = 0;
+    cudaError_t e = cudaGetDeviceCount(&avail);
+    if (e != cudaSuccess || avail <= 0)
+        return fail(K4B_ERR_NODEVICE, "no CUDA device: %s (this engine has no CPU fallback)",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (n_gpus <= 0) n_gpus = avail;
+    if (n_gpus > avail) return fail(K4B_ERR_PARAMS, "%d GPUs requested, %d visible", n_gpus, avail);
+    g_eng.devs.clear();
+    for (int i = 0; i < n_gpus; ++i) {
+        const int d = device_ids ? device_ids[i] : i;
+        if (d < 0 || d >= avail) return fail(K4B_ERR_PARAMS, "bad device id %d", d);
+        g_eng.devs.push_back(d);
+    }
+    g_eng.streams.assign(n_gpus, nullptr);
+    for (int i = 0; i < n_gpus; ++i) {
+        CU(cudaSetDevice(g_eng.devs[i]));
+        CU(cudaStreamCreateWithFlags(&g_eng.streams[i], cudaStreamNonBlocking));
+    }
+    if (n_gpus > 1) {
+        RC(load_nccl(g_eng.nccl));
+        g_eng.comms.assign(n_gpus, nullptr);
+        int nr = g_eng.nccl.CommInitAll(g_eng.comms.data(), n_gpus, g_eng.devs.data());
+        if (nr) return fail(K4B_ERR_NCCL, "ncclCommInitAll: %s", g_eng.nccl.GetErrorString(nr));
+    }
+    CU(cudaSetDevice(g_eng.devs[0]));
+    g_eng.inited = true;
+    return K4B_OK;
+}
+
+extern "C" void k4b_gpu_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_eng.inited) return;
+    for (size_t i = 0; i < g_eng.comms.size(); ++i)
+        if (g_eng.comms[i]) g_eng.nccl.CommDestroy(g_eng.comms[i]);
+    g_eng.comms.clear();
+    for (size_t i = 0; i < g_eng.devs.size(); ++i) {
+        cudaSetDevice(g_eng.devs[i]);
+        if (g_eng.streams[i]) cudaStreamDestroy(g_eng.streams[i]);
+    }
+    g_eng.streams.clear();
+    g_eng.devs.clear();
+    g_eng.inited = false;
+}
+
+extern "C" int k4b_gpu_count(void) { return g_eng.inited ? (int)g_eng.devs.size() : 0; }
+extern "C" const char *k4b_last_error(void) { return g_err; }
+
+static int ensure_init() {
+    if (g_eng.inited) return K4B_OK;
+    return k4b_gpu_init(1, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------
+// packed images
+// ------------------------------------------------------------------------------------------
+struct k4b_packed {
+    uint32_t *d_image = nullptr;
+    bool owns = false;
+    int device = 0;
+    uint32_t len = 0, K = 0, nw = 0, nwp = 0;
+    int has_non_acgt = 0;
+    uint64_t num_kmers = 0;
+    uint32_t *d_rc_planes = nullptr;  // lazily built: reverse-complemented planes (K > 128 path)
+    ImageView view() const { return ImageView{d_image, nwp, len}; }
+};
+
+static uint32_t padded_words(uint32_t len) {
+    const uint32_t nw = (len + 31) / 32;
+    return (nw + kTileGroups - 1) / kTileGroups * kTileGroups + kTileGroups;
+}
+extern "C" size_t k4b_packed_image_bytes(uint32_t concat_len) {
+    return (size_t)padded_words(concat_len) * 4 * sizeof(uint32_t);
+}
+extern "C" void *k4b_packed_image_ptr(k4b_packed *p) { return p ? p->d_image : nullptr; }
+extern "C" size_t k4b_packed_image_size(k4b_packed *p) { return p ? (size_t)p->nwp * 16 : 0; }
+extern "C" int k4b_packed_has_non_acgt(k4b_packed *p) { return p ? p->has_non_acgt : 0; }
+extern "C" uint64_t k4b_packed_num_kmers(k4b_packed *p) { return p ? p->num_kmers : 0; }
+extern "C" void k4b_packed_free(k4b_packed *p) {
+    if (!p) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(p->device);
+    if (p->owns && p->d_image) cudaFree(p->d_image);
+    if (p->d_rc_planes) cudaFree(p->d_rc_planes);
+    cudaSetDevice(cur);
+    delete p;
+}
+
+static int check_k(uint32_t K, uint32_t lo, uint32_t hi) {
+    if (K < lo || K > hi) return fail(K4B_ERR_PARAMS, "K=%u outside %u..%u", K, lo, hi);
+    return 0;
+}
+static int check_len(uint64_t len) {
+    if (!len) return fail(K4B_ERR_PARAMS, "empty sequence");
+    if (len > 0xffffffffull - 64ull * kTileGroups)
+        return fail(K4B_ERR_PARAMS, "sequence of %llu bases exceeds the 32-bit position space",
+                    (unsigned long long)len);
+    return 0;
+}
+
+extern "C" int k4b_pack_device(const void *d_concat, uint32_t concat_len, uint32_t K, void *stream,
+                               k4b_packed **out) {
+    if (!out) return fail(K4B_ERR_PARAMS, "out is NULL");
+    *out = nullptr;
+    RC(ensure_init());
+    RC(check_k(K, K4B_MIN_K, K4B_MAX_K));
+    if (!d_concat) return fail(K4B_ERR_PARAMS, "NULL sequence");
+    RC(check_len(concat_len));
+    if (((uintptr_t)d_concat & 15) != 0)
+        return fail(K4B_ERR_PARAMS, "device concat must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    k4b_packed *p = new k4b_packed;
+    cudaGetDevice(&p->device);
+    p->len = concat_len;
+    p->K = K;
+    p->nw = (concat_len + 31) / 32;
+    p->nwp = padded_words(concat_len);
+    p->owns = true;
+    struct Scratch {
+        uint32_t flags;
+        uint32_t pad;
+        unsigned long long count;
+    };
+    Scratch *d_s = nullptr;
+    Scratch h_s = {0, 0, 0};
+    cudaError_t e = cudaMalloc(&p->d_image, (size_t)p->nwp * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&d_s, sizeof(Scratch));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_s, 0, sizeof(Scratch), st);
+    if (e == cudaSuccess)
+        e = launch_pack((const uint8_t *)d_concat, concat_len, p->d_image, p->nwp, &d_s->flags, st);
+    if (e == cudaSuccess) e = launch_valid(p->d_image, p->nwp, concat_len, K, &d_s->count, st);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(&h_s, d_s, sizeof(Scratch), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (d_s) cudaFree(d_s);
+    if (e != cudaSuccess) {
+        k4b_packed_free(p);
+        return fail(cuda_code(e), "pack (%u bases): %s", concat_len, cudaGetErrorString(e));
+    }
+    p->has_non_acgt = (int)(h_s.flags & 1u);
+    p->num_kmers = h_s.count;
+    *out = p;
+    return K4B_OK;
+}
+
+extern "C" int k4b_pack_host(const uint8_t *concat, uint32_t concat_len, uint32_t K,
+                             k4b_packed **out) {
+    if (!out) return fail(K4B_ERR_PARAMS, "out is NULL");
+    *out = nullptr;
+    RC(ensure_init());
+    if (!concat) return fail(K4B_ERR_PARAMS, "NULL sequence");
+    RC(check_len(concat_len));
+    uint8_t *d_c = nullptr;
+    CU(cudaMalloc(&d_c, ((size_t)concat_len + 15) / 16 * 16));
+    cudaError_t e = cudaMemcpy(d_c, concat, concat_len, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d_c);
+        return fail(K4B_ERR_CUDA, "H2D concat: %s", cudaGetErrorString(e));
+    }
+    int rc = k4b_pack_device(d_c, concat_len, K, nullptr, out);
+    cudaFree(d_c);
+    return rc;
+}
+
+extern "C" int k4b_packed_from_image(void *d_image, size_t image_bytes, uint32_t concat_len,
+                                     uint32_t K, int has_non_acgt, k4b_packed **out) {
+    if (!out) return fail(K4B_ERR_PARAMS, "out is NULL");
+    *out = nullptr;
+    if (!d_image || image_bytes != k4b_packed_image_bytes(concat_len))
+        return fail(K4B_ERR_PARAMS, "image is %zu bytes, expected %zu", image_bytes,
+                    k4b_packed_image_bytes(concat_len));
+    RC(ensure_init());
+    RC(check_k(K, K4B_MIN_K, K4B_MAX_K));
+    k4b_packed *p = new k4b_packed;
+    cudaGetDevice(&p->device);
+    p->d_image = (uint32_t *)d_image;
+    p->owns = false;
+    p->len = concat_len;
+    p->K = K;
+    p->nw = (concat_len + 31) / 32;
+    p->nwp = padded_words(concat_len);
+    p->has_non_acgt = has_non_acgt;
+    p->num_kmers = 0;
+    *out = p;
+    return K4B_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// all-pairs on device-resident data
+// ------------------------------------------------------------------------------------------
+static thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static thread_local int g_ev_dev = -1;
+
+extern "C" float k4b_last_kernel_ms(void) {
+    if (!g_ev0) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(g_ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+extern "C" int k4b_allpairs_min_device(k4b_packed *queries, k4b_packed *targets, int both_strands,
+                                       int self_exclude, uint32_t q_begin, uint32_t q_end,
+                                       uint32_t clamp, uint16_t *d_out_min, void *stream,
+                                       int *launches) {
+    if (launches) *launches = 0;
+    if (!queries || !targets) return fail(K4B_ERR_PARAMS, "NULL packed handle");
+    if (queries->K != targets->K) return fail(K4B_ERR_PARAMS, "query/target K differ");
+    if (queries->device != targets->device)
+        return fail(K4B_ERR_PARAMS, "query and target images live on different devices");
+    if (q_end > queries->len) q_end = queries->len;
+    if (q_begin >= q_end) return K4B_OK;
+    if (!d_out_min) return fail(K4B_ERR_PARAMS, "d_out_min is NULL");
+    CU(cudaSetDevice(queries->device));
+    const uint32_t K = queries->K;
+    const uint32_t nq = q_end - q_begin;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool three = queries->has_non_acgt || targets->has_non_acgt;
+    const bool crick = both_strands != 0;
+    const uint32_t W = (K + 31) / 32;
+    const bool generic = W > (uint32_t)kMaxRegW;
+
+    if (generic && crick && !queries->d_rc_planes) {
+        CU(cudaMalloc(&queries->d_rc_planes, (size_t)queries->nwp * 12));
+        CU(launch_revcomp_planes(queries->view(), queries->d_rc_planes, st));
+    }
+    if (g_ev_dev != queries->device) {
+        if (g_ev0) {
+            cudaEventDestroy(g_ev0);
+            cudaEventDestroy(g_ev1);
+        }
+        CU(cudaEventCreate(&g_ev0));
+        CU(cudaEventCreate(&g_ev1));
+        g_ev_dev = queries->device;
+    }
+
+    uint32_t *d_min32 = nullptr;
+    CU(cudaMallocAsync(&d_min32, (size_t)nq * 4, st));
+    CU(launch_fill_u32(d_min32, nq, K + 1, st));
+
+    AllPairsParams prm;
+    prm.q = queries->view();
+    prm.t = targets->view();
+    prm.K = K;
+    prm.q_begin = q_begin;
+    prm.q_end = q_end;
+    prm.tiles_total = (targets->nw + kTileGroups - 1) / kTileGroups;
+    prm.out = d_min32;
+    prm.self_exclude = self_exclude ? 1 : 0;
+    // enough CTAs for ~16 balanced waves on 148 SMs x 2 resident CTAs; never below one tile
+    const uint32_t qpt = generic ? 1u : (uint32_t)queries_per_thread(W, three);
+    const uint32_t qblocks = (nq + kThreads * qpt - 1) / (kThreads * qpt);
+    uint32_t want_chunks = (4736 + qblocks - 1) / qblocks;
+    want_chunks = std::max(1u, std::min(want_chunks, prm.tiles_total));
+    prm.tiles_per_chunk = (prm.tiles_total + want_chunks - 1) / want_chunks;
+
+    cudaError_t e = cudaEventRecord(g_ev0, st);
+    if (e == cudaSuccess) {
+        if (!generic)
+            e = launch_allpairs(prm, three, crick, st, nullptr);
+        else
+            e = launch_allpairs_generic(prm, three, crick, queries->d_rc_planes, queries->nwp, st,
+                                        nullptr);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(g_ev1, st);
+    if (e == cudaSuccess)
+        e = launch_finalize(d_min32, queries->view(), q_begin, nq, K, clamp, d_out_min, st);
+    cudaFreeAsync(d_min32, st);
+    if (e != cudaSuccess) return fail(cuda_code(e), "allpairs launch: %s", cudaGetErrorString(e));
+    if (launches) *launches = 3;  // fill + allpairs + finalize
+    return K4B_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer entry points
+// ------------------------------------------------------------------------------------------
+namespace {
+struct DevJob {
+    k4b_packed *q = nullptr, *t = nullptr;  // t == q for all-vs-all
+    uint16_t *d_out = nullptr;
+    uint16_t *h_out = nullptr;  // pinned
+    uint32_t q_begin = 0, q_end = 0;
+    void release() {
+        if (d_out) cudaFree(d_out);
+        if (h_out) cudaFreeHost(h_out);
+        if (t && t != q) k4b_packed_free(t);
+        if (q) k4b_packed_free(q);
+        d_out = nullptr;
+        h_out = nullptr;
+        q = t = nullptr;
+    }
+};
+
+// broadcast the image of `src` (on device index 0 of the engine) to fresh images on every
+// other engine device: ONE ncclBroadcast per set, nothing else crosses NVLink afterwards
+int broadcast_packed(k4b_packed *src, std::vector<k4b_packed *> &out) {
+    const int n = (int)g_eng.devs.size();
+    out.assign(n, nullptr);
+    out[0] = src;
+    if (n == 1) return 0;
+    const size_t bytes = k4b_packed_image_size(src);
+    for (int i = 1; i < n; ++i) {
+        CU(cudaSetDevice(g_eng.devs[i]));
+        void *img = nullptr;
+        CU(cudaMalloc(&img, bytes));
+        int rc = k4b_packed_from_image(img, bytes, src->len, src->K, src->has_non_acgt, &out[i]);
+        if (rc) {
+            cudaFree(img);
+            return rc;
+        }
+        out[i]->owns = true;
+        out[i]->num_kmers = src->num_kmers;
+    }
+    int nr = g_eng.nccl.GroupStart();
+    for (int i = 0; i < n && !nr; ++i)
+        nr = g_eng.nccl.Broadcast(src->d_image, out[i]->d_image, bytes, kNcclUint8, 0,
+                                  g_eng.comms[i], g_eng.streams[i]);
+    int nr2 = g_eng.nccl.GroupEnd();
+    if (nr || nr2)
+        return fail(K4B_ERR_NCCL, "ncclBroadcast: %s", g_eng.nccl.GetErrorString(nr ? nr : nr2));
+    for (int i = 0; i < n; ++i) {
+        CU(cudaSetDevice(g_eng.devs[i]));
+        CU(cudaStreamSynchronize(g_eng.streams[i]));
+    }
+    return 0;
+}
+
+// queries [q_begin,q_end) split evenly by position over the engine's devices; per-device
+// minima land in pinned host buffers and are handed to `sink(pos, value)`
+template <typename Sink>
+int run_sharded(const uint8_t *q_concat, uint32_t q_len, const uint8_t *t_concat, uint32_t t_len,
+                uint32_t K, int both, int self_ex, uint32_t q_begin, uint32_t q_end,
+                uint32_t clamp, int use_all_devices, Sink sink) {
+    RC(ensure_init());
+    const int n = use_all_devices ? (int)g_eng.devs.size() : 1;
+    if (q_end > q_len) q_end = q_len;
+    if (q_begin >= q_end) return K4B_OK;
+    std::vector<DevJob> jobs(n);
+    auto cleanup = [&]() {
+        for (int i = 0; i < n; ++i) {
+            cudaSetDevice(g_eng.devs[i]);
+            jobs[i].release();
+        }
+        cudaSetDevice(g_eng.devs[0]);
+    };
+    int rc = 0;
+    do {
+        // pack once on device 0, broadcast to the rest
+        CU(cudaSetDevice(g_eng.devs[0]));
+        k4b_packed *q0 = nullptr, *t0 = nullptr;
+        if ((rc = k4b_pack_host(q_concat, q_len, K, &q0))) break;
+        jobs[0].q = q0;
+        const bool same = (t_concat == nullptr);
+        if (same) {
+            jobs[0].t = q0;
+        } else {
+            if ((rc = k4b_pack_host(t_concat, t_len, K, &t0))) break;
+            jobs[0].t = t0;
+        }
+        if (n > 1) {
+            std::vector<k4b_packed *> qs, ts;
+            rc = broadcast_packed(q0, qs);
+            for (int i = 1; i < n; ++i) jobs[i].q = qs.size() > (size_t)i ? qs[i] : nullptr;
+            if (rc) break;
+            if (same) {
+                for (int i = 1; i < n; ++i) jobs[i].t = jobs[i].q;
+            } else {
+                rc = broadcast_packed(t0, ts);
+                for (int i = 1; i < n; ++i) jobs[i].t = ts.size() > (size_t)i ? ts[i] : nullptr;
+                if (rc) break;
+            }
+        }
+        // launch every shard (asynchronous), then collect
+        const uint64_t span = (uint64_t)q_end - q_begin;
+        for (int i = 0; i < n && !rc; ++i) {
+            DevJob &j = jobs[i];
+            j.q_begin = q_begin + (uint32_t)(span * i / n);
+            j.q_end = q_begin + (uint32_t)(span * (i + 1) / n);
+            const uint32_t nq = j.q_end - j.q_begin;
+            if (!nq) continue;
+            cudaError_t e = cudaSetDevice(g_eng.devs[i]);
+            if (e == cudaSuccess) e = cudaMalloc(&j.d_out, (size_t)nq * 2);
+            if (e == cudaSuccess) e = cudaMallocHost(&j.h_out, (size_t)nq * 2);
+            if (e != cudaSuccess) {
+                rc = fail(cuda_code(e), "shard buffers: %s", cudaGetErrorString(e));
+                break;
+            }
+            rc = k4b_allpairs_min_device(j.q, j.t, both, self_ex, j.q_begin, j.q_end, clamp,
+                                         j.d_out, g_eng.streams[i], nullptr);
+            if (rc) break;
+            e = cudaMemcpyAsync(j.h_out, j.d_out, (size_t)nq * 2, cudaMemcpyDeviceToHost,
+                                g_eng.streams[i]);
+            if (e != cudaSuccess) rc = fail(cuda_code(e), "D2H: %s", cudaGetErrorString(e));
+        }
+        for (int i = 0; i < n; ++i) {
+            cudaSetDevice(g_eng.devs[i]);
+            cudaError_t e = cudaStreamSynchronize(g_eng.streams[i]);
+            if (e != cudaSuccess && !rc)
+                rc = fail(cuda_code(e), "device %d: %s", g_eng.devs[i], cudaGetErrorString(e));
+        }
+        if (rc) break;
+        // concatenate per-GPU minima back on the host
+        for (int i = 0; i < n; ++i) {
+            const DevJob &j = jobs[i];
+            for (uint32_t p = j.q_begin; p < j.q_end; ++p) sink(p, j.h_out[p - j.q_begin]);
+        }
+    } while (0);
+    cleanup();
+    return rc;
+}
+
+int check_full_sweep(uint32_t concat_len, uint32_t K, uint32_t sweep_start, uint32_t sweep_end) {
+    // Watson offsets s in [start,end] with s <= len-K, Crick offsets s-1 (hammings.cpp:924-928):
+    // start==1 and end >= len+1-K select every pair.  Sub-ranges (-b/-B, -m2) are a "next" row.
+    const uint32_t need_end = concat_len + 1 > K ? concat_len + 1 - K : 0;
+    if (sweep_start != 1 || (sweep_end != 0 && sweep_end < need_end))
+        return fail(K4B_ERR_UNSUPPORTED,
+                    "partial sweep %u..%u is not supported yet (full sweep is 1..%u)", sweep_start,
+                    sweep_end, concat_len + 2);
+    return 0;
+}
+}  // namespace
+
+extern "C" int k4b_hamm_exhaustive_shard(const uint8_t *concat, uint32_t concat_len, uint32_t K,
+                                         int both_strands, uint32_t q_begin, uint32_t q_end,
+                                         uint16_t *out_min) {
+    if (!concat || !out_min) return fail(K4B_ERR_PARAMS, "NULL buffer");
+    RC(check_k(K, K4B_MIN_K, K4B_MAX_K));
+    return run_sharded(concat, concat_len, nullptr, 0, K, both_strands, 1, q_begin, q_end, 0, 0,
+                       [&](uint32_t pos, uint16_t v) {
+                           if (v <= K && v < out_min[pos]) out_min[pos] = v;
+                       });
+}
+
+extern "C" int k4b_hamm_exhaustive(const uint8_t *concat, uint32_t concat_len, uint32_t K,
+                                   int both_strands, uint32_t sweep_start, uint32_t sweep_end,
+                                   uint16_t *out_min) {
+    if (!concat || !out_min) return fail(K4B_ERR_PARAMS, "NULL buffer");
+    RC(check_k(K, K4B_MIN_K, K4B_MAX_K));
+    RC(check_full_sweep(concat_len, K, sweep_start, sweep_end));
+    return run_sharded(concat, concat_len, nullptr, 0, K, both_strands, 1, 0, concat_len, 0, 1,
+                       [&](uint32_t pos, uint16_t v) {
+                           if (v <= K && v < out_min[pos]) out_min[pos] = v;
+                       });
+}
+
+extern "C" int k4b_hamm_targeted(const uint8_t *target_concat, uint64_t target_len,
+                                 const uint8_t *probe_concat, uint32_t probe_len, uint32_t K,
+                                 int R, int both_strands, uint32_t q_begin, uint32_t q_end,
+                                 uint8_t *out_h) {
+    if (!target_concat || !probe_concat || !out_h) return fail(K4B_ERR_PARAMS, "NULL buffer");
+    RC(check_k(K, K4B_MIN_K, 500));  // SfxArray.cpp:4255
+    if (R < 1 || R > 10) return fail(K4B_ERR_PARAMS, "R=%d outside 1..10", R);
+    if (K / (uint32_t)(R + 1) < 4)  // hammings.cpp:399-404
+        return fail(K4B_ERR_PARAMS, "K/(R+1) must be >= 4");
+    RC(check_len(target_len));
+    // "not found" value of the pigeonhole search: CoreLen = K/(Rmax+1), K/CoreLen
+    // (SfxArray.cpp:4462-4463)
+    const uint32_t core = K / (uint32_t)(R + 1);
+    const uint32_t notfound = K / core;
+    if (q_end == 0 || q_end > probe_len) q_end = probe_len;
+    return run_sharded(probe_concat, probe_len, target_concat, (uint32_t)target_len, K,
+                       both_strands, 0, q_begin, q_end, notfound, 1,
+                       [&](uint32_t pos, uint16_t v) {
+                           if (v <= K) out_h[pos] = (uint8_t)v;
+                       });
+}
+
+// ------------------------------------------------------------------------------------------
+// integer-pipe microbenchmark
+// ------------------------------------------------------------------------------------------
+extern "C" int k4b_microbench_intpipe(int which, int iters, double *gops) {
+    if (!gops) return fail(K4B_ERR_PARAMS, "gops is NULL");
+    RC(ensure_init());
+    uint32_t *d_sink = nullptr;
+    CU(cudaMalloc(&d_sink, 4));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    int blocks = 0, threads = 0, ops = 0;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {  // first rep is warm-up
+        CU(cudaEventRecord(a, 0));
+        cudaError_t e = launch_microbench(which, iters, d_sink, &blocks, &threads, &ops, 0);
+        if (e != cudaSuccess) return fail(K4B_ERR_CUDA, "microbench: %s", cudaGetErrorString(e));
+        CU(cudaEventRecord(b, 0));
+        CU(cudaEventSynchronize(b));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        const double g = (double)blocks * threads * ops * (double)iters / (ms * 1e-3) / 1e9;
+        if (rep > 0 && g > best) best = g;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d_sink);
+    *gops = best;
+    return K4B_OK;
+}
