@@ -105,18 +105,17 @@ __device__ __forceinline__ uint32_t eos_word(const uint32_t *img, uint32_t nwp, 
     if (w >= nwp) return 0xffffffffu;
     return img[w] & img[(size_t)nwp + w] & img[(size_t)2 * nwp + w];
 }
-// first EOS position >= pos, scanning no further than pos+K (returns >= pos+K when none)
+// first EOS position >= pos found while scanning the words that overlap [pos, pos+K); kNoEos
+// when those words hold none (a hit may lie at or beyond pos+K: callers compare)
+constexpr uint64_t kNoEos = ~0ull;
 __device__ uint64_t next_eos(const uint32_t *img, uint32_t nwp, uint64_t pos, uint32_t K) {
     const uint64_t lim = pos + K;
     uint32_t w = (uint32_t)(pos >> 5);
     uint32_t e = eos_word(img, nwp, w) & (0xffffffffu << (pos & 31));
     while (true) {
-        if (e) {
-            const uint64_t f = ((uint64_t)w << 5) + (__ffs(e) - 1);
-            return f;
-        }
+        if (e) return ((uint64_t)w << 5) + (__ffs(e) - 1);
         ++w;
-        if (((uint64_t)w << 5) >= lim) return lim;
+        if (((uint64_t)w << 5) >= lim) return kNoEos;
         e = eos_word(img, nwp, w);
     }
 }
@@ -129,15 +128,15 @@ __global__ void __launch_bounds__(256) valid_kernel(uint32_t *__restrict__ image
     if (g < nwp) {
         const uint64_t base = (uint64_t)g << 5;
         if (base < len) {
-            uint64_t ne = next_eos(image, nwp, base, K + 32);
-            if (ne >= base + 31 + K) {
+            // common case: no EOS anywhere in [base, base+31+K) -> all 32 starts are valid
+            uint64_t ne = next_eos(image, nwp, base, K + 31);
+            if (ne == kNoEos || ne >= base + 31 + K) {
                 v = 0xffffffffu;
             } else {
-                ne = next_eos(image, nwp, base, K);
                 for (int i = 0; i < 32; ++i) {
                     const uint64_t pos = base + i;
-                    if (ne < pos) ne = next_eos(image, nwp, pos, K);
-                    if (ne >= pos + K) v |= 1u << i;
+                    if (ne == kNoEos || ne < pos) ne = next_eos(image, nwp, pos, K);
+                    if (ne == kNoEos || ne >= pos + K) v |= 1u << i;
                 }
             }
         }

@@ -1,0 +1,150 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against (1) the golden files
+written by the unmodified reference, (2) the pinned oracle on seeded inputs, and (3)
+size-independent properties at BASELINE.json's config-1 size.  Bit-exact everywhere (integer
+work)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, case_id, golden_cases, load_case, random_genome
+
+import kit4b_b200 as k4b
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _engine():
+    k4b.gpu_init(1)
+    yield
+    k4b.gpu_shutdown()
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=case_id)
+def test_cuda_matches_reference_golden_files(oracle, case):
+    name, r = case
+    concat, chroms, glen = load_case(oracle, name)
+    hd = k4b.exhaustive(concat, r["K"], r["both"])
+    gold = open(os.path.join(GOLDEN, r["csv"]), "rb").read()
+    assert oracle.exhaustive_csv(glen, chroms, r["K"], hd) == gold
+
+
+RANDOM_CASES = [
+    # seed, chromosome lengths, K, both strands, alphabet size
+    (101, [5000], 10, True, 4),
+    (102, [3000, 2500], 25, True, 4),
+    (103, [4000, 31, 32, 33, 1000], 32, True, 4),
+    (104, [6000], 33, False, 4),
+    (105, [2000, 2000, 2000], 50, True, 4),
+    (106, [5000], 64, True, 4),
+    (107, [3000, 3000], 96, True, 4),
+    (108, [4000], 100, True, 4),
+    (109, [4100], 128, False, 4),
+    (110, [2500, 500], 129, True, 4),   # generic path
+    (111, [3000], 500, True, 4),        # generic path, many words
+    (112, [4000, 2000], 25, True, 7),   # N / Undef / InDel symbols: three-plane path
+    (113, [3000], 100, True, 5),
+    (114, [9000, 9000], 16, True, 2),   # low-complexity: many zero distances, early exit
+    (115, [20000], 25, True, 4),        # spans several tiles and query blocks
+]
+
+
+@pytest.mark.parametrize("seed,lens,K,both,alpha", RANDOM_CASES, ids=lambda v: str(v).replace(" ", ""))
+def test_cuda_matches_oracle_on_seeded_inputs(oracle, seed, lens, K, both, alpha):
+    c = random_genome(seed, lens, alpha)
+    want = oracle.exhaustive_sliding(c, K, both)
+    got = k4b.exhaustive(c, K, both)
+    assert np.array_equal(got, want)
+
+
+def test_shards_concatenate_to_the_full_result(oracle):
+    c = random_genome(201, [7000, 5000])
+    K = 25
+    want = oracle.exhaustive_sliding(c, K, True)
+    out = np.full(len(c), K + 1, dtype=np.uint16)
+    cuts = [0, 1, 2049, 5000, 7003, 9999, len(c)]
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        k4b.exhaustive_shard(c, K, True, b, e, out)
+    assert np.array_equal(out, want)
+
+
+def test_edge_cases(oracle):
+    # all chromosomes shorter than K -> nothing lowered
+    c = random_genome(301, [8, 9, 5])
+    assert (k4b.exhaustive(c, 12, True) == 13).all()
+    # sequence shorter than K
+    assert (k4b.exhaustive(np.zeros(7, np.uint8), 10, True) == 11).all()
+    # a single K-mer that is its own reverse complement
+    c = np.array([0, 1, 2, 3] * 3, dtype=np.uint8)
+    assert k4b.exhaustive(c, 12, False)[0] == 13
+    assert k4b.exhaustive(c, 12, True)[0] == 0
+    # K bounds (hammings.cpp:36-38)
+    for bad in (9, 5001):
+        with pytest.raises(k4b.K4BError):
+            k4b.exhaustive(random_genome(1, [100]), bad, True)
+    # length exactly K and K+1
+    for n in (25, 26):
+        c = random_genome(302 + n, [n])
+        assert np.array_equal(k4b.exhaustive(c, 25, True), oracle.exhaustive_brute(c, 25, True))
+
+
+def test_targeted_matches_oracle(oracle):
+    rng = np.random.default_rng(401)
+    target = random_genome(402, [30000, 20000])
+    # probes: mutated copies of target regions (forward and reverse complement) + random
+    parts = []
+    for start, nmut, rc in [(1000, 0, False), (5000, 1, False), (9000, 2, True), (12000, 3, False),
+                            (31000, 4, True), (35000, 6, False)]:
+        seg = target[start:start + 200].copy()
+        for p in rng.choice(200, size=nmut * 6, replace=False):
+            seg[p] = (seg[p] + 1 + rng.integers(0, 3)) % 4
+        if rc:
+            seg = oracle.CPL[seg[::-1]]
+        parts.append(seg)
+    parts.append(rng.integers(0, 4, size=500, dtype=np.uint8))
+    probes = []
+    for i, p in enumerate(parts):
+        probes.append(p)
+        if i + 1 < len(parts):
+            probes.append(np.array([7], dtype=np.uint8))
+    probes = np.ascontiguousarray(np.concatenate(probes))
+    for K, R in [(32, 3), (25, 3), (20, 1), (50, 5)]:
+        want = oracle.targeted_brute(target, probes, K, R, True)
+        got = k4b.targeted(target, probes, K, R, True)
+        assert np.array_equal(got, want), (K, R)
+
+
+@pytest.mark.parametrize("K", [25])
+def test_config1_size_properties(oracle, K):
+    """1 Mbp, K=25, both strands (BASELINE.json configs[0]): properties that hold at any size."""
+    G = 1_000_000
+    rng = np.random.default_rng(12)
+    c = rng.integers(0, 4, size=G, dtype=np.uint8)
+    # plant an exact duplicate, a reverse-complement copy and a 2-mismatch copy
+    c[700000:700060] = c[1000:1060]
+    c[800000:800060] = oracle.CPL[c[2000:2060][::-1]]
+    c[900000:900040] = c[3000:3040]
+    c[900010] = (c[900010] + 1) % 4
+    c[900030] = (c[900030] + 2) % 4
+    c = np.ascontiguousarray(c)
+    hd = k4b.exhaustive(c, K, True)
+    n = G - K + 1
+    assert (hd[n:] == K + 1).all() and (hd[:n] <= K).all()
+    assert (hd[1000:1000 + 36] == 0).all() and (hd[700000:700000 + 36] == 0).all()
+    assert (hd[2000:2000 + 36] == 0).all() and (hd[800000:800000 + 36] == 0).all()
+    assert hd[3000] <= 2 and hd[900000] <= 2
+    # Watson-only result can never be below the both-strand result
+    hw = k4b.exhaustive(c, K, False)
+    assert (hw >= hd).all()
+    assert (hw[2000:2000 + 36] > 0).any()
+    # spot check 48 random K-mers with an O(G*K) brute force on the host
+    X = np.lib.stride_tricks.sliding_window_view(c, K)
+    RCX = oracle.CPL[X[:, ::-1]]
+    for i in rng.choice(n, size=48, replace=False):
+        d = (X != X[i]).sum(1)
+        d[i] = K + 1
+        best = min(d.min(), (RCX != X[i]).sum(1).min())
+        assert hd[i] == best, i
+    # idempotence: a second run gives the same array
+    assert np.array_equal(hd, k4b.exhaustive(c, K, True))

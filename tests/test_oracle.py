@@ -1,0 +1,71 @@
+"""CPU tests: the oracle against the golden vectors written by the unmodified reference
+(tests/golden/make_golden.py), i.e. the pin that every GPU parity test leans on."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, case_id, golden_cases, golden_manifest, load_case, random_genome
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=case_id)
+def test_sliding_oracle_matches_reference_output(oracle, case):
+    name, r = case
+    concat, chroms, glen = load_case(oracle, name)
+    hd = oracle.exhaustive_sliding(concat, r["K"], r["both"], threads=3)
+    gold = open(os.path.join(GOLDEN, r["csv"]), "rb").read()
+    assert oracle.exhaustive_csv(glen, chroms, r["K"], hd) == gold
+
+
+@pytest.mark.parametrize("case", [c for c in golden_cases() if c[0] in ("adversarial", "nonacgt")], ids=case_id)
+def test_brute_and_numpy_oracles_match_reference_output(oracle, case):
+    name, r = case
+    concat, chroms, glen = load_case(oracle, name)
+    gold = open(os.path.join(GOLDEN, r["csv"]), "rb").read()
+    assert oracle.exhaustive_csv(glen, chroms, r["K"], oracle.exhaustive_brute(concat, r["K"], r["both"])) == gold
+    assert oracle.exhaustive_csv(glen, chroms, r["K"], oracle.numpy_brute(concat, r["K"], r["both"])) == gold
+
+
+def test_fasta_encoding_equals_reference_bioseq(oracle):
+    for name, case in golden_manifest().items():
+        fa = oracle.encode_fasta(open(os.path.join(GOLDEN, case["fasta"])).read())
+        bs = oracle.read_bioseq(os.path.join(GOLDEN, case["bioseq"]))
+        assert [n for n, _ in fa] == [n for n, _ in bs]
+        for (_, a), (_, b) in zip(fa, bs):
+            assert np.array_equal(a, b)
+
+
+def test_bioseq_writer_round_trip(oracle, tmp_path):
+    entries = oracle.read_bioseq(os.path.join(GOLDEN, "adversarial.seq"))
+    p = str(tmp_path / "rt.seq")
+    oracle.write_bioseq(p, entries)
+    back = oracle.read_bioseq(p)
+    assert [n for n, _ in back] == [n for n, _ in entries]
+    for (_, a), (_, b) in zip(entries, back):
+        assert np.array_equal(a, b)
+
+
+def test_oracle_formulations_agree_on_random_inputs(oracle):
+    for seed, lens, K, both in [(1, [700, 300], 10, True), (2, [900], 31, True), (3, [400, 20, 500], 32, False),
+                                (4, [1200], 70, True), (5, [50, 60, 70], 64, True)]:
+        c = random_genome(seed, lens)
+        a = oracle.exhaustive_sliding(c, K, both, threads=2)
+        b = oracle.exhaustive_brute(c, K, both)
+        assert np.array_equal(a, b), (seed, K)
+
+
+def test_oracle_edge_cases(oracle):
+    # every chromosome shorter than K: nothing is lowered
+    c = random_genome(9, [8, 9, 5])
+    assert (oracle.exhaustive_sliding(c, 12, True, threads=1) == 13).all()
+    # a single K-mer: Watson-only has no partner, Crick compares it with its own reverse complement
+    c = np.array([0, 1, 2, 3] * 3, dtype=np.uint8)  # ACGTACGTACGT is its own reverse complement
+    assert oracle.exhaustive_sliding(c, 12, False, threads=1)[0] == 13
+    assert oracle.exhaustive_sliding(c, 12, True, threads=1)[0] == 0
+
+
+def test_sampled_sliding_is_an_upper_bound(oracle):
+    c = random_genome(21, [1500])
+    full = oracle.exhaustive_sliding(c, 25, True, threads=2)
+    part, cells = oracle.exhaustive_sliding_sample(c, 25, True, 2, 1, 4)
+    assert cells > 0 and (part >= full).all()
