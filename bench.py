@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py - K-mer comparisons/s of the `hammings` hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] - `hammings -m1 -K50 -c` all-vs-all over a
+10 Mbp synthetic bacterial-scale multifasta.  A full pass is 2e14 K-mer comparisons (minutes
+on one GPU), so one *step* is one query batch: `--batch` consecutive query K-mers per GPU
+against ALL 10 M target K-mers on both strands.  Work per query is uniform, so batch
+throughput equals whole-job throughput.  With N GPUs every rank takes its own batch (weak
+scaling: per-GPU work fixed) after ONE NCCL broadcast of the packed target set from rank 0.
+
+Printed JSON (one line, rank 0):
+  value     Gcmp/s with inputs resident in HBM (CUDA events around exactly K steps, max over
+            ranks); comparisons = valid queries x valid targets x strands
+  e2e       same metric through the host-buffer C ABI / distributed host API: every step
+            copies the 1-byte/base concat host->device, packs, (broadcasts), compares, and
+            reads the minima back
+  roofline  integer-pipe roofline of the dominant kernel (allpairs_min): achieved = word-compares
+            (32-base XOR/fold/POPC units) per second over the kernel's own CUDA-event time;
+            peak = POPC issue rate measured live by the register-resident microbenchmark
+            (1 POPC per word-compare)
+  cpu_baseline  the reference's own CPU engine (oracle/_ref, unmodified sources) timed on this
+            host on a bounded sample of the same workload
+`--impl reference` times only that CPU engine, with all host threads, on the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (chromosome lengths, K, both strands, seed)   [SURVEY.md 8d table]
+    "cfg1": ([1_000_000], 25, True, 12),
+    "cfg2": ([9_200_000, 400_000, 200_000, 100_000, 100_000], 50, True, 21),
+    "cfg3": ([5_000_000] * 10, 100, True, 31),
+    "cfg5k32": ([5_000_000], 32, True, 51),
+}
+WORKLOAD_DESCR = {
+    "cfg1": "BASELINE configs[0]: hammings -m1 -K25 -c, 1 Mbp synthetic genome",
+    "cfg2": "BASELINE configs[1]: hammings -m1 -K50 -c all-vs-all, 10 Mbp synthetic bacterial-scale multifasta (1x9.2 Mbp + 4 plasmid-like 0.1-0.4 Mbp)",
+    "cfg3": "BASELINE configs[2]: hammings -m1 -K100 -c, 50 Mbp synthetic genome (10 x 5 Mbp)",
+    "cfg5k32": "BASELINE configs[4]: hammings -m1 -K32 -c, 5 Mbp synthetic genome",
+}
+
+
+def synth_genome(name):
+    lens, K, both, seed = WORKLOADS[name]
+    rng = np.random.default_rng(seed)
+    parts, chroms, pos = [], [], 0
+    for i, n in enumerate(lens):
+        parts.append(rng.integers(0, 4, size=n, dtype=np.uint8))
+        chroms.append(("chr%d" % (i + 1), pos, n))
+        pos += n
+        if i + 1 < len(lens):
+            parts.append(np.array([7], dtype=np.uint8))
+            pos += 1
+    return np.ascontiguousarray(np.concatenate(parts)), chroms, K, both
+
+
+def valid_count(chroms, K, b=None, e=None):
+    """number of valid K-mer starts (inside one chromosome) in flat range [b,e)"""
+    tot = 0
+    for _, start, n in chroms:
+        lo, hi = start, start + max(0, n - K + 1)
+        if b is not None:
+            lo, hi = max(lo, b), min(hi, e)
+        tot += max(0, hi - lo)
+    return tot
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi fields of the profiling recipe, via NVML)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.ok:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t:
+            self._stop.set()
+            self._t.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline
+# ------------------------------------------------------------------------------------------
+def cpu_reference_sample(workload, threads=None, target_seconds=15.0, sweeps=None):
+    """Times the reference's own CPU engine on a bounded sample of the workload: the leading
+    sweep offsets of the exhaustive run (-b1 -B<n>), all host threads.  Returns a dict with
+    Gcmp/s computed from the logical comparisons those sweeps cover."""
+    from oracle import hamm_oracle as ho
+    concat, chroms, K, both = synth_genome(workload)
+    L = len(concat)
+    cores = os.cpu_count() or 1
+    T = min(128, threads or cores)  # reference caps worker threads at 128 (libkit4b/commdefs.h:191)
+    N = valid_count(chroms, K)
+    # reference cost: ~(L-s) Watson + ~L Crick cells per sweep offset at ~1.1e8 cells/s/core
+    if sweeps is None:
+        per_sweep_core_s = (2.0 * L if both else 1.0 * L) / 1.1e8
+        sweeps = max(T, int(target_seconds * T / per_sweep_core_s))
+        sweeps = min(sweeps, L - K)
+    ref = ho.ref_binary(nosleep=True)
+
+    def logical_cmps(n):
+        s = np.arange(1, n + 1, dtype=np.float64)
+        w = 2.0 * np.maximum(0.0, N - s).sum()          # each Watson cell serves (i,j) and (j,i)
+        c = float(n) * N if both else 0.0                # each Crick cell serves one ordered pair
+        return w + c
+
+    if ref:
+        with tempfile.TemporaryDirectory() as td:
+            seq = os.path.join(td, "g.seq")
+            entries = [(nm, concat[st:st + n]) for nm, st, n in chroms]
+            ho.write_bioseq(seq, entries, title=workload)
+            args = [ref, "hammings", "-m1", "-K%d" % K, "-T%d" % T, "-b1", "-B%d" % sweeps, "-i", seq]
+            if both:
+                args.insert(3, "-c")
+            t0 = time.perf_counter()
+            p = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+            dt = time.perf_counter() - t0
+            if p.returncode != 0:
+                raise RuntimeError("reference run failed: " + p.stdout.decode("latin-1")[-400:])
+        kind = "reference"
+        how = ("unmodified reference hammings (oracle/_ref, libc sleep() interposed so its fixed 10 s "
+               "main-thread sleep is not billed) -m1 -K%d %s-T%d -b1 -B%d on the same genome: %d of %d "
+               "sweep offsets incl. genome load, per-thread array init and min-merge"
+               % (K, "-c " if both else "", T, sweeps, sweeps, L - K))
+    else:
+        t0 = time.perf_counter()
+        total = (L - K) + (2 * (L - K) + 1 if both else 0)
+        num = sweeps * (3 if both else 1)
+        ho.exhaustive_sliding_sample(concat, K, both, T, num, total)
+        dt = time.perf_counter() - t0
+        kind = "port"
+        how = "oracle C port (sliding diagonals), leading %d of %d diagonals, %d threads" % (num, total, T)
+    cmps = logical_cmps(sweeps)
+    return {"value": cmps / dt / 1e9, "unit": "Gcmp/s", "cores": T, "kind": kind, "sample": how,
+            "seconds": dt, "sweeps": sweeps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_reference_sample(args.workload, target_seconds=args.cpu_seconds)
+        if i >= args.warmup:
+            vals.append((last["value"], last["seconds"]))
+    v = float(np.mean([a for a, _ in vals]))
+    ms = float(np.mean([b for _, b in vals])) * 1e3
+    _, _, K, both = synth_genome(args.workload)
+    line = {
+        "impl": "reference", "metric": "kmer_comparisons_per_sec", "value": v, "unit": "Gcmp/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESCR[args.workload], "K": K, "both_strands": both,
+                   "step": "bounded sample: leading sweep offsets of the exhaustive run, all host threads"},
+        "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": v, "unit": "Gcmp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import kit4b_b200 as k4b
+    from kit4b_b200 import hamm
+    from kit4b_b200.dist import CudaEngine, exhaustive_distributed, shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: kit4b_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    k4b.gpu_init(1, [local])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    concat, chroms, K, both = synth_genome(args.workload)
+    L = len(concat)
+    S = 2 if both else 1
+    W = (K + 31) // 32
+    Nt = valid_count(chroms, K)
+    B = min(args.batch, L)
+    engine = CudaEngine(dev)
+
+    # ---- setup (untimed): rank 0 packs, ONE NCCL broadcast of the packed target set ----
+    if rank == 0:
+        image, packed, non_acgt = engine.pack(concat, K)
+        flag = torch.tensor([int(non_acgt)], dtype=torch.int64, device=dev)
+    else:
+        image = engine.empty_image(L)
+        flag = torch.zeros(1, dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(flag, src=0)
+        dist.broadcast(image, src=0)
+    if rank != 0:
+        packed = engine.adopt(image, L, K, bool(flag.item()))
+    torch.cuda.synchronize()
+
+    lo, hi = shard_bounds(0, L, world)[rank]
+
+    def batch_range(i):
+        span = max(1, hi - lo - B)
+        b = lo + (i * B) % span
+        return b, min(b + B, hi)
+
+    out = torch.empty(B, dtype=torch.int16, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i):
+        b, e = batch_range(i)
+        n = engine.compute(packed, both, b, e, out)
+        return n, valid_count(chroms, K, b, e)
+
+    # ---- device-resident timing: W warm-up, exactly K timed steps ----
+    for i in range(args.warmup):
+        flush.fill_(i & 0xFF)
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches, nq_total, kernel_ms = 0, 0, []
+    ev0.record(stream)
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (inside the bracket: ~0.1 ms)
+        n, nq = step(args.warmup + i)
+        launches += n + 1
+        nq_total += nq
+        kernel_ms.append(hamm.last_kernel_ms())  # CUDA events around the allpairs kernel itself
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    q = torch.tensor([float(nq_total)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(q, op=dist.ReduceOp.SUM)
+    ms_max, nq_all = float(t.item()), float(q.item())
+    cmps = nq_all * Nt * S
+    value = cmps / (ms_max * 1e-3) / 1e9
+
+    # roofline of the dominant kernel on this rank
+    k_ms = float(np.mean(kernel_ms))
+    wc_per_launch = (nq_total / max(1, args.steps)) * Nt * S * W
+    achieved = wc_per_launch / (k_ms * 1e-3) / 1e9
+    peak = hamm.microbench_intpipe(0, 4000)  # measured POPC lanes/s on this GPU
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "allpairs_dram_bytes.json")
+    if os.path.exists(tr_path):
+        try:
+            traffic = json.load(open(tr_path)).get(args.workload)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "int_pipe(popc)", "achieved": achieved, "peak": peak, "unit": "Gwc/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "kernel": "allpairs_min_kernel<W=%d>" % W, "kernel_ms": k_ms,
+                "kernel_share_of_step": k_ms * args.steps / ms if ms > 0 else None,
+                "peak_source": "measured live: register-resident POPC microbenchmark (k4b_microbench_intpipe), "
+                               "1 POPC per 32-base word-compare; nominal 16 lanes/clk/SM x 148 SMs x 1.965 GHz = 4654",
+                "hbm_note": "target planes (%.1f MB) stay L2-resident; HBM is not the bound"
+                            % (hamm.packed_image_bytes(L) / 1e6)}
+
+    # ---- end-to-end through the host-buffer API (H2D concat + pack + compare + D2H) ----
+    e2e_steps = args.e2e_steps if args.e2e_steps is not None else args.steps
+    pinned = torch.from_numpy(concat).pin_memory()
+    h_concat = pinned.numpy()
+    host_out = np.full(L, K + 1, dtype=np.uint16)
+
+    def e2e_step(i):
+        if world == 1:
+            b, e = batch_range(i)
+            hamm.exhaustive_shard(h_concat, K, both, b, e, host_out)
+            return valid_count(chroms, K, b, e), (e - b) * 2
+        # N ranks: global batch of world*B queries starting at a step-dependent offset
+        gb = (i * world * B) % max(1, L - world * B)
+        ge = min(gb + world * B, L)
+        exhaustive_distributed(h_concat if rank == 0 else None, K, both, gb, ge, engine=engine)
+        engine.keep.clear()
+        return valid_count(chroms, K, gb, ge), (ge - gb) * 2
+
+    for i in range(min(args.warmup, 1)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    nq_e2e, d2h = 0, 0
+    for i in range(e2e_steps):
+        nq, nb = e2e_step(1 + i)
+        nq_e2e += nq
+        d2h = nb
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_val = (nq_e2e * Nt * S) / float(tt.item()) / 1e9 if e2e_steps else None
+    e2e = {"value": e2e_val, "unit": "Gcmp/s", "h2d_bytes_per_step": int(L), "d2h_bytes_per_step": int(d2h),
+           "steps": e2e_steps,
+           "api": "k4b_hamm_exhaustive_shard (host buffers)" if world == 1 else
+                  "kit4b_b200.dist.exhaustive_distributed (rank-0 host buffer, NCCL broadcast, gather)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_reference_sample(args.workload, target_seconds=args.cpu_seconds)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": "kmer_comparisons_per_sec", "value": value, "unit": "Gcmp/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESCR[args.workload], "K": K, "both_strands": both,
+                       "genome_bases": int(L), "target_kmers": int(Nt),
+                       "step": "query batch of %d K-mers per GPU vs all targets, both strands" % B,
+                       "global_batch_queries": int(B * world), "parallelism": "query-shard x%d" % world,
+                       "l2": "256 MB flush write between timed steps"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    k4b.gpu_shutdown()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=131072, help="query K-mers per GPU per step")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the reference sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3 if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -104,6 +104,10 @@ int k4b_pack_host(const uint8_t *concat, uint32_t concat_len, uint32_t K, k4b_pa
 /* Packs a DEVICE-resident concat (16-byte aligned; pack + valid-start kernels only). */
 int k4b_pack_device(const void *d_concat, uint32_t concat_len, uint32_t K, void *stream,
                     k4b_packed **out);
+/* Same, writing the image into a caller-owned device buffer of k4b_packed_image_bytes() bytes
+ * (e.g. a buffer that is then broadcast to the other ranks over NCCL). */
+int k4b_pack_device_into(const void *d_concat, uint32_t concat_len, uint32_t K, void *d_image,
+                         size_t image_bytes, void *stream, k4b_packed **out);
 /* device pointer + size of the packed image (planes+valid bits), e.g. for ncclBroadcast */
 void *k4b_packed_image_ptr(k4b_packed *p);
 size_t k4b_packed_image_size(k4b_packed *p);

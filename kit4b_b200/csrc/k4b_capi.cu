@@ -197,24 +197,17 @@ static int check_len(uint64_t len) {
     return 0;
 }
 
-extern "C" int k4b_pack_device(const void *d_concat, uint32_t concat_len, uint32_t K, void *stream,
-                               k4b_packed **out) {
-    if (!out) return fail(K4B_ERR_PARAMS, "out is NULL");
-    *out = nullptr;
-    RC(ensure_init());
-    RC(check_k(K, K4B_MIN_K, K4B_MAX_K));
-    if (!d_concat) return fail(K4B_ERR_PARAMS, "NULL sequence");
-    RC(check_len(concat_len));
-    if (((uintptr_t)d_concat & 15) != 0)
-        return fail(K4B_ERR_PARAMS, "device concat must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
+// pack + valid-start kernels into `image` (caller- or library-owned)
+static int pack_into(const void *d_concat, uint32_t concat_len, uint32_t K, uint32_t *image,
+                     bool owns, cudaStream_t st, k4b_packed **out) {
     k4b_packed *p = new k4b_packed;
     cudaGetDevice(&p->device);
     p->len = concat_len;
     p->K = K;
     p->nw = (concat_len + 31) / 32;
     p->nwp = padded_words(concat_len);
-    p->owns = true;
+    p->owns = owns;
+    p->d_image = image;
     struct Scratch {
         uint32_t flags;
         uint32_t pad;
@@ -222,8 +215,7 @@ extern "C" int k4b_pack_device(const void *d_concat, uint32_t concat_len, uint32
     };
     Scratch *d_s = nullptr;
     Scratch h_s = {0, 0, 0};
-    cudaError_t e = cudaMalloc(&p->d_image, (size_t)p->nwp * 16);
-    if (e == cudaSuccess) e = cudaMalloc(&d_s, sizeof(Scratch));
+    cudaError_t e = cudaMalloc(&d_s, sizeof(Scratch));
     if (e == cudaSuccess) e = cudaMemsetAsync(d_s, 0, sizeof(Scratch), st);
     if (e == cudaSuccess)
         e = launch_pack((const uint8_t *)d_concat, concat_len, p->d_image, p->nwp, &d_s->flags, st);
@@ -240,6 +232,38 @@ extern "C" int k4b_pack_device(const void *d_concat, uint32_t concat_len, uint32
     p->num_kmers = h_s.count;
     *out = p;
     return K4B_OK;
+}
+
+static int pack_args_ok(const void *d_concat, uint32_t concat_len, uint32_t K, k4b_packed **out) {
+    if (!out) return fail(K4B_ERR_PARAMS, "out is NULL");
+    *out = nullptr;
+    RC(ensure_init());
+    RC(check_k(K, K4B_MIN_K, K4B_MAX_K));
+    if (!d_concat) return fail(K4B_ERR_PARAMS, "NULL sequence");
+    RC(check_len(concat_len));
+    if (((uintptr_t)d_concat & 15) != 0)
+        return fail(K4B_ERR_PARAMS, "device concat must be 16-byte aligned");
+    return 0;
+}
+
+extern "C" int k4b_pack_device(const void *d_concat, uint32_t concat_len, uint32_t K, void *stream,
+                               k4b_packed **out) {
+    RC(pack_args_ok(d_concat, concat_len, K, out));
+    uint32_t *image = nullptr;
+    cudaError_t e = cudaMalloc(&image, k4b_packed_image_bytes(concat_len));
+    if (e != cudaSuccess)
+        return fail(cuda_code(e), "cudaMalloc packed image: %s", cudaGetErrorString(e));
+    return pack_into(d_concat, concat_len, K, image, true, (cudaStream_t)stream, out);
+}
+
+extern "C" int k4b_pack_device_into(const void *d_concat, uint32_t concat_len, uint32_t K,
+                                    void *d_image, size_t image_bytes, void *stream,
+                                    k4b_packed **out) {
+    RC(pack_args_ok(d_concat, concat_len, K, out));
+    if (!d_image || image_bytes != k4b_packed_image_bytes(concat_len) || ((uintptr_t)d_image & 15))
+        return fail(K4B_ERR_PARAMS, "image buffer must be 16-byte aligned and %zu bytes",
+                    k4b_packed_image_bytes(concat_len));
+    return pack_into(d_concat, concat_len, K, (uint32_t *)d_image, false, (cudaStream_t)stream, out);
 }
 
 extern "C" int k4b_pack_host(const uint8_t *concat, uint32_t concat_len, uint32_t K,

@@ -1,0 +1,110 @@
+"""One-process-per-GPU sharding of the exhaustive engine (torchrun / torch.distributed).
+
+Mirrors the reference's only parallel axis - independent workers with private result arrays
+that are merged at the end (ngskit4b/hammings.cpp:2752-2766 thread blocks, :2855-2867 merge;
+-m2/-m3 node slices :2660-2689, :1126-1343) - but shards QUERY K-mers instead of sweep offsets,
+so no merge is needed: rank r owns the queries whose flat start position lies in its slice and
+compares them with every target.  The only collective on the data path is ONE broadcast of
+the bit-plane packed target set from rank 0 (NCCL over NVLink on GPUs); per-rank minima are
+gathered to rank 0 and concatenated on the host.
+
+torch is plumbing here (device buffers, streams, process group); the arithmetic is the CUDA
+engine behind the C ABI (kit4b_b200.hamm).  `engine` is pluggable so that the host-side
+shard/broadcast/gather logic can be exercised with the gloo backend on CPU in the tests.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import hamm
+
+
+def shard_bounds(q_begin: int, q_end: int, world: int) -> List[Tuple[int, int]]:
+    """Even split of [q_begin, q_end) by position (same formula as run_sharded in k4b_capi.cu)."""
+    span = max(0, q_end - q_begin)
+    return [(q_begin + span * r // world, q_begin + span * (r + 1) // world) for r in range(world)]
+
+
+class CudaEngine:
+    """Device side of one rank: pack (rank 0), adopt a broadcast image (others), run a shard."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.keep = []  # tensors that must outlive the handles built on them
+
+    def empty_image(self, length: int) -> torch.Tensor:
+        return torch.empty(hamm.packed_image_bytes(length), dtype=torch.uint8, device=self.device)
+
+    def pack(self, concat: np.ndarray, K: int):
+        """rank 0: H2D of the 1-byte/base concat + pack kernels into a torch-owned image."""
+        host = torch.from_numpy(np.ascontiguousarray(concat, dtype=np.uint8))
+        d_concat = host.to(self.device, non_blocking=False)
+        image = self.empty_image(len(concat))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        packed = hamm.Packed.from_device_into(d_concat.data_ptr(), len(concat), K, image.data_ptr(),
+                                              image.numel(), stream)
+        self.keep.append(image)
+        return image, packed, bool(packed.has_non_acgt)
+
+    def adopt(self, image: torch.Tensor, length: int, K: int, has_non_acgt: bool):
+        self.keep.append(image)
+        return hamm.Packed.from_image(image.data_ptr(), image.numel(), length, K, has_non_acgt)
+
+    def compute(self, packed, both: bool, b: int, e: int, out: torch.Tensor) -> int:
+        """Enqueues the shard [b,e) on the current stream; out: int16[e-b] on the device."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        return hamm.allpairs_min_device(packed, packed, both, True, b, e, out.data_ptr(), 0, stream)
+
+
+def exhaustive_distributed(concat: Optional[np.ndarray], K: int, both: bool, q_begin: int = 0,
+                           q_end: Optional[int] = None, engine=None, group=None) -> Optional[np.ndarray]:
+    """All-vs-all minima with queries sharded over the ranks of `group`.
+
+    rank 0 passes the concat (others pass None) and gets uint16[len(concat)] laid out like the
+    reference's m_pHamDist (K+1 where nothing was computed); other ranks get None."""
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    if engine is None:
+        engine = CudaEngine(torch.device("cuda", torch.cuda.current_device()))
+    dev = engine.device
+
+    # --- metadata, then ONE broadcast of the packed target set ---
+    meta = torch.zeros(4, dtype=torch.int64, device=dev)
+    packed = None
+    image = None
+    if rank == 0:
+        image, packed, non_acgt = engine.pack(concat, K)
+        qe = len(concat) if q_end is None else min(q_end, len(concat))
+        meta = torch.tensor([len(concat), int(non_acgt), q_begin, qe], dtype=torch.int64, device=dev)
+    dist.broadcast(meta, src=0, group=group)
+    length, non_acgt, qb, qe = (int(v) for v in meta.tolist())
+    if rank != 0:
+        image = engine.empty_image(length)
+    dist.broadcast(image, src=0, group=group)
+    if rank != 0:
+        packed = engine.adopt(image, length, K, bool(non_acgt))
+
+    # --- every rank: its own query slice against all targets, no further exchange ---
+    bounds = shard_bounds(qb, qe, world)
+    b, e = bounds[rank]
+    width = max(2, max(hi - lo for lo, hi in bounds))
+    width += width & 1  # even, so the int16 minima travel as int32 words (gloo has no int16)
+    out = torch.full((width,), K + 1, dtype=torch.int16, device=dev)
+    if e > b:
+        engine.compute(packed, both, b, e, out)
+
+    # --- gather per-rank minima on rank 0 and concatenate on the host ---
+    wire = out.view(torch.int32)
+    parts = [torch.empty_like(wire) for _ in range(world)] if rank == 0 else None
+    dist.gather(wire, parts, dst=0, group=group)
+    if rank != 0:
+        return None
+    result = np.full(length, K + 1, dtype=np.uint16)
+    for (lo, hi), t in zip(bounds, parts):
+        if hi > lo:
+            result[lo:hi] = t.cpu().numpy().view(np.uint16)[: hi - lo]
+    return result

@@ -48,6 +48,8 @@ SIGNATURES = {
     "k4b_packed_image_bytes": (ctypes.c_size_t, [ctypes.c_uint32]),
     "k4b_pack_host": (ctypes.c_int, [_u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(_vp)]),
     "k4b_pack_device": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, _vp, ctypes.POINTER(_vp)]),
+    "k4b_pack_device_into": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, _vp, ctypes.c_size_t, _vp,
+                                            ctypes.POINTER(_vp)]),
     "k4b_packed_image_ptr": (_vp, [_vp]),
     "k4b_packed_image_size": (ctypes.c_size_t, [_vp]),
     "k4b_packed_from_image": (ctypes.c_int, [_vp, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int,
@@ -157,6 +159,14 @@ class Packed:
         return cls(h, length, K)
 
     @classmethod
+    def from_device_into(cls, d_ptr: int, length: int, K: int, d_image_ptr: int, image_bytes: int,
+                         stream: int = 0) -> "Packed":
+        h = _vp()
+        _check(load_lib().k4b_pack_device_into(_vp(d_ptr), length, K, _vp(d_image_ptr), image_bytes, _vp(stream),
+                                               ctypes.byref(h)))
+        return cls(h, length, K)
+
+    @classmethod
     def from_image(cls, d_image_ptr: int, image_bytes: int, length: int, K: int, has_non_acgt: bool) -> "Packed":
         h = _vp()
         _check(load_lib().k4b_packed_from_image(_vp(d_image_ptr), image_bytes, length, K, int(has_non_acgt),
@@ -198,6 +208,10 @@ def allpairs_min_device(queries: Packed, targets: Packed, both_strands: bool, se
     _check(load_lib().k4b_allpairs_min_device(queries.handle, targets.handle, int(both_strands), int(self_exclude),
                                               q_begin, q_end, clamp, _vp(d_out_ptr), _vp(stream), ctypes.byref(n)))
     return n.value
+
+
+def packed_image_bytes(length: int) -> int:
+    return int(load_lib().k4b_packed_image_bytes(length))
 
 
 def last_kernel_ms() -> float:

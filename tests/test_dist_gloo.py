@@ -1,0 +1,85 @@
+"""CPU test of the N>1 host logic (kit4b_b200/dist.py): world_size-2 gloo run of the
+broadcast -> per-rank query shard -> gather/concatenate flow.  The CUDA engine is replaced by a
+stand-in that answers each shard with the oracle, so what is verified here is the sharding,
+the collective plumbing and the concatenation - the kernels have their own -m gpu tests."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, random_genome
+
+
+class OracleEngine:
+    """Stand-in for kit4b_b200.dist.CudaEngine on CPU (test infrastructure)."""
+
+    def __init__(self):
+        self.device = torch.device("cpu")
+        self.K = None
+
+    def empty_image(self, length):
+        return torch.empty(length, dtype=torch.uint8)
+
+    def pack(self, concat, K):
+        self.K = K
+        img = torch.from_numpy(np.ascontiguousarray(concat).copy())
+        return img, img.numpy(), bool((concat[(concat != 7)] > 3).any())
+
+    def adopt(self, image, length, K, has_non_acgt):
+        self.K = K
+        return image.numpy()
+
+    def compute(self, packed, both, b, e, out):
+        from oracle import hamm_oracle as ho
+        hd = ho.exhaustive_brute(packed, self.K, both, b, e)
+        out[: e - b] = torch.from_numpy(hd[b:e].view(np.int16).copy())
+        return 1
+
+
+def _worker(rank, world, port, K, both, qb, qe, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from kit4b_b200.dist import exhaustive_distributed
+    concat = random_genome(77, [900, 41, 700]) if rank == 0 else None
+    res = exhaustive_distributed(concat, K, both, qb, qe, engine=OracleEngine())
+    if rank == 0:
+        ret["res"] = res
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("K,both,qb,qe", [(25, True, 0, None), (40, False, 100, 1500)])
+def test_two_rank_shards_equal_single_process(oracle, K, both, qb, qe):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), K, both, qb, qe, ret), nprocs=2, join=True)
+    concat = random_genome(77, [900, 41, 700])
+    want = oracle.exhaustive_brute(concat, K, both, qb, len(concat) if qe is None else qe)
+    assert np.array_equal(ret["res"], want)
+
+
+def test_shard_bounds_partition():
+    from kit4b_b200.dist import shard_bounds
+    for qb, qe, w in [(0, 10, 3), (5, 5, 2), (0, 1_000_003, 8), (7, 9, 4)]:
+        b = shard_bounds(qb, qe, w)
+        assert b[0][0] == qb and b[-1][1] == qe
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        sizes = [hi - lo for lo, hi in b]
+        assert max(sizes) - min(sizes) <= 1
