@@ -86,7 +86,8 @@ int k4b_hamm_exhaustive_shard(const uint8_t *concat, uint32_t concat_len, uint32
  *                             (SfxArray.cpp:1746-1750)
  *   probe_concat/probe_len    probes in the LoadGenome layout (hammings.cpp:2201-2310)
  *   K 10..500, R 1..10; result per probe K-mer start = min(true both-strand minimum,
- *   K/(K/(R+1))) i.e. the reference's "not found" value (SfxArray.cpp:4462-4463)
+ *   K/(K/(R+1))) i.e. the reference's "not found" value (SfxArray.cpp:4462-4463); probe
+ *   symbols >= N are wildcards against target ACGT, > 4 of them report 0 (:4266-4326)
  *   out_h  probe_len entries PRE-FILLED 0xFF; written at valid probe K-mer starts */
 int k4b_hamm_targeted(const uint8_t *target_concat, uint64_t target_len,
                       const uint8_t *probe_concat, uint32_t probe_len, uint32_t K, int R,
@@ -123,7 +124,9 @@ void k4b_packed_free(k4b_packed *p);
  * (query position == target position) on the forward strand (Watson offsets start at 1,
  * hammings.cpp:2692; the reverse-complement self pair is kept, :3300-3489).
  * d_out_min: DEVICE uint16[q_end-q_begin]; positions that are not valid K-mer starts get
- * K+1.  clamp>0 caps results at clamp (targeted mode).  Asynchronous on `stream`.
+ * K+1.  clamp>0 selects the targeted (-m0) rules: results are capped at clamp, query symbols
+ * >= N act as wildcards and a K-mer with more than 4 of them reports 0
+ * (SfxArray.cpp:4266-4326).  Asynchronous on `stream`.
  * *launches (nullable) receives the number of kernels enqueued. */
 int k4b_allpairs_min_device(k4b_packed *queries, k4b_packed *targets, int both_strands,
                             int self_exclude, uint32_t q_begin, uint32_t q_end, uint32_t clamp,

@@ -1,0 +1,381 @@
+// k4b_hammings_main.cpp - `k4b_hammings [hammings] <flags>`: drop-in for `ngskit4b hammings`.
+// Same flags, defaults, validation order, input files, output bytes and exit codes as
+// ngskit4b/hammings.cpp:169-680 (CLI) and :2598-2966 / :2121-2595 (Process); the engines
+// behind it are the CUDA kernels reached through include/k4b_hamm.h.
+#include <fcntl.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+
+#include "../../../include/k4b_hamm.h"
+#include "k4b_host.h"
+
+using namespace k4bhost;
+
+static const char *kProg = "k4b_hammings";
+static const char *kVersion = "0.1.0 (B200 engine; kit4b 2.0.2 hammings interface)";
+static FILE *g_logf = nullptr;
+static int g_screen_level = 3, g_file_level = 0;
+
+static void logmsg(int level, const char *fmt, ...) {
+    // level: 0 fatal, 1 errors/warnings, 2/3 info (Diagnostics.h:5-54); same text to screen and log
+    char msg[2048];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(msg, sizeof(msg), fmt, ap);
+    va_end(ap);
+    struct timeval tv;
+    gettimeofday(&tv, nullptr);
+    struct tm tmv;
+    localtime_r(&tv.tv_sec, &tmv);
+    char ts[64];
+    strftime(ts, sizeof(ts), "%b %d %H:%M:%S", &tmv);
+    if (level <= g_screen_level) {
+        printf("[%s.%06ld %d](%s) %s\n", ts, (long)tv.tv_usec, 1900 + tmv.tm_year, kProg, msg);
+        fflush(stdout);
+    }
+    if (g_logf && level <= g_file_level) {
+        fprintf(g_logf, "[%s.%06ld %d](%s) %s\n", ts, (long)tv.tv_usec, 1900 + tmv.tm_year, kProg, msg);
+        fflush(g_logf);
+    }
+}
+
+static int touch_output(const std::string &path) {
+    // create + truncate + close up front so an unwritable path fails before the long run
+    // (hammings.cpp:2714-2737)
+    const int fd = open(path.c_str(), O_RDWR | O_CREAT, S_IRUSR | S_IWUSR);
+    if (fd < 0 || ftruncate(fd, 0) != 0) {
+        if (fd >= 0) close(fd);
+        logmsg(0, "Process: unable to create/truncate output file '%s'", path.c_str());
+        return kErrCreateFile;
+    }
+    close(fd);
+    return kOk;
+}
+
+// ---- exhaustive (-m1) ------------------------------------------------------------------------
+static int run_exhaustive(const Options &o) {
+    std::vector<SeqEntry> entries;
+    std::string title, err;
+    int rc = read_bioseq(o.in_file, entries, title, err);
+    if (rc) {
+        logmsg(0, "%s", err.c_str());
+        logmsg(0, "Unable to open assembly sequence file '%s'", o.in_file.c_str());
+        return rc;
+    }
+    const uint32_t K = (uint32_t)o.K;
+    Genome g;
+    build_genome(entries, K, g);
+    entries.clear();
+    entries.shrink_to_fit();
+    logmsg(2, "Genome containing %llu total nucleotides loaded with %llu subsequences of length %u...",
+           (unsigned long long)g.total_bases, (unsigned long long)g.num_subseqs, K);
+
+    // single node: silently clamp the sweep range to the genome length (hammings.cpp:2690-2706)
+    uint32_t ss = (uint32_t)o.sweep_start > g.genome_len ? g.genome_len : (uint32_t)o.sweep_start;
+    uint32_t se = o.sweep_end == 0 ? g.genome_len : std::min((uint32_t)o.sweep_end, g.genome_len);
+    logmsg(2, "Node sweep start is %u, and sweep end is %u", ss, se);
+
+    if (!o.out_file.empty() && (rc = touch_output(o.out_file))) return rc;
+
+    const uint32_t flat = g.genome_len - 2;
+    std::vector<uint16_t> hd(flat, (uint16_t)(K + 1));
+    logmsg(2, "Starting Hamming edit distance processing on %d GPU(s)", k4b_gpu_count());
+    const auto t0 = std::chrono::steady_clock::now();
+    rc = k4b_hamm_exhaustive(g.concat.data(), flat, K, o.crick ? 1 : 0, ss, se, hd.data());
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (rc) {
+        logmsg(0, "Hamming engine failed (%d): %s", rc, k4b_last_error());
+        return rc;
+    }
+    const double cmps = (double)g.num_subseqs * (double)g.num_subseqs * (o.crick ? 2.0 : 1.0);
+    logmsg(2, "Engine: %.3f s, %.1f G K-mer comparisons/s", secs, cmps / secs / 1e9);
+
+    if (!o.out_file.empty()) {
+        logmsg(2, "Writing Hamming edit distances to file: '%s'", o.out_file.c_str());
+        rc = write_exhaustive_csv(o.out_file, g, K, hd.data(), ss, se, err);
+        if (rc) {
+            logmsg(0, "%s", err.c_str());
+            return rc;
+        }
+    }
+    // distribution to the log (hammings.cpp:2939-2962)
+    std::vector<uint64_t> hist(K + 2, 0);
+    for (const Chrom &c : g.chroms)
+        for (uint32_t i = 0; i < c.num_subseqs; ++i) hist[std::min<uint32_t>(hd[c.start + i], K + 1)]++;
+    logmsg(2, "Distribution:\nEditDist,Freq,Proportion");
+    for (uint32_t d = 0; d < std::min(66u, K); ++d)
+        printf("%u,%llu,%1.3f\n", d, (unsigned long long)hist[d],
+               g.num_subseqs ? hist[d] * 100.0 / (double)g.num_subseqs : 0.0);
+    return kOk;
+}
+
+// ---- restricted / targeted (-m0) ------------------------------------------------------------------
+static int run_restricted(const Options &o) {
+    std::string err, title;
+    SfxData sfx;
+    logmsg(2, "Loading suffix array file '%s'", o.in_file.c_str());
+    int rc = read_sfx(o.in_file, sfx, err);
+    if (rc) {
+        logmsg(0, "%s", err.c_str());
+        logmsg(0, "Unable to open input bioseq suffix array file '%s'", o.in_file.c_str());
+        return rc;
+    }
+    logmsg(2, "Genome Assembly Name: '%s' Descr: '%s' Title: '%s' Version: %d", sfx.dataset.c_str(),
+           sfx.descr.c_str(), sfx.title.c_str(), sfx.version);
+    const uint32_t K = (uint32_t)o.K;
+    if (o.in_seq_file.empty()) {
+        logmsg(0, "Restricted Hammings for K-mers drawn from the indexed assembly itself (no -I) are not "
+                  "supported by this build; supply the source K-mer sequences with -I <bioseq>");
+        return kErrParams;
+    }
+    std::vector<SeqEntry> entries;
+    rc = read_bioseq(o.in_seq_file, entries, title, err);
+    if (rc) {
+        logmsg(0, "%s", err.c_str());
+        logmsg(0, "Unable to open assembly sequence file '%s'", o.in_seq_file.c_str());
+        return rc;
+    }
+    Genome g;
+    build_genome(entries, K, g);
+    entries.clear();
+    logmsg(2, "Genome containing %llu total nucleotides loaded with %llu subsequences of K-mer length %u...",
+           (unsigned long long)g.total_bases, (unsigned long long)g.num_subseqs, K);
+
+    const uint32_t plen = (uint32_t)g.concat.size();
+    std::vector<uint8_t> flat(plen, 0xff);
+    const auto t0 = std::chrono::steady_clock::now();
+    rc = k4b_hamm_targeted(sfx.seq.data(), sfx.seq.size(), g.concat.data(), plen, K, o.rhamm, o.crick ? 1 : 0, 0,
+                           plen, flat.data());
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (rc) {
+        logmsg(0, "Hamming engine failed (%d): %s", rc, k4b_last_error());
+        return rc;
+    }
+    logmsg(2, "Engine: %.3f s for %llu probe K-mers vs %zu target bases", secs,
+           (unsigned long long)g.num_subseqs, sfx.seq.size());
+
+    // per-loci array H[sum of entry lengths] preset 0xFF (hammings.cpp:2336-2354); loci that the
+    // reference's chunk scheduler would not sample stay 0xFF (hammings.cpp:1615-1674 with
+    // SfxArray.cpp:4262: every SampleN-th K-mer of each chunk, chunks restart the stride)
+    std::vector<uint8_t> h((size_t)g.total_bases, 0xff);
+    std::vector<RChrom> rch;
+    const uint64_t max_chunk = std::max<uint64_t>(10000, g.total_bases / 10000);
+    uint64_t hofs = 0;
+    for (const Chrom &c : g.chroms) {
+        rch.push_back(RChrom{c.name, c.len});
+        if (c.len >= K) {
+            uint64_t seq_ofs = 0;
+            while (seq_ofs + K <= c.len) {
+                const uint64_t chunk_len = std::min<uint64_t>(max_chunk, c.len - seq_ofs);
+                if (chunk_len < K) break;
+                for (uint64_t ofs = 0; ofs + K <= chunk_len; ofs += (uint64_t)o.sample)
+                    h[hofs + seq_ofs + ofs] = flat[c.start + seq_ofs + ofs];
+                seq_ofs += 1 + chunk_len - K;
+            }
+        }
+        hofs += c.len;
+    }
+    if (!o.out_file.empty()) {
+        logmsg(2, "Writing Hamming edit distances to file: '%s'", o.out_file.c_str());
+        switch (o.resformat) {
+            case 0: rc = write_restricted_csv(o.out_file, rch, K, h.data(), o.prefix, err); break;
+            case 1: rc = write_restricted_bed(o.out_file, rch, K, o.rhamm, h.data(), o.prefix, err); break;
+            default:
+                rc = write_restricted_wiggle(o.out_file, rch, K, o.rhamm, o.sensitivity, h.data(), o.prefix, err);
+                break;
+        }
+        if (rc) {
+            logmsg(0, "%s", err.c_str());
+            return rc;
+        }
+    }
+    // distribution 0..R+1 to the log (hammings.cpp:2535-2587)
+    uint64_t hist[256] = {0}, sampled = 0, unsampled = 0;
+    hofs = 0;
+    for (const Chrom &c : g.chroms) {
+        if (c.len >= K)
+            for (uint32_t i = 0; i + K <= c.len; ++i) {
+                const uint8_t v = h[hofs + i];
+                if (v < 0x7f) {
+                    hist[v]++;
+                    sampled++;
+                } else {
+                    unsampled++;
+                }
+            }
+        hofs += c.len;
+    }
+    if (o.sample > 1) logmsg(2, "Sampled %llu K-mers, did not sample %llu", (unsigned long long)sampled, (unsigned long long)unsampled);
+    logmsg(2, "Distribution:\nEditDist,Freq,Proportion");
+    for (int d = 0; d <= o.rhamm + 1; ++d)
+        printf("%d%c,%llu,%1.3f\n", d, d == o.rhamm + 1 ? '+' : ' ', (unsigned long long)hist[d],
+               sampled ? hist[d] * 100.0 / (double)sampled : 0.0);
+    return kOk;
+}
+
+int main(int argc, char **argv) {
+    // `ngskit4b hammings ...` style invocation: the subprocess word may lead (ngskit4b.cpp:295-312)
+    std::vector<char *> av(argv, argv + argc);
+    if (argc > 1 && (!strcmp(argv[1], "hammings") || !strcmp(argv[1], "-phammings"))) av.erase(av.begin() + 1);
+    std::vector<std::string> expanded;
+    std::string err;
+    if (expand_param_files((int)av.size(), av.data(), expanded, err) < 0) {
+        printf("%s\n", err.c_str());
+        printf("\n%s K-mer Hamming distance generator, Version %s\n", kProg, kVersion);
+        print_usage(kProg);
+        return 1;
+    }
+    std::vector<char *> pv;
+    for (std::string &s : expanded) pv.push_back(&s[0]);
+    pv.push_back(nullptr);
+    Options o;
+    const int perr = parse_args((int)expanded.size(), pv.data(), o, err);
+    if (o.help) {  // --help takes precedence over error reporting, and exits 1 (hammings.cpp:255-265)
+        printf("\n%s hammings - K-mer Hamming distance generator, Version %s\nOptions ---\n", kProg, kVersion);
+        print_usage(kProg);
+        printf("\nNote: Parameters can be entered into a parameter file, one parameter per line.");
+        printf("\n      To invoke this parameter file then precede its name with '@'");
+        printf("\n      e.g. %s @myparams.txt\n\n", kProg);
+        return 1;
+    }
+    if (o.version) {
+        printf("\n%s Version %s\n", kProg, kVersion);
+        return 1;
+    }
+    if (perr) {
+        printf("\n%s K-mer Hamming distance generator, Version %s\n", kProg, kVersion);
+        printf("%s: %s\n", kProg, err.c_str());
+        print_usage(kProg);
+        printf("\nUse '-h' to view option and parameter usage\n");
+        return 1;
+    }
+    // ---- validation, in the reference's order (hammings.cpp:274-520) ----
+    if (o.file_log_level < 0 || o.file_log_level > 4) {
+        printf("\nError: FileLogLevel '-l%d' specified outside of range %d..%d\n", o.file_log_level, 0, 4);
+        return 1;
+    }
+    g_screen_level = o.file_log_level;
+    if (!o.log_file.empty()) {
+        g_file_level = o.file_log_level;
+        g_logf = fopen(o.log_file.c_str(), "a");
+        if (!g_logf) {
+            printf("\nError: Unable to start diagnostics subsystem\n Most likely cause is that logfile '%s' can't be opened/created\n",
+                   o.log_file.c_str());
+            return 1;
+        }
+    }
+    logmsg(2, "Version: %s", kVersion);
+    if (o.mode < 0 || o.mode > 5) {
+        logmsg(0, "Error: Processing mode '-m%d' specified outside of range %d..%d", o.mode, 0, 5);
+        return 1;
+    }
+    if (o.mode <= 2 && (o.K < (int)K4B_MIN_K || o.K > (int)K4B_MAX_K)) {
+        logmsg(0, "Error: k-mer sequence length '-K%d' specified outside of range %d..%d", o.K, K4B_MIN_K, K4B_MAX_K);
+        return 1;
+    }
+    if (o.mode == 0) {
+        if (o.prefix.size() > 10) {
+            logmsg(0, "Prefix \"%s\" length must <= %d chars", o.prefix.c_str(), 10);
+            return 1;
+        }
+        for (char ch : o.prefix)
+            if (!isalnum((unsigned char)ch)) {
+                logmsg(0, "Prefix \"%s\" may only contain alpha-numeric chars", o.prefix.c_str());
+                return 1;
+            }
+        if (o.sensitivity < 0 || o.sensitivity > 3) {
+            logmsg(0, "Error: Restricted hamming sensitivity '-s%d' specified outside of range %d..%d", o.sensitivity, 0, 3);
+            return 1;
+        }
+        if (o.rhamm < 1 || o.rhamm > 10) {
+            logmsg(0, "Error: Restricted Hamming limit '-r%d' specified outside of range %d..%d", o.rhamm, 1, 10);
+            return 1;
+        }
+        if (o.resformat < 0 || o.resformat > 2) {
+            logmsg(0, "Error: Restricted Hamming output file format '-S%d' specified outside of range %d..%d", o.resformat, 0, 2);
+            return 1;
+        }
+        if (o.K / (o.rhamm + 1) < 4) {
+            logmsg(0, "Error: Restricted hamming limit '-r%d' is incompatible with k-mer sequence length '-k%d'", o.rhamm, o.K);
+            return 1;
+        }
+        if (o.sample < 1 || o.sample > 100) {
+            logmsg(0, "Error: Sampling '-S%d' specified outside of range 1..%d", o.sample, 100);
+            return 1;
+        }
+        if (o.intrainterboth < 0 || o.intrainterboth > 2) {
+            logmsg(0, "Error: Hamming processing Intra/Inter/Both '-z%d' specified outside of range 0..2", o.intrainterboth);
+            return 1;
+        }
+        if (o.K > 500) {  // CSfxArray::LocateHammings rejects longer K-mers (SfxArray.cpp:4255)
+            logmsg(0, "Error: restricted Hammings support K-mers of at most 500 bases");
+            return 1;
+        }
+    }
+    if (o.mode == 1 || o.mode == 2) {
+        if (o.mode == 1) {
+            if (o.sweep_start < 0) {
+                logmsg(0, "Error: Sweep start '-b%d' must be >= 1", o.sweep_start);
+                return 1;
+            }
+            if (o.sweep_start == 0) o.sweep_start = 1;
+            if (o.sweep_end != 0 && o.sweep_end < o.sweep_start) {
+                logmsg(0, "Error: Sweep end '-B%d' must be either 0 or >= %d", o.sweep_end, o.sweep_start);
+                return 1;
+            }
+        } else {
+            if (o.numnodes < 2 || o.numnodes > 10000 || o.node < 1) {
+                logmsg(0, "Error: In distributed processing mode both number of nodes '-n<num>' (2..10000) and node instance "
+                          "'-N<node>' must be specified");
+                return 1;
+            }
+        }
+        if (o.sample < 1 || o.sample > 10000000) {
+            logmsg(0, "Error: Sampling '-S%d' specified outside of range 1..10000000", o.sample);
+            return 1;
+        }
+    }
+    std::string out_file = o.out_file;
+    if (o.sample > 1 && !o.out_file.empty()) {  // every mode: hammings.cpp:508-509
+        logmsg(1, "Warning: When sampling no output to file is supported");
+        out_file.clear();
+    }
+    Options run = o;
+    run.out_file = out_file;
+
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = 0;
+    if (run.mode == 3) {
+        rc = merge_hamming_csv(run.in_file, run.out_file, err);
+        if (rc) logmsg(0, "Merge failed: %s", err.c_str());
+    } else if (run.mode == 4 || run.mode == 5) {
+        logmsg(0, "Error: the quick-load binary transforms (-m4/-m5) are not part of this build");
+        rc = kErrParams;
+    } else if (run.mode == 2 || (run.mode == 1 && run.sample > 1)) {
+        logmsg(0, "Error: multi-node sweep slices (-m2) and sweep sampling (-k) are not part of this build; "
+                  "use -m1 with --gpus to shard one run over the GPUs of this box");
+        rc = kErrParams;
+    } else {
+        rc = k4b_gpu_init(run.gpus, nullptr);
+        if (rc) {
+            logmsg(0, "Unable to initialise the GPU engine (%d): %s", rc, k4b_last_error());
+        } else {
+            rc = run.mode == 1 ? run_exhaustive(run) : run_restricted(run);
+            k4b_gpu_shutdown();
+        }
+    }
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const int code = rc >= 0 ? 0 : 1;
+    logmsg(2, "Exit code: %d Total processing time: %.3f seconds", code, secs);
+    if (g_logf) fclose(g_logf);
+    return code;
+}

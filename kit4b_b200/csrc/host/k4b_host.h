@@ -1,0 +1,120 @@
+// k4b_host.h - host side of the `hammings` drop-in: input containers, the concatenated
+// genome layout, report writers and the CLI.  Everything here mirrors behaviour of the
+// reference's ngskit4b/hammings.cpp + libkit4b readers for this one subprocess; the numeric
+// work is behind the C ABI in include/k4b_hamm.h.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace k4bhost {
+
+// result codes follow libkit4b/ErrorCodes.h:15-33
+enum : int {
+    kOk = 0,
+    kErrParams = -100,
+    kErrMem = -95,
+    kErrNotBioseq = -94,
+    kErrFileType = -92,
+    kErrOpnFile = -90,
+    kErrCreateFile = -89,
+    kErrFileVer = -86,
+    kErrFileAccess = -85,
+    kErrParse = -46,
+};
+
+struct SeqEntry {
+    std::string name;            // <= 80 chars (commdefs.h:140)
+    std::vector<uint8_t> codes;  // one base code per byte, soft-mask flag (0x08) still present
+};
+
+// ---- containers -------------------------------------------------------------------------
+// 'bios' container, type 1 / version 10 (libkit4b/BioSeqFile.h:28-58, BioSeqFile.cpp:378-470,
+// :928-1045, :1174-1220); entries come back in EntryID order (= FASTA order)
+int read_bioseq(const std::string &path, std::vector<SeqEntry> &entries, std::string &title,
+                std::string &err);
+// minimal writer of the same container (used by the FASTA front end and by tests)
+int write_bioseq(const std::string &path, const std::vector<SeqEntry> &entries,
+                 const std::string &title, std::string &err);
+// FASTA text -> entries (libkit4b/Fasta.cpp:1658-1705 Ascii2Sense, :1167; genbioseq.cpp:402-404)
+int read_fasta(const std::string &path, std::vector<SeqEntry> &entries, std::string &err);
+
+// 'sfx5' suffix-array container: only the entries and the concatenated sequence are read
+// (libkit4b/SfxArray.h:98-123, :194-207; SfxArray.cpp:499-580, :629-825)
+struct SfxEntry {
+    std::string name;
+    uint32_t len = 0;
+    uint64_t start = 0;  // offset into the concatenated sequence
+};
+struct SfxData {
+    std::string dataset, descr, title;
+    int version = 0;
+    std::vector<SfxEntry> entries;
+    std::vector<uint8_t> seq;  // ConcatSeqLen bytes: each entry's bases followed by EOS (7)
+};
+int read_sfx(const std::string &path, SfxData &out, std::string &err);
+
+// ---- concatenated layout (hammings.cpp:2981-3134 LoadGenome) -------------------------------
+struct Chrom {
+    std::string name;
+    uint32_t len = 0;
+    uint32_t start = 0;       // offset into concat (== SeqOfs-1 of the reference)
+    uint32_t num_subseqs = 0;  // max(0, len-K+1)
+};
+struct Genome {
+    std::vector<uint8_t> concat;  // chr1 EOS chr2 EOS ... chrN (no EOG sentinels), mask stripped
+    std::vector<Chrom> chroms;
+    uint32_t genome_len = 0;      // the reference's m_GenomeLen == concat.size()+2
+    uint64_t total_bases = 0;
+    uint64_t num_subseqs = 0;
+};
+void build_genome(const std::vector<SeqEntry> &entries, uint32_t K, Genome &g);
+
+// ---- writers ---------------------------------------------------------------------------------
+// exhaustive CSV, literal restatement of hammings.cpp:2899-2929 (quirks included)
+int write_exhaustive_csv(const std::string &path, const Genome &g, uint32_t K, const uint16_t *hd,
+                         uint32_t sweep_start, uint32_t sweep_end, std::string &err);
+// restricted reports over the per-loci array H[sum of entry lengths] (hammings.cpp:1711-2118)
+struct RChrom {
+    std::string name;
+    uint32_t len = 0;
+};
+int write_restricted_csv(const std::string &path, const std::vector<RChrom> &chroms, uint32_t K,
+                         const uint8_t *h, const std::string &prefix, std::string &err);
+int write_restricted_bed(const std::string &path, const std::vector<RChrom> &chroms, uint32_t K, int R,
+                         const uint8_t *h, const std::string &prefix, std::string &err);
+int write_restricted_wiggle(const std::string &path, const std::vector<RChrom> &chroms, uint32_t K,
+                            int R, int sensitivity, const uint8_t *h, const std::string &prefix,
+                            std::string &err);
+// -m3: line-wise minimum of two exhaustive CSVs (hammings.cpp:1126-1343)
+int merge_hamming_csv(const std::string &from, const std::string &into, std::string &err);
+
+// ---- CLI ----------------------------------------------------------------------------------------
+struct Options {
+    int mode = 0;            // -m (default 0 = restricted, hammings.cpp:312)
+    int sensitivity = 0;     // -s
+    int resformat = 0;       // -S
+    bool crick = false;      // -c
+    int intrainterboth = 0;  // -z
+    int rhamm = 3;           // -r
+    std::string prefix;      // -p
+    int numnodes = 1, node = 0;  // -n -N
+    int sweep_start = 0, sweep_end = 0;  // -b -B
+    int K = 100;             // -K
+    int sample = 1;          // -k
+    std::string in_file, in_seq_file, out_file, log_file;  // -i -I -o -F
+    int file_log_level = 3;  // -f
+    int threads = 0;         // -T
+    int gpus = 0;            // --gpus (extension; 0 = all visible)
+    bool help = false, version = false;
+};
+// returns 0, or -1 after printing the problem (caller prints usage and exits 1)
+int parse_args(int argc, char **argv, Options &o, std::string &err);
+// expands @file arguments (libkit4b/Utility.cpp:1200-1313)
+int expand_param_files(int argc, char **argv, std::vector<std::string> &out, std::string &err);
+// argtable3-style integer: decimal, 0x/0o/0b prefixes, optional KB/MB/GB suffix
+bool parse_int_arg(const char *s, long &v);
+void print_usage(const char *prog);
+
+}  // namespace k4bhost

@@ -1,0 +1,355 @@
+// k4b_reports.cpp - output writers of the `hammings` drop-in.  Byte-exact parity with the
+// reference lives here, so each loop walks the same flat arrays in the same order as the
+// reference and keeps its quirks (a9, a16).
+#include <errno.h>
+#include <fcntl.h>
+#include <stdio.h>
+#include <string.h>
+#include <strings.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <fstream>
+
+#include "k4b_host.h"
+
+namespace k4bhost {
+
+namespace {
+
+// buffered fd writer; retries short writes like CUtility::RetryWrites (libkit4b/Utility.cpp:713)
+class Out {
+  public:
+    int open_trunc(const std::string &path, std::string &err) {
+        fd_ = ::open(path.c_str(), O_RDWR | O_CREAT, S_IRUSR | S_IWUSR);
+        if (fd_ < 0 || ftruncate(fd_, 0) != 0) {
+            err = "unable to create/truncate output file '" + path + "': " + strerror(errno);
+            if (fd_ >= 0) ::close(fd_);
+            fd_ = -1;
+            return kErrCreateFile;
+        }
+        buf_.reserve(1 << 20);
+        return kOk;
+    }
+    void put(const char *s, size_t n) {
+        buf_.append(s, n);
+        if (buf_.size() >= (1 << 20) - 4096) flush();
+    }
+    void put(const std::string &s) { put(s.data(), s.size()); }
+    bool flush() {
+        size_t off = 0;
+        while (off < buf_.size()) {
+            const ssize_t w = ::write(fd_, buf_.data() + off, buf_.size() - off);
+            if (w < 0) {
+                if (errno == EINTR || errno == EAGAIN) continue;
+                ok_ = false;
+                break;
+            }
+            off += (size_t)w;
+        }
+        buf_.clear();
+        return ok_;
+    }
+    int close_sync(std::string &err) {
+        flush();
+        if (fd_ >= 0) {
+            fsync(fd_);
+            ::close(fd_);
+            fd_ = -1;
+        }
+        if (!ok_) {
+            err = "write failed";
+            return kErrFileAccess;
+        }
+        return kOk;
+    }
+
+  private:
+    int fd_ = -1;
+    bool ok_ = true;
+    std::string buf_;
+};
+
+// founder prefix filter: name must start (case-insensitively) with <prefix> followed by '|' and
+// '#'; the tag is stripped from printed names (hammings.cpp:1733-1742, :1805-1809,
+// seghaplotypes.h:3-5)
+struct PrefixFilter {
+    std::string tag;
+    explicit PrefixFilter(const std::string &prefix) {
+        if (!prefix.empty()) tag = prefix + "|#";
+    }
+    bool skip(const std::string &name) const {
+        return !tag.empty() && strncasecmp(name.c_str(), tag.c_str(), tag.size()) != 0;
+    }
+    const char *printed(const std::string &name) const {
+        // the reference prints &szChromName[PrefixLen]; a shorter name would have been skipped
+        return name.c_str() + tag.size();
+    }
+};
+
+}  // namespace
+
+int write_exhaustive_csv(const std::string &path, const Genome &g, uint32_t K, const uint16_t *hd,
+                         uint32_t sweep_start, uint32_t sweep_end, std::string &err) {
+    Out out;
+    int rc = out.open_trunc(path, err);
+    if (rc) return rc;
+    char line[256];
+    int n = snprintf(line, sizeof(line), "%u,%d,%d\n", g.genome_len, (int)(sweep_start + 1), (int)sweep_end);
+    out.put(line, (size_t)n);
+    const uint32_t flat = g.genome_len - 2;
+    if (!g.chroms.empty()) {
+        size_t ci = 0;
+        uint32_t cur_loci = 0;
+        // SeqIdx walks the flat array; a chromosome switch skips K positions (its K-1 tail
+        // positions + the separator) - which over-skips after a chromosome shorter than K and
+        // then reads mis-aligned (and possibly past-the-end) values exactly as the reference does
+        for (uint64_t seq_idx = 0; seq_idx < flat; ++seq_idx, ++cur_loci) {
+            if (cur_loci >= g.chroms[ci].num_subseqs) {
+                if (ci + 1 == g.chroms.size()) break;
+                ++ci;
+                cur_loci = 0;
+                seq_idx += K;
+            }
+            const uint32_t v = seq_idx < flat ? hd[seq_idx] : K + 1;
+            if (v <= K) {
+                n = snprintf(line, sizeof(line), "\"%s\",%d,%d\n", g.chroms[ci].name.c_str(), (int)cur_loci, (int)v);
+                out.put(line, (size_t)n);
+            }
+        }
+    }
+    return out.close_sync(err);
+}
+
+int write_restricted_csv(const std::string &path, const std::vector<RChrom> &chroms, uint32_t K,
+                         const uint8_t *h, const std::string &prefix, std::string &err) {
+    Out out;
+    int rc = out.open_trunc(path, err);
+    if (rc) return rc;
+    const PrefixFilter pf(prefix);
+    out.put("\"Chrom\",\"StartLoci\",\"Len\",\"Hamming\"\n");
+    char line[512];
+    uint64_t ofs = 0;
+    for (const RChrom &c : chroms) {
+        const uint8_t *p = h + ofs;
+        ofs += c.len;
+        if (c.len < K || pf.skip(c.name)) continue;
+        // run-length walk with the reference's off-by-ones: the loop starts at loci 1 while
+        // still reading H[0], so the last K-mer is never examined and every run after the
+        // first is reported one position late (hammings.cpp:1811-1829)
+        int run_len = 0, cur = *p, run_loci = 0;
+        for (uint32_t loci = 1; loci <= c.len - K; ++loci, ++p) {
+            if (*p == cur) {
+                ++run_len;
+                continue;
+            }
+            int n = snprintf(line, sizeof(line), "\"%s\",%d,%d,%d\n", pf.printed(c.name), run_loci, run_len, cur);
+            out.put(line, (size_t)n);
+            run_len = 1;
+            cur = *p;
+            run_loci = (int)loci;
+        }
+        int n = snprintf(line, sizeof(line), "\"%s\",%d,%d,%d\n", pf.printed(c.name), run_loci, run_len, cur);
+        out.put(line, (size_t)n);
+    }
+    return out.close_sync(err);
+}
+
+int write_restricted_bed(const std::string &path, const std::vector<RChrom> &chroms, uint32_t K, int R,
+                         const uint8_t *h, const std::string &prefix, std::string &err) {
+    Out out;
+    int rc = out.open_trunc(path, err);
+    if (rc) return rc;
+    const PrefixFilter pf(prefix);
+    char line[512];
+    int n = snprintf(line, sizeof(line),
+                     "track type=bedGraph name=ResHamming%d_%d description=\"Restricted Hammings for K-mer length "
+                     "%d and Hamming limit %d\"\n",
+                     (int)K, R, (int)K, R);
+    out.put(line, (size_t)n);
+    uint64_t ofs = 0;
+    for (const RChrom &c : chroms) {
+        const uint8_t *p = h + ofs;
+        ofs += c.len;
+        if (c.len < K || pf.skip(c.name)) continue;
+        // same walk as the CSV but the run length starts at 1 (hammings.cpp:1945-1965)
+        int run_len = 1, cur = *p, run_loci = 0;
+        for (uint32_t loci = 1; loci <= c.len - K; ++loci, ++p) {
+            if (*p == cur) {
+                ++run_len;
+                continue;
+            }
+            n = snprintf(line, sizeof(line), "%s\t%d\t%d\t%d\n", pf.printed(c.name), run_loci, run_loci + run_len - 1, cur);
+            out.put(line, (size_t)n);
+            run_len = 1;
+            cur = *p;
+            run_loci = (int)loci;
+        }
+        n = snprintf(line, sizeof(line), "%s\t%d\t%d\t%d\n", pf.printed(c.name), run_loci, run_loci + run_len - 1, cur);
+        out.put(line, (size_t)n);
+    }
+    return out.close_sync(err);
+}
+
+int write_restricted_wiggle(const std::string &path, const std::vector<RChrom> &chroms, uint32_t K,
+                            int R, int sensitivity, const uint8_t *h, const std::string &prefix,
+                            std::string &err) {
+    Out out;
+    int rc = out.open_trunc(path, err);
+    if (rc) return rc;
+    const PrefixFilter pf(prefix);
+    std::string hdr(2 * path.size() + 512, '\0');
+    int n = snprintf(&hdr[0], hdr.size(),
+                     "track type=wiggle_0 color=50,150,255 autoScale=off maxHeightPixels=128:32:8 name=\"Hammings "
+                     "(%d,%d,%d) - %s\" description=\"Hammings Sensitivity: %d KMerLen: %d RHamm: %d  for %s\"\n",
+                     sensitivity, (int)K, R, path.c_str(), sensitivity, (int)K, R, path.c_str());
+    out.put(hdr.data(), (size_t)n);
+    char line[512];
+    uint64_t ofs = 0;
+    for (const RChrom &c : chroms) {
+        const uint8_t *p = h + ofs;
+        ofs += c.len;
+        if (c.len < K || pf.skip(c.name)) continue;
+        // correct loop bounds here, but after a change the span start is loci+1 so every span
+        // but the first is printed one position late (hammings.cpp:2084-2103)
+        uint32_t span_len = 0, span_start = 0, loci = 0;
+        uint8_t cur = *p;
+        for (loci = 0; loci <= c.len - K; ++loci, ++p) {
+            if (*p != cur) {
+                n = snprintf(line, sizeof(line), "variableStep chrom=%s span=%d\n%d %d\n", pf.printed(c.name),
+                             (int)span_len, (int)(span_start + 1), (int)cur);
+                out.put(line, (size_t)n);
+                cur = *p;
+                span_len = 0;
+                span_start = loci + 1;
+            }
+            ++span_len;
+        }
+        if (span_start != loci) {
+            n = snprintf(line, sizeof(line), "variableStep chrom=%s span=%d\n%d %d\n", pf.printed(c.name),
+                         (int)span_len, (int)(span_start + 1), (int)cur);
+            out.put(line, (size_t)n);
+        }
+    }
+    return out.close_sync(err);
+}
+
+// ---- -m3 merge -----------------------------------------------------------------------------------
+namespace {
+struct CsvRow {
+    bool ok = false;        // "chrom",loci,dist shape
+    std::string chrom;
+    long loci = 0, dist = 0;
+    int nfields = 0;
+};
+// minimal CSV line split: the reference only accepts rows whose first field is quoted and whose
+// second and third are not (hammings.cpp:1243-1248)
+CsvRow parse_row(const std::string &line) {
+    CsvRow r;
+    std::vector<std::string> f;
+    std::vector<bool> quoted;
+    size_t i = 0;
+    while (i <= line.size()) {
+        std::string cur;
+        bool q = false;
+        while (i < line.size() && (line[i] == ' ' || line[i] == '\t')) ++i;
+        if (i < line.size() && line[i] == '"') {
+            q = true;
+            ++i;
+            while (i < line.size() && line[i] != '"') cur.push_back(line[i++]);
+            if (i < line.size()) ++i;
+            while (i < line.size() && line[i] != ',') ++i;
+        } else {
+            while (i < line.size() && line[i] != ',') cur.push_back(line[i++]);
+        }
+        f.push_back(cur);
+        quoted.push_back(q);
+        if (i >= line.size()) break;
+        ++i;  // skip the comma
+    }
+    r.nfields = (int)f.size();
+    if (f.size() >= 3 && quoted[0] && !quoted[1] && !quoted[2]) {
+        r.ok = true;
+        r.chrom = f[0];
+        r.loci = strtol(f[1].c_str(), nullptr, 10);
+        r.dist = strtol(f[2].c_str(), nullptr, 10);
+    }
+    return r;
+}
+bool next_line(std::ifstream &in, std::string &line) {
+    while (std::getline(in, line)) {
+        while (!line.empty() && (line.back() == '\r' || line.back() == '\n')) line.pop_back();
+        size_t b = 0;
+        while (b < line.size() && isspace((unsigned char)line[b])) ++b;
+        if (b == line.size()) continue;  // blank lines are skipped by the CSV reader
+        return true;
+    }
+    return false;
+}
+}  // namespace
+
+int merge_hamming_csv(const std::string &from, const std::string &into, std::string &err) {
+    std::ifstream fin(from);
+    if (!fin) {
+        err = "unable to open '" + from + "'";
+        return kErrOpnFile;
+    }
+    std::ifstream tin(into);
+    const bool copy = !tin.good();  // no existing target: the result is a copy of `from`
+    const std::string tmp = copy ? into : into + ".tmp";
+    Out out;
+    int rc = out.open_trunc(tmp, err);
+    if (rc) return rc;
+    out.put("\"Chrom\",\"Loci\",\"Hamming\"");
+    std::string lf, lt;
+    int num_errs = 0;
+    bool fail = false;
+    char line[512];
+    while (true) {
+        if (!next_line(fin, lf)) break;
+        if (!copy && !next_line(tin, lt)) break;
+        CsvRow a = parse_row(lf), b;
+        if (a.nfields < 3) {
+            fail = true;
+            break;
+        }
+        if (!copy) {
+            b = parse_row(lt);
+            if (b.nfields < 3) {
+                fail = true;
+                break;
+            }
+        }
+        if (!a.ok) continue;              // descriptor rows (e.g. the "G,2,G" header) are dropped
+        if (!copy && !b.ok) continue;
+        long d = a.dist;
+        if (!copy) {
+            if (strcasecmp(a.chrom.c_str(), b.chrom.c_str()) != 0 || a.loci != b.loci) {
+                if (num_errs++ > 1) {
+                    fail = true;
+                    break;
+                }
+                continue;
+            }
+            d = std::min(a.dist, b.dist);
+        }
+        int n = snprintf(line, sizeof(line), "\n\"%s\",%ld,%ld", a.chrom.c_str(), a.loci, d);
+        out.put(line, (size_t)n);
+    }
+    rc = out.close_sync(err);
+    if (fail) {
+        err = "merge inputs are inconsistent";
+        return -1;
+    }
+    if (rc) return rc;
+    if (!copy) {
+        tin.close();
+        if (remove(into.c_str()) != 0 || rename(tmp.c_str(), into.c_str()) != 0) {
+            err = "unable to replace '" + into + "'";
+            return -1;
+        }
+    }
+    return kOk;
+}
+
+}  // namespace k4bhost

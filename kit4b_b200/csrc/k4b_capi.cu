@@ -326,6 +326,9 @@ extern "C" int k4b_allpairs_min_device(k4b_packed *queries, k4b_packed *targets,
                                        int self_exclude, uint32_t q_begin, uint32_t q_end,
                                        uint32_t clamp, uint16_t *d_out_min, void *stream,
                                        int *launches) {
+    // clamp > 0 selects the targeted (-m0) rules: results capped at the "not found" value, probe
+    // symbols >= N are wildcards, more than 4 of them report 0
+    const bool targeted_rules = clamp > 0;
     if (launches) *launches = 0;
     if (!queries || !targets) return fail(K4B_ERR_PARAMS, "NULL packed handle");
     if (queries->K != targets->K) return fail(K4B_ERR_PARAMS, "query/target K differ");
@@ -370,6 +373,7 @@ extern "C" int k4b_allpairs_min_device(k4b_packed *queries, k4b_packed *targets,
     prm.tiles_total = (targets->nw + kTileGroups - 1) / kTileGroups;
     prm.out = d_min32;
     prm.self_exclude = self_exclude ? 1 : 0;
+    prm.wildcard = targeted_rules ? 1 : 0;
     // enough CTAs for ~16 balanced waves on 148 SMs x 2 resident CTAs; never below one tile
     const uint32_t qpt = generic ? 1u : (uint32_t)queries_per_thread(W, three);
     const uint32_t qblocks = (nq + kThreads * qpt - 1) / (kThreads * qpt);
@@ -387,7 +391,8 @@ extern "C" int k4b_allpairs_min_device(k4b_packed *queries, k4b_packed *targets,
     }
     if (e == cudaSuccess) e = cudaEventRecord(g_ev1, st);
     if (e == cudaSuccess)
-        e = launch_finalize(d_min32, queries->view(), q_begin, nq, K, clamp, d_out_min, st);
+        e = launch_finalize(d_min32, queries->view(), q_begin, nq, K, clamp, targeted_rules ? 4 : -1,
+                            d_out_min, st);
     cudaFreeAsync(d_min32, st);
     if (e != cudaSuccess) return fail(cuda_code(e), "allpairs launch: %s", cudaGetErrorString(e));
     if (launches) *launches = 3;  // fill + allpairs + finalize

@@ -155,8 +155,10 @@ __global__ void fill_u32_kernel(uint32_t *d, uint32_t n, uint32_t v) {
 
 // minima -> uint16 results; positions that are not valid K-mer starts report K+1 (the
 // reference's "never lowered" fill value, hammings.cpp:3120-3122)
+// max_wild >= 0 (targeted mode): a query K-mer holding more than max_wild symbols >= N reports 0
+// (SfxArray.cpp:4322-4326)
 __global__ void finalize_kernel(const uint32_t *__restrict__ min32, ImageView q, uint32_t q_begin,
-                                uint32_t n, uint32_t K, uint32_t clamp,
+                                uint32_t n, uint32_t K, uint32_t clamp, int max_wild,
                                 uint16_t *__restrict__ out16) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -164,6 +166,17 @@ __global__ void finalize_kernel(const uint32_t *__restrict__ min32, ImageView q,
     const bool ok = pos < q.len && ((q.valid()[pos >> 5] >> (pos & 31)) & 1u);
     uint32_t v = min32[i];
     if (clamp && v > clamp) v = clamp;
+    if (ok && max_wild >= 0) {
+        const uint32_t *p2 = q.plane(2);
+        uint32_t cnt = 0;
+        for (uint32_t done = 0; done < K; done += 32) {
+            const uint32_t at = pos + done, wi = at >> 5, sh = at & 31;
+            uint32_t bits = __funnelshift_r(p2[wi], p2[wi + 1], sh);
+            if (K - done < 32) bits &= (1u << (K - done)) - 1u;
+            cnt += __popc(bits);
+        }
+        if ((int)cnt > max_wild) v = 0;
+    }
     out16[i] = ok ? (uint16_t)v : (uint16_t)(K + 1);
 }
 
@@ -223,17 +236,36 @@ __device__ __forceinline__ void revcomp(const Kmer<W, P> &q, uint32_t K, uint32_
     }
 }
 
-template <int W, int P>
+// a = query, b = candidate.  WILD (targeted mode, three planes): query symbols >= N are
+// wildcards that match any target ACGT base but never a target N (SfxArray.cpp:4266-4296);
+// the query was prepared by make_wild(): plane 2 holds the NOT-wild mask, planes 0/1 are zero
+// at wildcard positions.
+template <int W, int P, bool WILD>
 __device__ __forceinline__ uint32_t kmer_dist(const Kmer<W, P> &a, const Kmer<W, P> &b) {
     uint32_t d = 0;
 #pragma unroll
     for (int w = 0; w < W; ++w) {
         uint32_t m = a.w[0][w] ^ b.w[0][w];
         m |= a.w[1][w] ^ b.w[1][w];
-        if (P == 3) m |= a.w[2][w] ^ b.w[2][w];
+        if (P == 3) {
+            if (WILD) m = (m & a.w[2][w]) | b.w[2][w];
+            else m |= a.w[2][w] ^ b.w[2][w];
+        }
         d += __popc(m);
     }
     return d;
+}
+
+template <int W, int P>
+__device__ __forceinline__ void make_wild(Kmer<W, P> &q, uint32_t tail_mask) {
+    if (P != 3) return;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const uint32_t nw = ~q.w[P - 1][w] & ((w == W - 1) ? tail_mask : 0xffffffffu);
+        q.w[0][w] &= nw;
+        q.w[1][w] &= nw;
+        q.w[P - 1][w] = nw;
+    }
 }
 
 // candidate K-mer at shift s of the group whose plane words are cw[p][0..W]
@@ -248,7 +280,7 @@ __device__ __forceinline__ void cut_candidate(const uint32_t (&cw)[P][W + 1], ui
     }
 }
 
-template <int W, int P, int Q, bool CRICK>
+template <int W, int P, int Q, bool CRICK, bool WILD>
 __global__ void __launch_bounds__(kThreads, 2) allpairs_min_kernel(const AllPairsParams prm) {
     constexpr int S = CRICK ? 2 : 1;
     constexpr int NARR = P + 1;  // planes + valid
@@ -269,6 +301,10 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_kernel(const AllPair
         qpos[j] = qbase + j * kThreads + tid;
         load_kmer<W, P>(prm.q, qpos[j], tail_mask, qk[j][0]);
         if (CRICK) revcomp<W, P>(qk[j][0], K, tail_mask, qk[j][1]);
+        if (WILD) {
+            make_wild<W, P>(qk[j][0], tail_mask);
+            if (CRICK) make_wild<W, P>(qk[j][1], tail_mask);
+        }
         // start from the current global minimum (monotone, so a stale read is still an upper
         // bound): lets a query that already reached the floor 0 skip work
         best[j] = qpos[j] < prm.q_end ? prm.out[qpos[j] - prm.q_begin] : 0u;
@@ -330,8 +366,8 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_kernel(const AllPair
                     cut_candidate<W, P>(cw, s, tail_mask, c);
 #pragma unroll
                     for (int j = 0; j < Q; ++j) {
-                        uint32_t d = kmer_dist<W, P>(qk[j][0], c);
-                        if (CRICK) d = min(d, kmer_dist<W, P>(qk[j][1], c));
+                        uint32_t d = kmer_dist<W, P, WILD>(qk[j][0], c);
+                        if (CRICK) d = min(d, kmer_dist<W, P, WILD>(qk[j][1], c));
                         best[j] = min(best[j], d);
                     }
                 }
@@ -346,9 +382,9 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_kernel(const AllPair
                     const uint32_t cpos = cpos0 + s;
 #pragma unroll
                     for (int j = 0; j < Q; ++j) {
-                        uint32_t d = kmer_dist<W, P>(qk[j][0], c);
+                        uint32_t d = kmer_dist<W, P, WILD>(qk[j][0], c);
                         if (self_here && cpos == qpos[j]) d = kNoDist;
-                        if (CRICK) d = min(d, kmer_dist<W, P>(qk[j][1], c));
+                        if (CRICK) d = min(d, kmer_dist<W, P, WILD>(qk[j][1], c));
                         best[j] = min(best[j], d);
                     }
                 }
@@ -370,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_kernel(const AllPair
 // generic path for K > 32*kMaxRegW: one query per thread, distance accumulated word by word
 // for the 32 candidates of a group (accumulators in registers, K-mers cut on the fly).
 // ---------------------------------------------------------------------------------------
-template <int P, bool CRICK>
+template <int P, bool CRICK, bool WILD>
 __global__ void __launch_bounds__(kThreads, 2) allpairs_min_generic_kernel(const AllPairsParams prm,
                                                                            const uint32_t *__restrict__ q_rc_image,
                                                                            uint32_t q_rc_nwp) {
@@ -413,6 +449,12 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_generic_kernel(const
                     const uint32_t *pl = qimg[s2] + (size_t)p * qnwp[s2] + wi;
                     qw[s2][p] = __funnelshift_r(pl[0], pl[1], sh) & m;
                 }
+                if (WILD && P == 3) {
+                    const uint32_t nw = ~qw[s2][P - 1] & m;
+                    qw[s2][0] &= nw;
+                    qw[s2][1] &= nw;
+                    qw[s2][P - 1] = nw;
+                }
             }
             uint32_t c0[P], c1[P];
 #pragma unroll
@@ -429,7 +471,10 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_generic_kernel(const
                 for (int s2 = 0; s2 < S; ++s2) {
                     uint32_t x = qw[s2][0] ^ c[0];
                     x |= qw[s2][1] ^ c[1];
-                    if (P == 3) x |= qw[s2][2] ^ c[2];
+                    if (P == 3) {
+                        if (WILD) x = (x & qw[s2][P - 1]) | c[P - 1];
+                        else x |= qw[s2][P - 1] ^ c[P - 1];
+                    }
                     acc[s2][s] += __popc(x);
                 }
             }
@@ -501,18 +546,23 @@ cudaError_t launch_fill_u32(uint32_t *d, uint32_t n, uint32_t v, cudaStream_t st
     return cudaGetLastError();
 }
 cudaError_t launch_finalize(const uint32_t *d_min32, ImageView q, uint32_t q_begin, uint32_t n,
-                            uint32_t K, uint32_t clamp, uint16_t *d_out16, cudaStream_t st) {
+                            uint32_t K, uint32_t clamp, int max_wild, uint16_t *d_out16,
+                            cudaStream_t st) {
     if (!n) return cudaSuccess;
-    finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_min32, q, q_begin, n, K, clamp, d_out16);
+    finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_min32, q, q_begin, n, K, clamp, max_wild, d_out16);
     return cudaGetLastError();
 }
 
 template <int W, int P, int Q>
 static cudaError_t launch_ap(const AllPairsParams &p, bool crick, dim3 grid, cudaStream_t st) {
-    if (crick)
-        allpairs_min_kernel<W, P, Q, true><<<grid, kThreads, 0, st>>>(p);
-    else
-        allpairs_min_kernel<W, P, Q, false><<<grid, kThreads, 0, st>>>(p);
+    const bool wild = P == 3 && p.wildcard;
+    if (wild) {
+        if (crick) allpairs_min_kernel<W, P, Q, true, (P == 3)><<<grid, kThreads, 0, st>>>(p);
+        else allpairs_min_kernel<W, P, Q, false, (P == 3)><<<grid, kThreads, 0, st>>>(p);
+    } else {
+        if (crick) allpairs_min_kernel<W, P, Q, true, false><<<grid, kThreads, 0, st>>>(p);
+        else allpairs_min_kernel<W, P, Q, false, false><<<grid, kThreads, 0, st>>>(p);
+    }
     return cudaGetLastError();
 }
 
@@ -562,12 +612,15 @@ cudaError_t launch_allpairs_generic(const AllPairsParams &p, bool three_planes, 
     dim3 grid(chunks, qb);
     if (n_ctas) *n_ctas = (int)(chunks * qb);
     if (!nq || !chunks) return cudaSuccess;
-    if (three_planes) {
-        if (crick) allpairs_min_generic_kernel<3, true><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
-        else allpairs_min_generic_kernel<3, false><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
+    if (three_planes && p.wildcard) {
+        if (crick) allpairs_min_generic_kernel<3, true, true><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
+        else allpairs_min_generic_kernel<3, false, true><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
+    } else if (three_planes) {
+        if (crick) allpairs_min_generic_kernel<3, true, false><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
+        else allpairs_min_generic_kernel<3, false, false><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
     } else {
-        if (crick) allpairs_min_generic_kernel<2, true><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
-        else allpairs_min_generic_kernel<2, false><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
+        if (crick) allpairs_min_generic_kernel<2, true, false><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
+        else allpairs_min_generic_kernel<2, false, false><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
     }
     return cudaGetLastError();
 }

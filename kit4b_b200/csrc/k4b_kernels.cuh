@@ -42,6 +42,7 @@ struct AllPairsParams {
     uint32_t tiles_per_chunk;
     uint32_t *out;           // [q_end-q_begin] running minima (pre-set to K+1)
     int self_exclude;        // skip forward pair with query pos == target pos
+    int wildcard;            // targeted mode: query symbols >= N match any target ACGT base
 };
 
 // host-callable launchers (defined in k4b_kernels.cu)
@@ -51,7 +52,8 @@ cudaError_t launch_valid(uint32_t *d_image, uint32_t nwp, uint32_t len, uint32_t
                          unsigned long long *d_count, cudaStream_t st);
 cudaError_t launch_fill_u32(uint32_t *d, uint32_t n, uint32_t v, cudaStream_t st);
 cudaError_t launch_finalize(const uint32_t *d_min32, ImageView q, uint32_t q_begin, uint32_t n,
-                            uint32_t K, uint32_t clamp, uint16_t *d_out16, cudaStream_t st);
+                            uint32_t K, uint32_t clamp, int max_wild, uint16_t *d_out16,
+                            cudaStream_t st);
 // returns cudaErrorInvalidValue when K needs more than the supported words
 cudaError_t launch_allpairs(const AllPairsParams &p, bool three_planes, bool crick,
                             cudaStream_t st, int *n_ctas);

@@ -76,6 +76,8 @@ def ref_binary(nosleep: bool = True):
 
 
 def _u8(a):
+    if a.dtype != np.uint8 or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError("oracle inputs must be contiguous uint8 arrays")
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
 
 
@@ -223,6 +225,82 @@ def exhaustive_csv(genome_len: int, chroms, K: int, hd: np.ndarray, sweep_start:
         seq_idx += 1
         cur += 1
     return "".join(lines).encode("latin-1")
+
+
+def restricted_per_loci(chroms, concat_values: np.ndarray) -> np.ndarray:
+    """concat-layout results (with separator slots) -> the reference's per-loci array
+    H[sum of entry lengths] (hammings.cpp:2336-2354, :1615-1674)."""
+    return np.concatenate([concat_values[st:st + ln] for (_, st, ln) in chroms]) if chroms else np.zeros(0, np.uint8)
+
+
+def restricted_report(chroms, K: int, R: int, h: np.ndarray, fmt: int, out_name: str = "", sensitivity: int = 0,
+                      prefix: str = "") -> bytes:
+    """Literal restatement of the three restricted-mode writers incl. their off-by-ones
+    (hammings.cpp:1711-1849 CSV, :1853-1984 BED, :1987-2118 Wiggle)."""
+    tag = (prefix + "|#") if prefix else ""
+    out = []
+    if fmt == 0:
+        out.append('"Chrom","StartLoci","Len","Hamming"\n')
+    elif fmt == 1:
+        out.append('track type=bedGraph name=ResHamming%d_%d description="Restricted Hammings for K-mer length %d '
+                   'and Hamming limit %d"\n' % (K, R, K, R))
+    else:
+        out.append('track type=wiggle_0 color=50,150,255 autoScale=off maxHeightPixels=128:32:8 name="Hammings '
+                   '(%d,%d,%d) - %s" description="Hammings Sensitivity: %d KMerLen: %d RHamm: %d  for %s"\n'
+                   % (sensitivity, K, R, out_name, sensitivity, K, R, out_name))
+    ofs = 0
+    vals = h.tolist()
+    for (name, _st, ln) in chroms:
+        base = ofs
+        ofs += ln
+        if ln < K or (tag and name[:len(tag)].lower() != tag.lower()):
+            continue
+        nm = name[len(tag):]
+        if fmt in (0, 1):
+            run_len = 0 if fmt == 0 else 1
+            cur, run_loci, p = vals[base], 0, base
+            for loci in range(1, ln - K + 1):
+                if vals[p] == cur:
+                    run_len += 1
+                else:
+                    out.append(('"%s",%d,%d,%d\n' % (nm, run_loci, run_len, cur)) if fmt == 0 else
+                               ("%s\t%d\t%d\t%d\n" % (nm, run_loci, run_loci + run_len - 1, cur)))
+                    run_len, cur, run_loci = 1, vals[p], loci
+                p += 1
+            out.append(('"%s",%d,%d,%d\n' % (nm, run_loci, run_len, cur)) if fmt == 0 else
+                       ("%s\t%d\t%d\t%d\n" % (nm, run_loci, run_loci + run_len - 1, cur)))
+        else:
+            span_len, span_start, cur, loci = 0, 0, vals[base], 0
+            for loci in range(0, ln - K + 1):
+                v = vals[base + loci]
+                if v != cur:
+                    out.append("variableStep chrom=%s span=%d\n%d %d\n" % (nm, span_len, span_start + 1, cur))
+                    cur, span_len, span_start = v, 0, loci + 1
+                span_len += 1
+            loci = ln - K + 1
+            if span_start != loci:
+                out.append("variableStep chrom=%s span=%d\n%d %d\n" % (nm, span_len, span_start + 1, cur))
+    return "".join(out).encode("latin-1")
+
+
+def read_sfx(path: str):
+    """(entries [(name, start, len)], concatenated sequence) of an 'sfx5' file (SfxArray.h:98-123, :194-207)."""
+    b = open(path, "rb").read()
+    if b[:4] != b"sfx5":
+        raise ValueError("not an sfx5 file")
+    entries_ofs, entries_size = struct.unpack_from("<QI", b, 20)
+    block_ofs = struct.unpack_from("<Q", b, 44)[0]
+    nent = struct.unpack_from("<I", b, entries_ofs)[0]
+    entries = []
+    for i in range(nent):
+        off = entries_ofs + 8 + i * 111
+        name = b[off + 8: b.index(b"\0", off + 8)].decode("latin-1")
+        seqlen = struct.unpack_from("<I", b, off + 8 + 81 + 2)[0]
+        start = struct.unpack_from("<Q", b, off + 8 + 81 + 2 + 4)[0]
+        entries.append((name, start, seqlen))
+    concat_len = struct.unpack_from("<Q", b, block_ofs + 8)[0]
+    seq = np.frombuffer(b, dtype=np.uint8, count=concat_len, offset=block_ofs + 20) & 0x07
+    return entries, np.ascontiguousarray(seq)
 
 
 # --------------------------------------------------------------------------------------------

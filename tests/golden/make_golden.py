@@ -81,10 +81,74 @@ def make_cases():
     return cases
 
 
+def make_targeted_cases():
+    """-m0 -I (targeted) cases: a small indexed assembly and probe sets built from mutated copies of
+    it (forward and reverse complement) plus random sequence; one probe set carries N / '-' symbols."""
+    rng = random.Random(41)
+    t1, t2 = rnd(rng, 12000), rnd(rng, 8000)
+    target = [("tA", t1), ("tB", t2)]
+    rng = random.Random(42)
+
+    def probe_set(with_n):
+        parts = []
+        for src, start, n, nmut, rc in [(t1, 500, 300, 0, False), (t1, 3000, 300, 4, False), (t2, 1000, 300, 9, True),
+                                        (t1, 7000, 300, 14, False), (t2, 5000, 300, 20, True), (t1, 9000, 200, 30, False)]:
+            seg = mutate(rng, src[start:start + n], nmut)
+            parts.append(revcomp(seg) if rc else seg)
+        parts.append(rnd(rng, 600))
+        p1 = "".join(parts)
+        p2 = mutate(rng, t2[6000:6400], 10) + rnd(rng, 150)
+        if with_n:
+            p1 = p1[:310] + "N" + p1[311:650] + "NN" + p1[652:900] + "NNNNN" + p1[905:1200] + "-" + p1[1201:]
+            p2 = p2[:40] + "R" + p2[41:]
+        return [("pX", p1), ("pshort", "ACGTACGTAC"), ("pY", p2)]
+
+    return dict(target=target,
+                probes={"tp": probe_set(False), "tpn": probe_set(True)},
+                runs=[dict(probes="tp", K=32, R=3, both=True, fmt=0), dict(probes="tp", K=32, R=3, both=True, fmt=1),
+                      dict(probes="tp", K=32, R=3, both=True, fmt=2), dict(probes="tp", K=25, R=3, both=False, fmt=0),
+                      dict(probes="tp", K=20, R=1, both=True, fmt=0), dict(probes="tp", K=50, R=5, both=True, fmt=0),
+                      dict(probes="tpn", K=32, R=3, both=True, fmt=0), dict(probes="tpn", K=25, R=2, both=True, fmt=2)])
+
+
+def main_targeted(manifest):
+    case = make_targeted_cases()
+    tfa = os.path.join(HERE, "targ.fa")
+    sfx = os.path.join(HERE, "targ.sfx")
+    open(tfa, "w").write(fasta(case["target"]))
+    subprocess.run([REF.replace("_nosleep", ""), "index", "-i", tfa, "-o", sfx, "-r", "targ", "-T2"], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    probes = {}
+    for pname, entries in case["probes"].items():
+        fa = os.path.join(HERE, pname + ".fa")
+        seq = os.path.join(HERE, pname + ".seq")
+        open(fa, "w").write(fasta(entries))
+        subprocess.run([REF, "genbioseq", "-i", fa, "-o", seq, "-r", pname], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        probes[pname] = dict(fasta=os.path.basename(fa), bioseq=os.path.basename(seq))
+    runs = []
+    for r in case["runs"]:
+        ext = ("csv", "bed", "wig")[r["fmt"]]
+        tag = "%s.K%dr%d%s%s" % (r["probes"], r["K"], r["R"], "c" if r["both"] else "w",
+                                 ("k%d" % r["sample"]) if r.get("sample") else "")
+        out = os.path.join(HERE, "targeted.%s.%s" % (tag, ext))
+        # the Wiggle header embeds the -o path: run with a relative name from inside tests/golden
+        args = [REF.replace("_nosleep", ""), "hammings", "-m0", "-K%d" % r["K"], "-r%d" % r["R"], "-S%d" % r["fmt"],
+                "-T2", "-i", "targ.sfx", "-I", probes[r["probes"]]["bioseq"], "-o", os.path.basename(out)]
+        if r["both"]:
+            args.insert(3, "-c")
+        if r.get("sample"):
+            args.insert(3, "-k%d" % r["sample"])
+        subprocess.run(args, check=True, cwd=HERE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        runs.append(dict(r, out=os.path.basename(out)))
+    manifest["__targeted__"] = dict(target_fasta="targ.fa", sfx="targ.sfx", probes=probes, runs=runs)
+
+
 def main():
     if not os.access(REF, os.X_OK):
         sys.exit("reference binary missing: run oracle/build_ref.sh first")
     manifest = {}
+    main_targeted(manifest)
     for name, case in make_cases().items():
         fa = os.path.join(HERE, name + ".fa")
         seq = os.path.join(HERE, name + ".seq")
@@ -101,6 +165,19 @@ def main():
             subprocess.run(args, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             runs.append(dict(K=r["K"], both=r["both"], csv=os.path.basename(out)))
         manifest[name] = dict(fasta=os.path.basename(fa), bioseq=os.path.basename(seq), runs=runs)
+    # -m3 merge: Watson-only file merged INTO a copy of ... both-strand file, and a copy-merge
+    import shutil
+    into = os.path.join(HERE, "merge.tiny2.into.csv")
+    shutil.copyfile(os.path.join(HERE, "tiny2.K25w.csv"), into)
+    subprocess.run([REF, "hammings", "-m3", "-i", os.path.join(HERE, "tiny2.K25c.csv"), "-o", into], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    fresh = os.path.join(HERE, "merge.tiny2.copy.csv")
+    if os.path.exists(fresh):
+        os.remove(fresh)
+    subprocess.run([REF, "hammings", "-m3", "-i", os.path.join(HERE, "tiny2.K25c.csv"), "-o", fresh], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    manifest["__merge__"] = {"from": "tiny2.K25c.csv", "into_before": "tiny2.K25w.csv",
+                             "into_after": "merge.tiny2.into.csv", "copy_after": "merge.tiny2.copy.csv"}
     json.dump(manifest, open(os.path.join(HERE, "manifest.json"), "w"), indent=1, sort_keys=True)
     print("wrote", len(manifest), "cases")
 

@@ -148,3 +148,60 @@ def test_config1_size_properties(oracle, K):
         assert hd[i] == best, i
     # idempotence: a second run gives the same array
     assert np.array_equal(hd, k4b.exhaustive(c, K, True))
+
+
+# ---- the drop-in binary end to end: same flags in, same bytes out ---------------------------
+def _run_cli(args, cwd=None):
+    import subprocess
+    from kit4b_b200 import hostlib
+    p = subprocess.run([hostlib.cli_path()] + args, cwd=cwd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    return p.stdout
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=case_id)
+def test_cli_exhaustive_output_file_equals_reference(case, tmp_path):
+    from conftest import golden_manifest
+    name, r = case
+    out = str(tmp_path / "out.csv")
+    args = ["hammings", "-m1", "-K%d" % r["K"], "-T3", "-i", os.path.join(GOLDEN, golden_manifest()[name]["bioseq"]),
+            "-o", out]
+    if r["both"]:
+        args.insert(2, "-c")
+    _run_cli(args)
+    assert open(out, "rb").read() == open(os.path.join(GOLDEN, r["csv"]), "rb").read()
+
+
+def _targeted_runs():
+    from conftest import golden_manifest
+    m = golden_manifest()["__targeted__"]
+    return [(m, r) for r in m["runs"]]
+
+
+@pytest.mark.parametrize("mr", _targeted_runs(), ids=lambda mr: mr[1]["out"])
+def test_cli_targeted_output_file_equals_reference(mr, tmp_path):
+    m, r = mr
+    args = ["hammings", "-m0", "-K%d" % r["K"], "-r%d" % r["R"], "-S%d" % r["fmt"], "-i", os.path.join(GOLDEN, m["sfx"]),
+            "-I", os.path.join(GOLDEN, m["probes"][r["probes"]]["bioseq"]), "-o", r["out"]]
+    if r["both"]:
+        args.insert(2, "-c")
+    _run_cli(args, cwd=str(tmp_path))  # relative -o: the Wiggle header embeds the path as given
+    assert open(os.path.join(str(tmp_path), r["out"]), "rb").read() == open(os.path.join(GOLDEN, r["out"]), "rb").read()
+
+
+def test_targeted_wildcards_and_n_rule(oracle):
+    """probe symbols >= N are wildcards, > 4 of them report 0, target N never matches."""
+    rng = np.random.default_rng(501)
+    target = random_genome(502, [6000, 4000]).copy()
+    target[1000:1003] = 4            # N run inside the target
+    target[2500] = 6
+    probes = target[900:1500].copy()
+    for p in (50, 130, 131, 200, 260, 261, 262, 263, 264, 400):
+        probes[p] = 4
+    probes[300] = 5
+    probes = np.ascontiguousarray(np.concatenate([probes, [7], rng.integers(0, 5, size=400, dtype=np.uint8)]),
+                                  dtype=np.uint8)
+    for K, R, both in [(32, 3, True), (25, 2, False), (64, 5, True), (140, 9, True)]:
+        want = oracle.targeted_brute(target, probes, K, R, both)
+        got = k4b.targeted(target, probes, K, R, both)
+        assert np.array_equal(got, want), (K, R, both)

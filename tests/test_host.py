@@ -1,0 +1,120 @@
+"""CPU tests of the C++ host front end (containers, LoadGenome layout, byte-exact writers, CLI
+parsing) through libk4bhost.so.  Arrays come from the pinned oracle; expected bytes are the
+files written by the unmodified reference (tests/golden)."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, case_id, golden_cases, golden_manifest, load_case
+
+from kit4b_b200 import hostlib
+
+
+def targeted_runs():
+    m = golden_manifest()["__targeted__"]
+    return [(m, r) for r in m["runs"]]
+
+
+@pytest.mark.parametrize("name", [n for n in golden_manifest() if not n.startswith("__")])
+def test_bioseq_reader_and_genome_layout(oracle, name):
+    case = golden_manifest()[name]
+    want, chroms, glen = load_case(oracle, name)
+    got, gch, gl = hostlib.concat_from_bioseq(os.path.join(GOLDEN, case["bioseq"]), 25)
+    assert gl == glen and np.array_equal(got, want)
+    assert gch == [(n, s, l) for (n, s, l) in chroms]
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=case_id)
+def test_exhaustive_csv_writer_is_byte_exact(oracle, case, tmp_path):
+    name, r = case
+    concat, _, _ = load_case(oracle, name)
+    hd = oracle.exhaustive_sliding(concat, r["K"], r["both"], threads=3)
+    out = str(tmp_path / "o.csv")
+    hostlib.write_exhaustive_csv(os.path.join(GOLDEN, golden_manifest()[name]["bioseq"]), r["K"], hd, out)
+    assert open(out, "rb").read() == open(os.path.join(GOLDEN, r["csv"]), "rb").read()
+
+
+@pytest.mark.parametrize("mr", targeted_runs(), ids=lambda mr: mr[1]["out"])
+def test_restricted_writers_are_byte_exact(oracle, mr, tmp_path, monkeypatch):
+    m, r = mr
+    ents, tseq = oracle.read_sfx(os.path.join(GOLDEN, m["sfx"]))
+    pb = os.path.join(GOLDEN, m["probes"][r["probes"]]["bioseq"])
+    concat, chroms, _ = oracle.concat_entries(oracle.read_bioseq(pb))
+    h = oracle.restricted_per_loci(chroms, oracle.targeted_brute(tseq, concat, r["K"], r["R"], r["both"]))
+    monkeypatch.chdir(tmp_path)  # the Wiggle header embeds the -o path as given
+    hostlib.write_restricted(pb, r["K"], r["R"], r["fmt"], h, r["out"])
+    assert open(r["out"], "rb").read() == open(os.path.join(GOLDEN, r["out"]), "rb").read()
+
+
+def test_sfx_reader(oracle):
+    m = golden_manifest()["__targeted__"]
+    ents, seq = hostlib.read_sfx(os.path.join(GOLDEN, m["sfx"]))
+    wents, wseq = oracle.read_sfx(os.path.join(GOLDEN, m["sfx"]))
+    assert ents == wents and np.array_equal(seq, wseq)
+
+
+def test_fasta_front_end_equals_reference_genbioseq(oracle, tmp_path):
+    for name, case in golden_manifest().items():
+        if name.startswith("__"):
+            continue
+        out = str(tmp_path / (name + ".seq"))
+        hostlib.fasta_to_bioseq(os.path.join(GOLDEN, case["fasta"]), out, name)
+        mine = oracle.read_bioseq(out)
+        ref = oracle.read_bioseq(os.path.join(GOLDEN, case["bioseq"]))
+        assert [n for n, _ in mine] == [n for n, _ in ref]
+        for (_, a), (_, b) in zip(mine, ref):
+            assert np.array_equal(a, b)
+        # and the C++ reader reads its own writer
+        got, _, _ = hostlib.concat_from_bioseq(out, 25)
+        want, _, _ = oracle.concat_entries(ref)
+        assert np.array_equal(got, want)
+
+
+def test_merge_matches_reference(tmp_path):
+    m = golden_manifest()["__merge__"]
+    into = str(tmp_path / "into.csv")
+    shutil.copyfile(os.path.join(GOLDEN, m["into_before"]), into)
+    hostlib.merge_csv(os.path.join(GOLDEN, m["from"]), into)
+    assert open(into, "rb").read() == open(os.path.join(GOLDEN, m["into_after"]), "rb").read()
+    fresh = str(tmp_path / "fresh.csv")
+    hostlib.merge_csv(os.path.join(GOLDEN, m["from"]), fresh)
+    assert open(fresh, "rb").read() == open(os.path.join(GOLDEN, m["copy_after"]), "rb").read()
+
+
+def test_cli_syntax_variants(tmp_path):
+    d = hostlib.parse_cli(["-m1", "-K25", "-c", "-i", "g.seq", "-o", "out.csv"])
+    assert (d["mode"], d["K"], d["crick"], d["in_file"], d["out_file"]) == (1, 25, 1, "g.seq", "out.csv")
+    d = hostlib.parse_cli(["--mode=1", "--seqlen", "50", "--strandcrick", "--in=g.seq"])
+    assert (d["mode"], d["K"], d["crick"]) == (1, 50, 1)
+    d = hostlib.parse_cli(["-m", "0", "--seq", "p.seq", "-r2", "-S2", "-i", "a.sfx", "--gpus=4"])
+    assert (d["mode"], d["rhamm"], d["resformat"], d["in_seq_file"], d["gpus"]) == (0, 2, 2, "p.seq", 4)
+    # defaults: restricted mode, K=100, Watson only, R=3 (hammings.cpp:312-332)
+    d = hostlib.parse_cli(["-i", "x"])
+    assert (d["mode"], d["K"], d["crick"], d["rhamm"], d["sample"]) == (0, 100, 0, 3, 1)
+    # unique long-option prefixes, argtable-style integers
+    d = hostlib.parse_cli(["--seql=0x20", "--sweeps=2", "-B", "1KB", "-i", "x", "-m1"])
+    assert (d["K"], d["sweep_start"], d["sweep_end"]) == (32, 2, 1024)
+    # grouped literals
+    d = hostlib.parse_cli(["-cm1", "-i", "x"])
+    assert d["crick"] == 1 and d["mode"] == 1
+    # @parameter file: several options per line, comments, blank lines
+    pf = tmp_path / "params.txt"
+    pf.write_text("# comment\n-m1 -K31\n\n; other comment\n// c++ comment\n  -c\n-i genome.seq\n")
+    d = hostlib.parse_cli(["@" + str(pf), "-o", "o.csv"])
+    assert (d["mode"], d["K"], d["crick"], d["in_file"], d["out_file"]) == (1, 31, 1, "genome.seq", "o.csv")
+    for bad in (["-m1"], ["-i", "x", "-K", "abc"], ["-i", "x", "--nosuch"], ["-i"], ["-i", "x", "stray"]):
+        with pytest.raises(RuntimeError):
+            hostlib.parse_cli(bad)
+
+
+def test_cli_binary_exit_codes():
+    import subprocess
+    exe = hostlib.cli_path()
+    assert os.path.exists(exe)
+    assert subprocess.run([exe, "-h"], capture_output=True).returncode == 1      # hammings.cpp:255-265
+    assert subprocess.run([exe, "-v"], capture_output=True).returncode == 1
+    assert subprocess.run([exe], capture_output=True).returncode == 1            # -i is required
+    assert subprocess.run([exe, "hammings", "-m1", "-K5", "-i", "x"], capture_output=True).returncode == 1
+    assert subprocess.run([exe, "-m0", "-K32", "-r9", "-i", "x"], capture_output=True).returncode == 1  # K/(R+1) < 4

@@ -28,6 +28,8 @@ def test_brute_and_numpy_oracles_match_reference_output(oracle, case):
 
 def test_fasta_encoding_equals_reference_bioseq(oracle):
     for name, case in golden_manifest().items():
+        if name.startswith("__"):
+            continue
         fa = oracle.encode_fasta(open(os.path.join(GOLDEN, case["fasta"])).read())
         bs = oracle.read_bioseq(os.path.join(GOLDEN, case["bioseq"]))
         assert [n for n, _ in fa] == [n for n, _ in bs]
@@ -69,3 +71,19 @@ def test_sampled_sliding_is_an_upper_bound(oracle):
     full = oracle.exhaustive_sliding(c, 25, True, threads=2)
     part, cells = oracle.exhaustive_sliding_sample(c, 25, True, 2, 1, 4)
     assert cells > 0 and (part >= full).all()
+
+
+def _targeted_runs():
+    m = golden_manifest()["__targeted__"]
+    return [(m, r) for r in m["runs"]]
+
+
+@pytest.mark.parametrize("mr", _targeted_runs(), ids=lambda mr: mr[1]["out"])
+def test_targeted_oracle_matches_reference_output(oracle, mr):
+    """-m0 -I: oracle array + restated writers == the reference's CSV / BED / Wiggle files."""
+    m, r = mr
+    _, tseq = oracle.read_sfx(os.path.join(GOLDEN, m["sfx"]))
+    concat, chroms, _ = oracle.concat_entries(oracle.read_bioseq(os.path.join(GOLDEN, m["probes"][r["probes"]]["bioseq"])))
+    h = oracle.restricted_per_loci(chroms, oracle.targeted_brute(tseq, concat, r["K"], r["R"], r["both"]))
+    rep = oracle.restricted_report(chroms, r["K"], r["R"], h, r["fmt"], out_name=r["out"])
+    assert rep == open(os.path.join(GOLDEN, r["out"]), "rb").read()
