@@ -7,7 +7,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -453,6 +456,20 @@ int broadcast_packed(k4b_packed *src, std::vector<k4b_packed *> &out) {
     return 0;
 }
 
+// K4B_TRACE=1 prints the host-side phase times of each host-buffer call to stderr
+struct PhaseTrace {
+    bool on = getenv("K4B_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+    void mark(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[k4b trace] %-22s %9.3f ms (total %9.3f ms)\n", what,
+                std::chrono::duration<double, std::milli>(now - last).count(),
+                std::chrono::duration<double, std::milli>(now - t0).count());
+        last = now;
+    }
+};
+
 // queries [q_begin,q_end) split evenly by position over the engine's devices; per-device
 // minima land in pinned host buffers and are handed to `sink(pos, value)`
 template <typename Sink>
@@ -464,6 +481,7 @@ int run_sharded(const uint8_t *q_concat, uint32_t q_len, const uint8_t *t_concat
     if (q_end > q_len) q_end = q_len;
     if (q_begin >= q_end) return K4B_OK;
     std::vector<DevJob> jobs(n);
+    PhaseTrace trace;
     auto cleanup = [&]() {
         for (int i = 0; i < n; ++i) {
             cudaSetDevice(g_eng.devs[i]);
@@ -498,6 +516,7 @@ int run_sharded(const uint8_t *q_concat, uint32_t q_len, const uint8_t *t_concat
                 if (rc) break;
             }
         }
+        trace.mark("H2D + pack (+bcast)");
         // launch every shard (asynchronous), then collect
         const uint64_t span = (uint64_t)q_end - q_begin;
         for (int i = 0; i < n && !rc; ++i) {
@@ -520,6 +539,7 @@ int run_sharded(const uint8_t *q_concat, uint32_t q_len, const uint8_t *t_concat
                                 g_eng.streams[i]);
             if (e != cudaSuccess) rc = fail(cuda_code(e), "D2H: %s", cudaGetErrorString(e));
         }
+        trace.mark("alloc + launch");
         for (int i = 0; i < n; ++i) {
             cudaSetDevice(g_eng.devs[i]);
             cudaError_t e = cudaStreamSynchronize(g_eng.streams[i]);
@@ -527,13 +547,16 @@ int run_sharded(const uint8_t *q_concat, uint32_t q_len, const uint8_t *t_concat
                 rc = fail(cuda_code(e), "device %d: %s", g_eng.devs[i], cudaGetErrorString(e));
         }
         if (rc) break;
+        trace.mark("kernels + D2H");
         // concatenate per-GPU minima back on the host
         for (int i = 0; i < n; ++i) {
             const DevJob &j = jobs[i];
             for (uint32_t p = j.q_begin; p < j.q_end; ++p) sink(p, j.h_out[p - j.q_begin]);
         }
+        trace.mark("host gather");
     } while (0);
     cleanup();
+    trace.mark("free");
     return rc;
 }
 

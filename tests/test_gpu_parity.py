@@ -205,3 +205,26 @@ def test_targeted_wildcards_and_n_rule(oracle):
         want = oracle.targeted_brute(target, probes, K, R, both)
         got = k4b.targeted(target, probes, K, R, both)
         assert np.array_equal(got, want), (K, R, both)
+
+
+def test_in_process_multi_gpu_shards(oracle):
+    """k4b_gpu_init(n>1): one process drives several GPUs - NCCL broadcast of the packed set,
+    query shards per device, minima concatenated on the host.  Needs >= 2 visible GPUs."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    k4b.gpu_shutdown()
+    try:
+        k4b.gpu_init(min(n, 8))
+        assert k4b.gpu_count() == min(n, 8)
+        c = random_genome(601, [30000, 12000, 9000])
+        for K, both in [(25, True), (100, False)]:
+            assert np.array_equal(k4b.exhaustive(c, K, both), oracle.exhaustive_sliding(c, K, both))
+        target = random_genome(602, [40000])
+        probes = np.ascontiguousarray(np.concatenate([target[100:900], [7], target[5000:5600]]), dtype=np.uint8)
+        probes[50] = (probes[50] + 1) % 4
+        assert np.array_equal(k4b.targeted(target, probes, 32, 3, True), oracle.targeted_brute(target, probes, 32, 3, True))
+    finally:
+        k4b.gpu_shutdown()
+        k4b.gpu_init(1)
