@@ -84,7 +84,11 @@ int k4b_hamm_exhaustive_shard(const uint8_t *concat, uint32_t concat_len, uint32
  * SfxArray.cpp:4227-4627) by exact brute force on the GPU.
  *   target_concat/target_len  the .sfx sequence area: each entry's bases followed by EOS
  *                             (SfxArray.cpp:1746-1750)
- *   probe_concat/probe_len    probes in the LoadGenome layout (hammings.cpp:2201-2310)
+ *   probe_concat/probe_len    probes in the LoadGenome layout (hammings.cpp:2201-2310); NULL
+ *                             = the probes are the K-mers of the target itself
+ *                             (CSfxArray::LocateSfxHammings, SfxArray.cpp:4107-4220: exact
+ *                             sense-strand self hits are skipped, results capped at 20);
+ *                             out_h then has target_len entries
  *   K 10..500, R 1..10; result per probe K-mer start = min(true both-strand minimum,
  *   K/(K/(R+1))) i.e. the reference's "not found" value (SfxArray.cpp:4462-4463); probe
  *   symbols >= N are wildcards against target ACGT, > 4 of them report 0 (:4266-4326)

@@ -132,30 +132,54 @@ static int run_restricted(const Options &o) {
     logmsg(2, "Genome Assembly Name: '%s' Descr: '%s' Title: '%s' Version: %d", sfx.dataset.c_str(),
            sfx.descr.c_str(), sfx.title.c_str(), sfx.version);
     const uint32_t K = (uint32_t)o.K;
-    if (o.in_seq_file.empty()) {
-        logmsg(0, "Restricted Hammings for K-mers drawn from the indexed assembly itself (no -I) are not "
-                  "supported by this build; supply the source K-mer sequences with -I <bioseq>");
+    const bool sep_probes = !o.in_seq_file.empty();
+    if (!sep_probes && o.intrainterboth != 0) {
+        logmsg(0, "Intra/inter filtering (-z%d) of K-mers drawn from the indexed assembly is not part of this build",
+               o.intrainterboth);
         return kErrParams;
     }
-    std::vector<SeqEntry> entries;
-    rc = read_bioseq(o.in_seq_file, entries, title, err);
-    if (rc) {
-        logmsg(0, "%s", err.c_str());
-        logmsg(0, "Unable to open assembly sequence file '%s'", o.in_seq_file.c_str());
-        return rc;
+    Genome g;  // probe set in the LoadGenome layout; for no -I it mirrors the suffix entries
+    std::vector<uint8_t> flat;
+    double secs = 0;
+    if (sep_probes) {
+        std::vector<SeqEntry> entries;
+        rc = read_bioseq(o.in_seq_file, entries, title, err);
+        if (rc) {
+            logmsg(0, "%s", err.c_str());
+            logmsg(0, "Unable to open assembly sequence file '%s'", o.in_seq_file.c_str());
+            return rc;
+        }
+        build_genome(entries, K, g);
+        entries.clear();
+        logmsg(2, "Genome containing %llu total nucleotides loaded with %llu subsequences of K-mer length %u...",
+               (unsigned long long)g.total_bases, (unsigned long long)g.num_subseqs, K);
+        const uint32_t plen = (uint32_t)g.concat.size();
+        flat.assign(plen, 0xff);
+        const auto t0 = std::chrono::steady_clock::now();
+        rc = k4b_hamm_targeted(sfx.seq.data(), sfx.seq.size(), g.concat.data(), plen, K, o.rhamm, o.crick ? 1 : 0, 0,
+                               plen, flat.data());
+        secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    } else {
+        // K-mers of the indexed assembly against the assembly itself (hammings.cpp:2311-2330)
+        for (const SfxEntry &e : sfx.entries) {
+            Chrom c;
+            c.name = e.name.substr(0, 80);
+            c.len = e.len;
+            c.start = (uint32_t)e.start;
+            c.num_subseqs = c.len >= K ? c.len - K + 1 : 0;
+            g.total_bases += c.len;
+            g.num_subseqs += c.num_subseqs;
+            g.chroms.push_back(std::move(c));
+        }
+        logmsg(2, "Targeted suffix genome has %zu sequences containing %llu total nucleotides, %llu sequences of at "
+                  "least K-mer length %u", sfx.entries.size(), (unsigned long long)g.total_bases,
+               (unsigned long long)g.num_subseqs, K);
+        flat.assign(sfx.seq.size(), 0xff);
+        const auto t0 = std::chrono::steady_clock::now();
+        rc = k4b_hamm_targeted(sfx.seq.data(), sfx.seq.size(), nullptr, 0, K, o.rhamm, o.crick ? 1 : 0, 0, 0,
+                               flat.data());
+        secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
-    Genome g;
-    build_genome(entries, K, g);
-    entries.clear();
-    logmsg(2, "Genome containing %llu total nucleotides loaded with %llu subsequences of K-mer length %u...",
-           (unsigned long long)g.total_bases, (unsigned long long)g.num_subseqs, K);
-
-    const uint32_t plen = (uint32_t)g.concat.size();
-    std::vector<uint8_t> flat(plen, 0xff);
-    const auto t0 = std::chrono::steady_clock::now();
-    rc = k4b_hamm_targeted(sfx.seq.data(), sfx.seq.size(), g.concat.data(), plen, K, o.rhamm, o.crick ? 1 : 0, 0,
-                           plen, flat.data());
-    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc) {
         logmsg(0, "Hamming engine failed (%d): %s", rc, k4b_last_error());
         return rc;

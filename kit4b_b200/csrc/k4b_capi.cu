@@ -599,7 +599,7 @@ extern "C" int k4b_hamm_targeted(const uint8_t *target_concat, uint64_t target_l
                                  const uint8_t *probe_concat, uint32_t probe_len, uint32_t K,
                                  int R, int both_strands, uint32_t q_begin, uint32_t q_end,
                                  uint8_t *out_h) {
-    if (!target_concat || !probe_concat || !out_h) return fail(K4B_ERR_PARAMS, "NULL buffer");
+    if (!target_concat || !out_h) return fail(K4B_ERR_PARAMS, "NULL buffer");
     RC(check_k(K, K4B_MIN_K, 500));  // SfxArray.cpp:4255
     if (R < 1 || R > 10) return fail(K4B_ERR_PARAMS, "R=%d outside 1..10", R);
     if (K / (uint32_t)(R + 1) < 4)  // hammings.cpp:399-404
@@ -609,6 +609,17 @@ extern "C" int k4b_hamm_targeted(const uint8_t *target_concat, uint64_t target_l
     // (SfxArray.cpp:4462-4463)
     const uint32_t core = K / (uint32_t)(R + 1);
     const uint32_t notfound = K / core;
+    if (!probe_concat) {
+        // probes are the K-mers of the indexed assembly itself (CSfxArray::LocateSfxHammings,
+        // SfxArray.cpp:4107-4220): exact self hits are skipped on the sense strand, the result
+        // is additionally capped at 20 (:4208-4209)
+        const uint32_t tl = (uint32_t)target_len;
+        if (q_end == 0 || q_end > tl) q_end = tl;
+        return run_sharded(target_concat, tl, nullptr, 0, K, both_strands, 1, q_begin, q_end,
+                           std::min(notfound, 20u), 1, [&](uint32_t pos, uint16_t v) {
+                               if (v <= K) out_h[pos] = (uint8_t)v;
+                           });
+    }
     if (q_end == 0 || q_end > probe_len) q_end = probe_len;
     return run_sharded(probe_concat, probe_len, target_concat, (uint32_t)target_len, K,
                        both_strands, 0, q_begin, q_end, notfound, 1,

@@ -383,7 +383,9 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_kernel(const AllPair
 #pragma unroll
                     for (int j = 0; j < Q; ++j) {
                         uint32_t d = kmer_dist<W, P, WILD>(qk[j][0], c);
-                        if (self_here && cpos == qpos[j]) d = kNoDist;
+                        // the reference skips only EXACT self hits (SfxArray.cpp:4418-4419,
+                        // :4585-4594); for identity comparison the self pair is always exact
+                        if (self_here && cpos == qpos[j] && d == 0) d = kNoDist;
                         if (CRICK) d = min(d, kmer_dist<W, P, WILD>(qk[j][1], c));
                         best[j] = min(best[j], d);
                     }
@@ -484,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_generic_kernel(const
         for (uint32_t s = 0; s < 32; ++s) {
             if (!((v >> s) & 1u)) continue;
             uint32_t d = acc[0][s];
-            if (self_here && ((g << 5) + s) == qpos) d = kNoDist;
+            if (self_here && ((g << 5) + s) == qpos && d == 0) d = kNoDist;
             if (CRICK) d = min(d, acc[S - 1][s]);
             best = min(best, d);
         }

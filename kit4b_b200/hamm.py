@@ -130,6 +130,11 @@ def targeted(target_concat, probe_concat, K: int, R: int, both_strands: bool, q_
              q_end: int = 0) -> np.ndarray:
     """Probe K-mers vs assembly (-m0 -I).  Returns uint8[len(probe_concat)], 0xFF where no K-mer starts."""
     t = _as_u8(target_concat)
+    if probe_concat is None:  # probes are the target's own K-mers (no -I)
+        out = np.full(len(t), 0xFF, dtype=np.uint8)
+        _check(load_lib().k4b_hamm_targeted(t.ctypes.data_as(_u8p), len(t), None, 0, K, R, int(both_strands),
+                                            q_begin, q_end, out.ctypes.data_as(_u8p)))
+        return out
     p = _as_u8(probe_concat)
     out = np.full(len(p), 0xFF, dtype=np.uint8)
     _check(load_lib().k4b_hamm_targeted(t.ctypes.data_as(_u8p), len(t), p.ctypes.data_as(_u8p), len(p), K, R,

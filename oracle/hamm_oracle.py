@@ -65,6 +65,8 @@ def lib():
         L.k4o_targeted_brute.argtypes = [u8p, ctypes.c_uint32, u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int,
                                          ctypes.c_int, u8p]
         L.k4o_targeted_brute.restype = None
+        L.k4o_targeted_self_brute.argtypes = [u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, u8p]
+        L.k4o_targeted_self_brute.restype = None
         _lib = L
     return _lib
 
@@ -165,6 +167,13 @@ def exhaustive_brute(concat: np.ndarray, K: int, both: bool, q_begin: int = 0, q
 def targeted_brute(target: np.ndarray, probes: np.ndarray, K: int, R: int, both: bool) -> np.ndarray:
     out = np.full(len(probes), 0xFF, dtype=np.uint8)
     lib().k4o_targeted_brute(_u8(target), len(target), _u8(probes), len(probes), K, R, int(both), _u8(out))
+    return out
+
+
+def targeted_self_brute(target: np.ndarray, K: int, R: int, both: bool) -> np.ndarray:
+    """no -I: the probes are the K-mers of the indexed assembly itself."""
+    out = np.full(len(target), 0xFF, dtype=np.uint8)
+    lib().k4o_targeted_self_brute(_u8(target), len(target), K, R, int(both), _u8(out))
     return out
 
 

@@ -144,11 +144,38 @@ def main_targeted(manifest):
     manifest["__targeted__"] = dict(target_fasta="targ.fa", sfx="targ.sfx", probes=probes, runs=runs)
 
 
+def main_targeted_self(manifest):
+    """-m0 without -I: K-mers of the indexed assembly against the assembly itself."""
+    rng = random.Random(61)
+    a = rnd(rng, 2500)
+    pal = "ACGTTGCATGCAACGTACGTTGCATGCAACGT"  # 32-mer equal to its own reverse complement
+    s1 = a[:800] + pal + a[800:1500] + "NNNNNNN" + a[1500:2000] + mutate(rng, a[100:400], 3) + a[2000:] + "N" + rnd(rng, 40)
+    s2 = rnd(rng, 300) + a[1000:1200] + rnd(rng, 100) + revcomp(mutate(rng, a[300:700], 5)) + rnd(rng, 200) + "AC-GT" + rnd(rng, 120)
+    s3 = mutate(rng, a[1700:1900], 1) + rnd(rng, 60)
+    tfa = os.path.join(HERE, "targs.fa")
+    sfx = os.path.join(HERE, "targs.sfx")
+    open(tfa, "w").write(fasta([("sA", s1), ("sB", s2), ("sC", s3)]))
+    subprocess.run([REF.replace("_nosleep", ""), "index", "-i", tfa, "-o", sfx, "-r", "targs", "-T2"], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    runs = []
+    for K, R, both, fmt in [(32, 3, True, 0), (25, 2, False, 0), (20, 1, True, 1), (50, 5, True, 2)]:
+        ext = ("csv", "bed", "wig")[fmt]
+        out = "targself.K%dr%d%s.%s" % (K, R, "c" if both else "w", ext)
+        args = [REF.replace("_nosleep", ""), "hammings", "-m0", "-K%d" % K, "-r%d" % R, "-S%d" % fmt, "-T2",
+                "-i", "targs.sfx", "-o", out]
+        if both:
+            args.insert(3, "-c")
+        subprocess.run(args, check=True, cwd=HERE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        runs.append(dict(K=K, R=R, both=both, fmt=fmt, out=out))
+    manifest["__targeted_self__"] = dict(target_fasta="targs.fa", sfx="targs.sfx", runs=runs)
+
+
 def main():
     if not os.access(REF, os.X_OK):
         sys.exit("reference binary missing: run oracle/build_ref.sh first")
     manifest = {}
     main_targeted(manifest)
+    main_targeted_self(manifest)
     for name, case in make_cases().items():
         fa = os.path.join(HERE, name + ".fa")
         seq = os.path.join(HERE, name + ".seq")

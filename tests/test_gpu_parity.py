@@ -228,3 +228,25 @@ def test_in_process_multi_gpu_shards(oracle):
     finally:
         k4b.gpu_shutdown()
         k4b.gpu_init(1)
+
+
+def _targeted_self_runs():
+    from conftest import golden_manifest
+    m = golden_manifest()["__targeted_self__"]
+    return [(m, r) for r in m["runs"]]
+
+
+@pytest.mark.parametrize("mr", _targeted_self_runs(), ids=lambda mr: mr[1]["out"])
+def test_cli_targeted_without_probe_file_equals_reference(oracle, mr, tmp_path):
+    """-m0 without -I: exact self hits skipped on the sense strand, wildcards, cap."""
+    m, r = mr
+    args = ["hammings", "-m0", "-K%d" % r["K"], "-r%d" % r["R"], "-S%d" % r["fmt"], "-i", os.path.join(GOLDEN, m["sfx"]),
+            "-o", r["out"]]
+    if r["both"]:
+        args.insert(2, "-c")
+    _run_cli(args, cwd=str(tmp_path))
+    assert open(os.path.join(str(tmp_path), r["out"]), "rb").read() == open(os.path.join(GOLDEN, r["out"]), "rb").read()
+    # and the array-level API against the oracle
+    _, tseq = oracle.read_sfx(os.path.join(GOLDEN, m["sfx"]))
+    assert np.array_equal(k4b.targeted(tseq, None, r["K"], r["R"], r["both"]),
+                          oracle.targeted_self_brute(tseq, r["K"], r["R"], r["both"]))

@@ -87,3 +87,18 @@ def test_targeted_oracle_matches_reference_output(oracle, mr):
     h = oracle.restricted_per_loci(chroms, oracle.targeted_brute(tseq, concat, r["K"], r["R"], r["both"]))
     rep = oracle.restricted_report(chroms, r["K"], r["R"], h, r["fmt"], out_name=r["out"])
     assert rep == open(os.path.join(GOLDEN, r["out"]), "rb").read()
+
+
+def _targeted_self_runs():
+    m = golden_manifest()["__targeted_self__"]
+    return [(m, r) for r in m["runs"]]
+
+
+@pytest.mark.parametrize("mr", _targeted_self_runs(), ids=lambda mr: mr[1]["out"])
+def test_targeted_self_oracle_matches_reference_output(oracle, mr):
+    """-m0 without -I (K-mers of the indexed assembly against itself)."""
+    m, r = mr
+    ents, tseq = oracle.read_sfx(os.path.join(GOLDEN, m["sfx"]))
+    h = oracle.restricted_per_loci(ents, oracle.targeted_self_brute(tseq, r["K"], r["R"], r["both"]))
+    rep = oracle.restricted_report(ents, r["K"], r["R"], h, r["fmt"], out_name=r["out"])
+    assert rep == open(os.path.join(GOLDEN, r["out"]), "rb").read()
