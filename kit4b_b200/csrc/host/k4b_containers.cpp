@@ -2,6 +2,8 @@
 // FASTA) and the concatenated genome layout.  Written from the on-disk formats documented in
 // SURVEY.md 8a (a2-a4, a15); see k4b_host.h for the reference loci each function mirrors.
 #include <errno.h>
+#include <math.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -310,6 +312,58 @@ void build_genome(const std::vector<SeqEntry> &entries, uint32_t K, Genome &g) {
         g.chroms.push_back(std::move(c));
     }
     g.genome_len = (uint32_t)g.concat.size() + 2;
+}
+
+
+// ---- sweep ranges ---------------------------------------------------------------------------------
+namespace {
+// work-balanced slice boundary L for node k of n (hammings.cpp:1516-1543): total work is
+// G*G (Crick) + G*G/2 (Watson); solve G*L + L*L/2 = k/n of it by fixed-point iteration.  The
+// float/double mix of the original arithmetic is kept because the integer result is printed
+// in the output header.
+uint32_t slice_boundary(uint32_t G, int k, int n) {
+    if (k < 1) return 0;
+    if (k == n) return G;
+    const double tot = ((double)G * G) + ((double)G * G) / 2;
+    const double want = (tot * k) / n;
+    double cur = sqrt((2.0f * k * tot) / n);
+    if (cur > G) cur = G;
+    double prev;
+    do {
+        prev = cur;
+        const double got = ((uint64_t)G * prev) + (prev * prev) / 2;
+        cur = (prev * want) / got;
+    } while (labs((long)(((int64_t)prev - (int64_t)cur))) > 1);
+    return (uint32_t)prev;
+}
+}  // namespace
+
+void node_sweep_range(uint32_t genome_len, uint32_t num_chroms, bool watson_only, int num_nodes, int node,
+                      uint32_t &sweep_start, uint32_t &sweep_end) {
+    uint32_t l1, l2;
+    if (!watson_only) {
+        l1 = slice_boundary(genome_len, node, num_nodes);
+        l2 = slice_boundary(genome_len, node - 1, num_nodes);
+    } else {
+        const uint64_t area = ((uint64_t)genome_len * (uint64_t)genome_len) / 2;
+        l1 = (uint32_t)sqrt((2.0f * node * area) / num_nodes);
+        l2 = (uint32_t)sqrt((2.0f * (node - 1) * area) / num_nodes) - 1;
+    }
+    uint32_t ss = genome_len - l1, se = genome_len - l2;
+    // allowance for the inter-chromosome markers plus a safety margin so slices overlap
+    if (ss > 2 * num_chroms) ss -= 2 * num_chroms;
+    else ss = 0;
+    se += 10 + 2 * num_chroms;
+    if (se > genome_len) se = genome_len;
+    if (ss > 10) ss -= 10;
+    else ss = 1;
+    sweep_start = ss;
+    sweep_end = se;
+}
+
+void single_sweep_range(uint32_t genome_len, uint32_t b, uint32_t B, uint32_t &sweep_start, uint32_t &sweep_end) {
+    sweep_start = b > genome_len ? genome_len : b;
+    sweep_end = B == 0 ? genome_len : (B > genome_len ? genome_len : B);
 }
 
 }  // namespace k4bhost

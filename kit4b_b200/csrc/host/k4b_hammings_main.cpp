@@ -79,9 +79,13 @@ static int run_exhaustive(const Options &o) {
     logmsg(2, "Genome containing %llu total nucleotides loaded with %llu subsequences of length %u...",
            (unsigned long long)g.total_bases, (unsigned long long)g.num_subseqs, K);
 
-    // single node: silently clamp the sweep range to the genome length (hammings.cpp:2690-2706)
-    uint32_t ss = (uint32_t)o.sweep_start > g.genome_len ? g.genome_len : (uint32_t)o.sweep_start;
-    uint32_t se = o.sweep_end == 0 ? g.genome_len : std::min((uint32_t)o.sweep_end, g.genome_len);
+    // -m1: -b/-B silently clamped to the genome length; -m2: work-balanced node slice
+    // (hammings.cpp:2660-2706)
+    uint32_t ss, se;
+    if (o.mode == 2)
+        node_sweep_range(g.genome_len, (uint32_t)g.chroms.size(), !o.crick, o.numnodes, o.node, ss, se);
+    else
+        single_sweep_range(g.genome_len, (uint32_t)o.sweep_start, (uint32_t)o.sweep_end, ss, se);
     logmsg(2, "Node sweep start is %u, and sweep end is %u", ss, se);
 
     if (!o.out_file.empty() && (rc = touch_output(o.out_file))) return rc;
@@ -384,16 +388,16 @@ int main(int argc, char **argv) {
     } else if (run.mode == 4 || run.mode == 5) {
         logmsg(0, "Error: the quick-load binary transforms (-m4/-m5) are not part of this build");
         rc = kErrParams;
-    } else if (run.mode == 2 || (run.mode == 1 && run.sample > 1)) {
-        logmsg(0, "Error: multi-node sweep slices (-m2) and sweep sampling (-k) are not part of this build; "
-                  "use -m1 with --gpus to shard one run over the GPUs of this box");
+    } else if ((run.mode == 1 || run.mode == 2) && run.sample > 1) {
+        logmsg(0, "Error: sweep sampling (-k) is not part of this build (log-only in the reference, and its result "
+                  "depends on -T)");
         rc = kErrParams;
     } else {
         rc = k4b_gpu_init(run.gpus, nullptr);
         if (rc) {
             logmsg(0, "Unable to initialise the GPU engine (%d): %s", rc, k4b_last_error());
         } else {
-            rc = run.mode == 1 ? run_exhaustive(run) : run_restricted(run);
+            rc = run.mode != 0 ? run_exhaustive(run) : run_restricted(run);
             k4b_gpu_shutdown();
         }
     }

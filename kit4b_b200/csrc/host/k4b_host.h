@@ -71,6 +71,13 @@ struct Genome {
 };
 void build_genome(const std::vector<SeqEntry> &entries, uint32_t K, Genome &g);
 
+// ---- sweep ranges (hammings.cpp:2660-2706) ------------------------------------------------------
+// -m2: the slice of sweep instances node `node` of `num_nodes` processes, widened so that
+// neighbouring slices overlap; -m1: the -b/-B values clamped to the genome length
+void node_sweep_range(uint32_t genome_len, uint32_t num_chroms, bool watson_only, int num_nodes, int node,
+                      uint32_t &sweep_start, uint32_t &sweep_end);
+void single_sweep_range(uint32_t genome_len, uint32_t b, uint32_t B, uint32_t &sweep_start, uint32_t &sweep_end);
+
 // ---- writers ---------------------------------------------------------------------------------
 // exhaustive CSV, literal restatement of hammings.cpp:2899-2929 (quirks included)
 int write_exhaustive_csv(const std::string &path, const Genome &g, uint32_t K, const uint16_t *hd,

@@ -104,6 +104,13 @@ int k4bh_fasta_to_bioseq(const char *fasta_path, const char *bioseq_path, const 
     return rc ? set_err(rc, err) : 0;
 }
 
+// sweep range of a -m2 node slice (num_nodes, node) or of -m1 -b/-B (num_nodes == 0: b, B)
+void k4bh_sweep_range(uint32_t genome_len, uint32_t num_chroms, int watson_only, int num_nodes, int node_or_b,
+                      uint32_t B, uint32_t *ss, uint32_t *se) {
+    if (num_nodes > 0) node_sweep_range(genome_len, num_chroms, watson_only != 0, num_nodes, node_or_b, *ss, *se);
+    else single_sweep_range(genome_len, (uint32_t)node_or_b, B, *ss, *se);
+}
+
 int k4bh_merge_csv(const char *from, const char *into) {
     std::string err;
     int rc = merge_hamming_csv(from, into, err);

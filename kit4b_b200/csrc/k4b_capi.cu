@@ -325,10 +325,25 @@ extern "C" float k4b_last_kernel_ms(void) {
     return ms;
 }
 
+struct SweepRange {  // see AllPairsParams
+    bool ranged = false;
+    long long w_lo = 0, w_hi = 0, c1_lo = 0, c1_hi = -1, c2_lo = 0, c2_hi = -1;
+};
+static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_strands,
+                         int self_exclude, uint32_t q_begin, uint32_t q_end, uint32_t clamp,
+                         const SweepRange &sweep, uint16_t *d_out_min, void *stream, int *launches);
+
 extern "C" int k4b_allpairs_min_device(k4b_packed *queries, k4b_packed *targets, int both_strands,
                                        int self_exclude, uint32_t q_begin, uint32_t q_end,
                                        uint32_t clamp, uint16_t *d_out_min, void *stream,
                                        int *launches) {
+    return allpairs_impl(queries, targets, both_strands, self_exclude, q_begin, q_end, clamp,
+                         SweepRange(), d_out_min, stream, launches);
+}
+
+static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_strands,
+                         int self_exclude, uint32_t q_begin, uint32_t q_end, uint32_t clamp,
+                         const SweepRange &sweep, uint16_t *d_out_min, void *stream, int *launches) {
     // clamp > 0 selects the targeted (-m0) rules: results capped at the "not found" value, probe
     // symbols >= N are wildcards, more than 4 of them report 0
     const bool targeted_rules = clamp > 0;
@@ -377,6 +392,10 @@ extern "C" int k4b_allpairs_min_device(k4b_packed *queries, k4b_packed *targets,
     prm.out = d_min32;
     prm.self_exclude = self_exclude ? 1 : 0;
     prm.wildcard = targeted_rules ? 1 : 0;
+    prm.ranged = sweep.ranged ? 1 : 0;
+    prm.w_lo = sweep.w_lo; prm.w_hi = sweep.w_hi;
+    prm.c1_lo = sweep.c1_lo; prm.c1_hi = sweep.c1_hi;
+    prm.c2_lo = sweep.c2_lo; prm.c2_hi = sweep.c2_hi;
     // enough CTAs for ~16 balanced waves on 148 SMs x 2 resident CTAs; never below one tile
     const uint32_t qpt = generic ? 1u : (uint32_t)queries_per_thread(W, three);
     const uint32_t qblocks = (nq + kThreads * qpt - 1) / (kThreads * qpt);
@@ -475,7 +494,7 @@ struct PhaseTrace {
 template <typename Sink>
 int run_sharded(const uint8_t *q_concat, uint32_t q_len, const uint8_t *t_concat, uint32_t t_len,
                 uint32_t K, int both, int self_ex, uint32_t q_begin, uint32_t q_end,
-                uint32_t clamp, int use_all_devices, Sink sink) {
+                uint32_t clamp, int use_all_devices, const SweepRange &sweep, Sink sink) {
     RC(ensure_init());
     const int n = use_all_devices ? (int)g_eng.devs.size() : 1;
     if (q_end > q_len) q_end = q_len;
@@ -532,8 +551,8 @@ int run_sharded(const uint8_t *q_concat, uint32_t q_len, const uint8_t *t_concat
                 rc = fail(cuda_code(e), "shard buffers: %s", cudaGetErrorString(e));
                 break;
             }
-            rc = k4b_allpairs_min_device(j.q, j.t, both, self_ex, j.q_begin, j.q_end, clamp,
-                                         j.d_out, g_eng.streams[i], nullptr);
+            rc = allpairs_impl(j.q, j.t, both, self_ex, j.q_begin, j.q_end, clamp, sweep, j.d_out,
+                               g_eng.streams[i], nullptr);
             if (rc) break;
             e = cudaMemcpyAsync(j.h_out, j.d_out, (size_t)nq * 2, cudaMemcpyDeviceToHost,
                                 g_eng.streams[i]);
@@ -560,14 +579,31 @@ int run_sharded(const uint8_t *q_concat, uint32_t q_len, const uint8_t *t_concat
     return rc;
 }
 
-int check_full_sweep(uint32_t concat_len, uint32_t K, uint32_t sweep_start, uint32_t sweep_end) {
-    // Watson offsets s in [start,end] with s <= len-K, Crick offsets s-1 (hammings.cpp:924-928):
-    // start==1 and end >= len+1-K select every pair.  Sub-ranges (-b/-B, -m2) are a "next" row.
-    const uint32_t need_end = concat_len + 1 > K ? concat_len + 1 - K : 0;
-    if (sweep_start != 1 || (sweep_end != 0 && sweep_end < need_end))
-        return fail(K4B_ERR_UNSUPPORTED,
-                    "partial sweep %u..%u is not supported yet (full sweep is 1..%u)", sweep_start,
-                    sweep_end, concat_len + 2);
+// Pair sets selected by sweep instances SSeqStart..SSeqEnd (hammings.cpp:883-939): Watson
+// offset s for SSeqStart <= s <= min(SSeqEnd, len-K); Crick offset s-1, which walks the
+// anti-diagonal c = len-1-(s-1) and, for s-1 >= 1, after wrapping also c = 2len-K-(s-1)
+// (hammings.cpp:3345-3347, :3410-3415).  The full range selects every pair.
+int make_sweep(uint32_t len, uint32_t K, uint32_t sweep_start, uint32_t sweep_end, SweepRange &r) {
+    r = SweepRange();
+    if (sweep_start == 0) return fail(K4B_ERR_PARAMS, "sweep start must be >= 1");
+    const long long L = len, k = K;
+    long long se = sweep_end == 0 ? L + 2 : (long long)sweep_end;
+    const long long ss = sweep_start;
+    const bool full = ss == 1 && se >= L + 1 - k;
+    if (full || L < k) return 0;
+    r.ranged = true;
+    r.w_lo = ss;
+    r.w_hi = std::min(se, L - k);
+    const long long sp_lo = ss - 1, sp_hi = std::min(se, L + 1 - k) - 1;
+    if (sp_hi >= sp_lo) {
+        r.c1_lo = L - 1 - sp_hi;
+        r.c1_hi = L - 1 - sp_lo;
+        const long long lo2 = std::max(sp_lo, 1LL);
+        if (sp_hi >= lo2) {
+            r.c2_lo = 2 * L - k - sp_hi;
+            r.c2_hi = 2 * L - k - lo2;
+        }
+    }
     return 0;
 }
 }  // namespace
@@ -578,7 +614,7 @@ extern "C" int k4b_hamm_exhaustive_shard(const uint8_t *concat, uint32_t concat_
     if (!concat || !out_min) return fail(K4B_ERR_PARAMS, "NULL buffer");
     RC(check_k(K, K4B_MIN_K, K4B_MAX_K));
     return run_sharded(concat, concat_len, nullptr, 0, K, both_strands, 1, q_begin, q_end, 0, 0,
-                       [&](uint32_t pos, uint16_t v) {
+                       SweepRange(), [&](uint32_t pos, uint16_t v) {
                            if (v <= K && v < out_min[pos]) out_min[pos] = v;
                        });
 }
@@ -588,9 +624,10 @@ extern "C" int k4b_hamm_exhaustive(const uint8_t *concat, uint32_t concat_len, u
                                    uint16_t *out_min) {
     if (!concat || !out_min) return fail(K4B_ERR_PARAMS, "NULL buffer");
     RC(check_k(K, K4B_MIN_K, K4B_MAX_K));
-    RC(check_full_sweep(concat_len, K, sweep_start, sweep_end));
+    SweepRange sweep;
+    RC(make_sweep(concat_len, K, sweep_start, sweep_end, sweep));
     return run_sharded(concat, concat_len, nullptr, 0, K, both_strands, 1, 0, concat_len, 0, 1,
-                       [&](uint32_t pos, uint16_t v) {
+                       sweep, [&](uint32_t pos, uint16_t v) {
                            if (v <= K && v < out_min[pos]) out_min[pos] = v;
                        });
 }
@@ -616,13 +653,13 @@ extern "C" int k4b_hamm_targeted(const uint8_t *target_concat, uint64_t target_l
         const uint32_t tl = (uint32_t)target_len;
         if (q_end == 0 || q_end > tl) q_end = tl;
         return run_sharded(target_concat, tl, nullptr, 0, K, both_strands, 1, q_begin, q_end,
-                           std::min(notfound, 20u), 1, [&](uint32_t pos, uint16_t v) {
+                           std::min(notfound, 20u), 1, SweepRange(), [&](uint32_t pos, uint16_t v) {
                                if (v <= K) out_h[pos] = (uint8_t)v;
                            });
     }
     if (q_end == 0 || q_end > probe_len) q_end = probe_len;
     return run_sharded(probe_concat, probe_len, target_concat, (uint32_t)target_len, K,
-                       both_strands, 0, q_begin, q_end, notfound, 1,
+                       both_strands, 0, q_begin, q_end, notfound, 1, SweepRange(),
                        [&](uint32_t pos, uint16_t v) {
                            if (v <= K) out_h[pos] = (uint8_t)v;
                        });

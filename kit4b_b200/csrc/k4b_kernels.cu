@@ -280,7 +280,7 @@ __device__ __forceinline__ void cut_candidate(const uint32_t (&cw)[P][W + 1], ui
     }
 }
 
-template <int W, int P, int Q, bool CRICK, bool WILD>
+template <int W, int P, int Q, bool CRICK, bool WILD, bool RANGED>
 __global__ void __launch_bounds__(kThreads, 2) allpairs_min_kernel(const AllPairsParams prm) {
     constexpr int S = CRICK ? 2 : 1;
     constexpr int NARR = P + 1;  // planes + valid
@@ -358,7 +358,19 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_kernel(const AllPair
                 for (int w = 0; w <= W; ++w) cw[p][w] = tile[st][p][g + w];
             const uint32_t gabs = gabs0 + g;
             const bool self_here = prm.self_exclude && gabs >= qg_lo && gabs <= qg_hi;
-            if (v == 0xffffffffu && !self_here) {
+            if (RANGED) {
+                // sub-range sweeps: skip groups no query of this CTA can pair with
+                const long long t0 = (long long)gabs << 5, t1 = t0 + 31;
+                const long long qlo = qbase, qhi = (long long)qbase + kThreads * Q - 1;
+                const long long kk = (long long)K - 1;
+                bool any = (t1 >= qlo + prm.w_lo && t0 <= qhi + prm.w_hi) ||
+                           (t1 >= qlo - prm.w_hi && t0 <= qhi - prm.w_lo);
+                if (CRICK)
+                    any = any || (t1 >= prm.c1_lo - kk - qhi && t0 <= prm.c1_hi - kk - qlo) ||
+                          (t1 >= prm.c2_lo - kk - qhi && t0 <= prm.c2_hi - kk - qlo);
+                if (!any) continue;
+            }
+            if (!RANGED && v == 0xffffffffu && !self_here) {
                 // fast path: 32 valid candidates, no self pair possible
 #pragma unroll 4
                 for (uint32_t s = 0; s < 32; ++s) {
@@ -386,7 +398,20 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_kernel(const AllPair
                         // the reference skips only EXACT self hits (SfxArray.cpp:4418-4419,
                         // :4585-4594); for identity comparison the self pair is always exact
                         if (self_here && cpos == qpos[j] && d == 0) d = kNoDist;
-                        if (CRICK) d = min(d, kmer_dist<W, P, WILD>(qk[j][1], c));
+                        if (RANGED) {
+                            const long long dl = (long long)cpos - (long long)qpos[j];
+                            const long long ad = dl < 0 ? -dl : dl;
+                            if (ad < prm.w_lo || ad > prm.w_hi) d = kNoDist;
+                        }
+                        if (CRICK) {
+                            uint32_t dr = kmer_dist<W, P, WILD>(qk[j][1], c);
+                            if (RANGED) {
+                                const long long cc = (long long)cpos + (long long)qpos[j] + K - 1;
+                                if (!((cc >= prm.c1_lo && cc <= prm.c1_hi) || (cc >= prm.c2_lo && cc <= prm.c2_hi)))
+                                    dr = kNoDist;
+                            }
+                            d = min(d, dr);
+                        }
                         best[j] = min(best[j], d);
                     }
                 }
@@ -486,8 +511,21 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_generic_kernel(const
         for (uint32_t s = 0; s < 32; ++s) {
             if (!((v >> s) & 1u)) continue;
             uint32_t d = acc[0][s];
-            if (self_here && ((g << 5) + s) == qpos && d == 0) d = kNoDist;
-            if (CRICK) d = min(d, acc[S - 1][s]);
+            const uint32_t cpos = (g << 5) + s;
+            if (self_here && cpos == qpos && d == 0) d = kNoDist;
+            if (prm.ranged) {
+                const long long dl = (long long)cpos - (long long)qpos;
+                const long long ad = dl < 0 ? -dl : dl;
+                if (ad < prm.w_lo || ad > prm.w_hi) d = kNoDist;
+            }
+            if (CRICK) {
+                uint32_t dr = acc[S - 1][s];
+                if (prm.ranged) {
+                    const long long cc = (long long)cpos + (long long)qpos + K - 1;
+                    if (!((cc >= prm.c1_lo && cc <= prm.c1_hi) || (cc >= prm.c2_lo && cc <= prm.c2_hi))) dr = kNoDist;
+                }
+                d = min(d, dr);
+            }
             best = min(best, d);
         }
     }
@@ -558,12 +596,15 @@ cudaError_t launch_finalize(const uint32_t *d_min32, ImageView q, uint32_t q_beg
 template <int W, int P, int Q>
 static cudaError_t launch_ap(const AllPairsParams &p, bool crick, dim3 grid, cudaStream_t st) {
     const bool wild = P == 3 && p.wildcard;
-    if (wild) {
-        if (crick) allpairs_min_kernel<W, P, Q, true, (P == 3)><<<grid, kThreads, 0, st>>>(p);
-        else allpairs_min_kernel<W, P, Q, false, (P == 3)><<<grid, kThreads, 0, st>>>(p);
+    if (p.ranged) {  // sub-range sweeps exist only in exhaustive (identity) mode
+        if (crick) allpairs_min_kernel<W, P, Q, true, false, true><<<grid, kThreads, 0, st>>>(p);
+        else allpairs_min_kernel<W, P, Q, false, false, true><<<grid, kThreads, 0, st>>>(p);
+    } else if (wild) {
+        if (crick) allpairs_min_kernel<W, P, Q, true, (P == 3), false><<<grid, kThreads, 0, st>>>(p);
+        else allpairs_min_kernel<W, P, Q, false, (P == 3), false><<<grid, kThreads, 0, st>>>(p);
     } else {
-        if (crick) allpairs_min_kernel<W, P, Q, true, false><<<grid, kThreads, 0, st>>>(p);
-        else allpairs_min_kernel<W, P, Q, false, false><<<grid, kThreads, 0, st>>>(p);
+        if (crick) allpairs_min_kernel<W, P, Q, true, false, false><<<grid, kThreads, 0, st>>>(p);
+        else allpairs_min_kernel<W, P, Q, false, false, false><<<grid, kThreads, 0, st>>>(p);
     }
     return cudaGetLastError();
 }

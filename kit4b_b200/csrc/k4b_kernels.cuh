@@ -43,6 +43,11 @@ struct AllPairsParams {
     uint32_t *out;           // [q_end-q_begin] running minima (pre-set to K+1)
     int self_exclude;        // skip forward pair with query pos == target pos
     int wildcard;            // targeted mode: query symbols >= N match any target ACGT base
+    // sweep sub-range (-b/-B, -m2 slices; hammings.cpp:924-928): a forward pair (q,t) counts iff
+    // w_lo <= |q-t| <= w_hi, a reverse-complement pair iff c = q+t+K-1 lies in [c1_lo,c1_hi] or
+    // [c2_lo,c2_hi] (the two anti-diagonals one Crick sweep offset covers)
+    int ranged;
+    long long w_lo, w_hi, c1_lo, c1_hi, c2_lo, c2_hi;
 };
 
 // host-callable launchers (defined in k4b_kernels.cu)

@@ -38,6 +38,9 @@ def load():
         L.k4bh_read_sfx.restype = ctypes.c_long
         L.k4bh_read_sfx.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
         L.k4bh_fasta_to_bioseq.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
+        L.k4bh_sweep_range.restype = None
+        L.k4bh_sweep_range.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
         L.k4bh_merge_csv.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
         L.k4bh_parse_cli.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_int),
                                      ctypes.c_char_p]
@@ -94,6 +97,13 @@ def read_sfx(path: str):
 
 def fasta_to_bioseq(fasta: str, bioseq: str, title: str = "k4b"):
     _check(load().k4bh_fasta_to_bioseq(fasta.encode(), bioseq.encode(), title.encode()))
+
+
+def node_sweep_range(genome_len: int, num_chroms: int, watson_only: bool, num_nodes: int, node: int):
+    """(SSeqStart, SSeqEnd) of a -m2 node slice."""
+    a, b = ctypes.c_uint32(0), ctypes.c_uint32(0)
+    load().k4bh_sweep_range(genome_len, num_chroms, int(watson_only), num_nodes, node, 0, ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
 
 
 def merge_csv(src: str, into: str):

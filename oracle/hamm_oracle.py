@@ -67,6 +67,9 @@ def lib():
         L.k4o_targeted_brute.restype = None
         L.k4o_targeted_self_brute.argtypes = [u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, u8p]
         L.k4o_targeted_self_brute.restype = None
+        L.k4o_exhaustive_sliding_sweep.argtypes = [u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, u16p,
+                                                   ctypes.c_uint32, ctypes.c_uint32]
+        L.k4o_exhaustive_sliding_sweep.restype = None
         _lib = L
     return _lib
 
@@ -146,6 +149,14 @@ def exhaustive_sliding(concat: np.ndarray, K: int, both: bool, threads: int = 0)
     hd = np.full(len(concat), K + 1, dtype=np.uint16)
     if len(concat):
         lib().k4o_exhaustive_sliding(_u8(concat), len(concat), K, int(both), _u16(hd), threads or os.cpu_count() or 1)
+    return hd
+
+
+def exhaustive_sliding_sweep(concat: np.ndarray, K: int, both: bool, sweep_start: int, sweep_end: int) -> np.ndarray:
+    """Only the pairs visited by sweep instances sweep_start..sweep_end (-b/-B, -m2)."""
+    hd = np.full(len(concat), K + 1, dtype=np.uint16)
+    if len(concat):
+        lib().k4o_exhaustive_sliding_sweep(_u8(concat), len(concat), K, int(both), _u16(hd), sweep_start, sweep_end)
     return hd
 
 

@@ -170,12 +170,35 @@ def main_targeted_self(manifest):
     manifest["__targeted_self__"] = dict(target_fasta="targs.fa", sfx="targs.sfx", runs=runs)
 
 
+def main_sweeps(manifest):
+    """-m1 with -b/-B sub-ranges and -m2 node slices on the adversarial genome."""
+    seq = "adversarial.seq"
+    runs = []
+    for K, both, b, B in [(12, True, 1, 50), (12, True, 37, 400), (12, False, 5, 5), (16, True, 300, 0),
+                          (12, True, 1000, 1300), (12, True, 1, 1), (33, True, 2, 900)]:
+        out = "sweep.K%d%s.b%dB%d.csv" % (K, "c" if both else "w", b, B)
+        args = [REF, "hammings", "-m1", "-K%d" % K, "-T3", "-b%d" % b, "-B%d" % B, "-i", seq, "-o", out]
+        if both:
+            args.insert(3, "-c")
+        subprocess.run(args, check=True, cwd=HERE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        runs.append(dict(mode=1, K=K, both=both, b=b, B=B, csv=out))
+    for K, both, n, N in [(12, True, 3, 1), (12, True, 3, 2), (12, True, 3, 3), (12, False, 4, 2), (16, True, 2, 1)]:
+        out = "slice.K%d%s.n%dN%d.csv" % (K, "c" if both else "w", n, N)
+        args = [REF, "hammings", "-m2", "-K%d" % K, "-T3", "-n%d" % n, "-N%d" % N, "-i", seq, "-o", out]
+        if both:
+            args.insert(3, "-c")
+        subprocess.run(args, check=True, cwd=HERE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        runs.append(dict(mode=2, K=K, both=both, n=n, N=N, csv=out))
+    manifest["__sweeps__"] = dict(bioseq=seq, runs=runs)
+
+
 def main():
     if not os.access(REF, os.X_OK):
         sys.exit("reference binary missing: run oracle/build_ref.sh first")
     manifest = {}
     main_targeted(manifest)
     main_targeted_self(manifest)
+    main_sweeps(manifest)
     for name, case in make_cases().items():
         fa = os.path.join(HERE, name + ".fa")
         seq = os.path.join(HERE, name + ".seq")

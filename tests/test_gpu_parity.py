@@ -250,3 +250,33 @@ def test_cli_targeted_without_probe_file_equals_reference(oracle, mr, tmp_path):
     _, tseq = oracle.read_sfx(os.path.join(GOLDEN, m["sfx"]))
     assert np.array_equal(k4b.targeted(tseq, None, r["K"], r["R"], r["both"]),
                           oracle.targeted_self_brute(tseq, r["K"], r["R"], r["both"]))
+
+
+def _sweep_runs():
+    from conftest import golden_manifest
+    m = golden_manifest()["__sweeps__"]
+    return [(m, r) for r in m["runs"]]
+
+
+@pytest.mark.parametrize("mr", _sweep_runs(), ids=lambda mr: mr[1]["csv"])
+def test_cli_sweep_subranges_and_node_slices_equal_reference(mr, tmp_path):
+    m, r = mr
+    out = str(tmp_path / "o.csv")
+    args = ["hammings", "-m%d" % r["mode"], "-K%d" % r["K"], "-i", os.path.join(GOLDEN, m["bioseq"]), "-o", out]
+    args += ["-b%d" % r["b"], "-B%d" % r["B"]] if r["mode"] == 1 else ["-n%d" % r["n"], "-N%d" % r["N"]]
+    if r["both"]:
+        args.insert(2, "-c")
+    _run_cli(args)
+    assert open(out, "rb").read() == open(os.path.join(GOLDEN, r["csv"]), "rb").read()
+
+
+def test_sweep_subranges_match_oracle_on_seeded_inputs(oracle):
+    for seed, lens, K, both, ss, se in [(701, [6000, 3000], 25, True, 1, 100), (702, [9000], 50, True, 4000, 6000),
+                                        (703, [5000, 40, 2500], 100, True, 2, 0), (704, [7000], 32, False, 10, 10),
+                                        (705, [3000, 3000], 150, True, 100, 2500), (706, [4000], 25, True, 3990, 0)]:
+        c = random_genome(seed, lens)
+        glen = len(c) + 2
+        end = glen if se == 0 else se
+        want = oracle.exhaustive_sliding_sweep(c, K, both, ss, end)
+        got = k4b.exhaustive(c, K, both, ss, se)
+        assert np.array_equal(got, want), (seed, K, ss, se)

@@ -102,3 +102,38 @@ def test_targeted_self_oracle_matches_reference_output(oracle, mr):
     h = oracle.restricted_per_loci(ents, oracle.targeted_self_brute(tseq, r["K"], r["R"], r["both"]))
     rep = oracle.restricted_report(ents, r["K"], r["R"], h, r["fmt"], out_name=r["out"])
     assert rep == open(os.path.join(GOLDEN, r["out"]), "rb").read()
+
+
+def _sweep_runs():
+    m = golden_manifest()["__sweeps__"]
+    return [(m, r) for r in m["runs"]]
+
+
+def _sweep_range(r, glen, nchroms):
+    from kit4b_b200 import hostlib
+    if r["mode"] == 2:
+        return hostlib.node_sweep_range(glen, nchroms, not r["both"], r["n"], r["N"])
+    return min(r["b"], glen), (glen if r["B"] == 0 else min(r["B"], glen))
+
+
+@pytest.mark.parametrize("mr", _sweep_runs(), ids=lambda mr: mr[1]["csv"])
+def test_sweep_subranges_and_node_slices_match_reference_output(oracle, mr):
+    """-b/-B sub-ranges and -m2 slices: oracle pair selection + host range arithmetic."""
+    m, r = mr
+    concat, chroms, glen = oracle.concat_entries(oracle.read_bioseq(os.path.join(GOLDEN, m["bioseq"])))
+    ss, se = _sweep_range(r, glen, len(chroms))
+    hd = oracle.exhaustive_sliding_sweep(concat, r["K"], r["both"], ss, se)
+    assert oracle.exhaustive_csv(glen, chroms, r["K"], hd, ss, se) == open(os.path.join(GOLDEN, r["csv"]), "rb").read()
+
+
+def test_merged_node_slices_equal_the_single_node_run(tmp_path):
+    """-m2 slices folded together with -m3 reproduce the -m1 values (the reference's multi-node flow)."""
+    import shutil
+    from kit4b_b200 import hostlib
+    into = str(tmp_path / "merged.csv")
+    shutil.copyfile(os.path.join(GOLDEN, "slice.K12c.n3N1.csv"), into)
+    for n in (2, 3):
+        hostlib.merge_csv(os.path.join(GOLDEN, "slice.K12c.n3N%d.csv" % n), into)
+    merged = open(into).read().split("\n")[1:]
+    full = open(os.path.join(GOLDEN, "adversarial.K12c.csv")).read().strip("\n").split("\n")[1:]
+    assert merged == full
