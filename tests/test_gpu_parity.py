@@ -280,3 +280,23 @@ def test_sweep_subranges_match_oracle_on_seeded_inputs(oracle):
         want = oracle.exhaustive_sliding_sweep(c, K, both, ss, end)
         got = k4b.exhaustive(c, K, both, ss, se)
         assert np.array_equal(got, want), (seed, K, ss, se)
+
+
+def test_config1_full_output_md5_equals_reference_run(tmp_path):
+    """BASELINE.json configs[0] / BASELINE.md: 1 Mbp genome (Python random seed 12), K=25, both
+    strands.  The unmodified reference needed 36 min on 8 cores for this file; its output md5 and
+    the md5 of the input FASTA are recorded in BASELINE.md.  Same flags in, same bytes out."""
+    import hashlib
+    import random
+    from kit4b_b200 import hostlib
+    random.seed(12)
+    s = "".join(random.choices("ACGT", k=1_000_000))
+    fa = ">chr1 synthetic\n" + "".join(s[i:i + 80] + "\n" for i in range(0, len(s), 80))
+    assert hashlib.md5(fa.encode()).hexdigest() == "e02b7eebf84f54c2c205567402029947"
+    fa_path, seq, out = str(tmp_path / "g.fa"), str(tmp_path / "g.seq"), str(tmp_path / "out.csv")
+    open(fa_path, "w").write(fa)
+    hostlib.fasta_to_bioseq(fa_path, seq, "cfg1")
+    _run_cli(["hammings", "-m1", "-K25", "-c", "-T8", "-i", seq, "-o", out])
+    data = open(out, "rb").read()
+    assert len(data) == 15_888_524 and data.count(b"\n") == 999_977
+    assert hashlib.md5(data).hexdigest() == "f1b2e85a8f64dc68dcc60cc2403cfb1a"
