@@ -386,8 +386,8 @@ int main(int argc, char **argv) {
         rc = merge_hamming_csv(run.in_file, run.out_file, err);
         if (rc) logmsg(0, "Merge failed: %s", err.c_str());
     } else if (run.mode == 4 || run.mode == 5) {
-        logmsg(0, "Error: the quick-load binary transforms (-m4/-m5) are not part of this build");
-        rc = kErrParams;
+        rc = run.mode == 4 ? csv_to_bham(run.in_file, run.out_file, err) : bham_to_csv(run.in_file, run.out_file, err);
+        if (rc) logmsg(0, "Transform failed: %s", err.c_str());
     } else if ((run.mode == 1 || run.mode == 2) && run.sample > 1) {
         logmsg(0, "Error: sweep sampling (-k) is not part of this build (log-only in the reference, and its result "
                   "depends on -T)");

@@ -97,6 +97,15 @@ int write_restricted_wiggle(const std::string &path, const std::vector<RChrom> &
 // -m3: line-wise minimum of two exhaustive CSVs (hammings.cpp:1126-1343)
 int merge_hamming_csv(const std::string &from, const std::string &into, std::string &err);
 
+// -m4 / -m5: exhaustive CSV <-> 'bham' quick-load binary (hammings.cpp:79-92, :941-1066,
+// :1345-1514).  The layout (pack(1) header with magic 'bham', version 1, <= 1000 chromosome
+// offsets; per chromosome id, 81-byte name, NumEls, uint16 distances) is the reference's, but
+// lengths and offsets are computed correctly here: the reference advances its length by ONE
+// byte per 2-byte distance (hammings.cpp:1464), so its own files are truncated, overlap
+// chromosomes and carry uninitialised heap bytes - they are not reproducible even by itself.
+int csv_to_bham(const std::string &csv, const std::string &bham, std::string &err);
+int bham_to_csv(const std::string &bham, const std::string &csv, std::string &err);
+
 // ---- CLI ----------------------------------------------------------------------------------------
 struct Options {
     int mode = 0;            // -m (default 0 = restricted, hammings.cpp:312)

@@ -117,6 +117,17 @@ int k4bh_merge_csv(const char *from, const char *into) {
     return rc ? set_err(rc, err) : 0;
 }
 
+int k4bh_csv_to_bham(const char *csv, const char *bham) {
+    std::string err;
+    int rc = csv_to_bham(csv, bham, err);
+    return rc ? set_err(rc, err) : 0;
+}
+int k4bh_bham_to_csv(const char *bham, const char *csv) {
+    std::string err;
+    int rc = bham_to_csv(bham, csv, err);
+    return rc ? set_err(rc, err) : 0;
+}
+
 // parses a command line (argv[0] = program); fills ints[0..15] and strs (4 x 512 chars:
 // in, inseq, out, prefix).  Returns 0, or -1 with k4bh_last_error() set.
 int k4bh_parse_cli(int argc, char **argv, int *ints, char *strs) {

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <fstream>
+#include <iterator>
 
 #include "k4b_host.h"
 
@@ -350,6 +351,126 @@ int merge_hamming_csv(const std::string &from, const std::string &into, std::str
         }
     }
     return kOk;
+}
+
+
+// ---- -m4 / -m5 quick-load binary -----------------------------------------------------------------
+namespace {
+constexpr size_t kBhamMaxChroms = 1000;
+constexpr size_t kBhamHdrSize = 4 + 4 + 4 + 2 + 4 * kBhamMaxChroms;  // tsHHamHdr, pack(1)
+constexpr size_t kBhamChromFixed = 4 + 81 + 4;                       // tsHHamChrom before Dists
+}  // namespace
+
+int csv_to_bham(const std::string &csv, const std::string &bham, std::string &err) {
+    std::ifstream in(csv);
+    if (!in) {
+        err = "unable to open '" + csv + "'";
+        return kErrOpnFile;
+    }
+    struct ChromBlock {
+        std::string name;
+        std::vector<uint16_t> dists;
+    };
+    std::vector<ChromBlock> blocks;
+    std::string line;
+    while (next_line(in, line)) {
+        const CsvRow r = parse_row(line);
+        if (r.nfields < 3) {
+            err = "expected at least 3 fields per line in '" + csv + "'";
+            return kErrParse;
+        }
+        if (!r.ok) continue;  // descriptor rows
+        if (blocks.empty() || strcasecmp(blocks.back().name.c_str(), r.chrom.c_str()) != 0) {
+            if (blocks.size() == kBhamMaxChroms) {
+                err = "more than 1000 chromosomes";
+                return kErrParams;
+            }
+            blocks.push_back(ChromBlock{r.chrom.substr(0, 80), {}});
+        }
+        if (r.loci != (long)blocks.back().dists.size()) {  // loci must ascend without gaps
+            err = "Hamming loci are not monotonically ascending in '" + csv + "'";
+            return kErrParse;
+        }
+        blocks.back().dists.push_back((uint16_t)r.dist);
+    }
+    std::vector<uint8_t> img(kBhamHdrSize, 0);
+    memcpy(img.data(), "bham", 4);
+    const uint32_t version = 1;
+    memcpy(img.data() + 4, &version, 4);
+    const uint16_t nch = (uint16_t)blocks.size();
+    memcpy(img.data() + 12, &nch, 2);
+    for (size_t c = 0; c < blocks.size(); ++c) {
+        const uint32_t ofs = (uint32_t)img.size();
+        memcpy(img.data() + 14 + 4 * c, &ofs, 4);
+        const uint32_t id = (uint32_t)c + 1, nels = (uint32_t)blocks[c].dists.size();
+        img.resize(img.size() + kBhamChromFixed + 2 * (size_t)nels, 0);
+        uint8_t *p = img.data() + ofs;
+        memcpy(p, &id, 4);
+        memcpy(p + 4, blocks[c].name.c_str(), blocks[c].name.size());
+        memcpy(p + 4 + 81, &nels, 4);
+        if (nels) memcpy(p + kBhamChromFixed, blocks[c].dists.data(), 2 * (size_t)nels);
+    }
+    if (img.size() > 0x7fffffffu) {
+        err = "Hammings do not fit the 31-bit length field of the bham header";
+        return kErrParams;
+    }
+    const int32_t len = (int32_t)img.size();
+    memcpy(img.data() + 8, &len, 4);
+    Out out;
+    int rc = out.open_trunc(bham, err);
+    if (rc) return rc;
+    out.put((const char *)img.data(), img.size());
+    return out.close_sync(err);
+}
+
+int bham_to_csv(const std::string &bham, const std::string &csv, std::string &err) {
+    std::ifstream in(bham, std::ios::binary);
+    if (!in) {
+        err = "unable to open '" + bham + "'";
+        return kErrOpnFile;
+    }
+    std::vector<uint8_t> img((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    if (img.size() < kBhamHdrSize) {
+        err = "'" + bham + "' is too short to be a bham file";
+        return kErrParse;
+    }
+    if (memcmp(img.data(), "bham", 4) != 0) {
+        err = "'" + bham + "' is not a bham file";
+        return kErrFileType;
+    }
+    uint16_t nch;
+    memcpy(&nch, img.data() + 12, 2);
+    if (nch < 1 || nch > kBhamMaxChroms) {
+        err = "bham file holds no chromosomes";
+        return -59;  // eBSFerrNoEntries
+    }
+    Out out;
+    int rc = out.open_trunc(csv, err);
+    if (rc) return rc;
+    out.put("\"Chrom\",\"Loci\",\"Hamming\"\n");
+    char line[256];
+    for (uint16_t c = 0; c < nch; ++c) {
+        uint32_t ofs, nels;
+        memcpy(&ofs, img.data() + 14 + 4 * (size_t)c, 4);
+        if ((size_t)ofs + kBhamChromFixed > img.size()) {
+            err = "corrupt bham chromosome offset";
+            return kErrParse;
+        }
+        memcpy(&nels, img.data() + ofs + 4 + 81, 4);
+        if ((size_t)ofs + kBhamChromFixed + 2 * (size_t)nels > img.size()) {
+            err = "bham chromosome data lies outside the file";
+            return kErrParse;
+        }
+        const char *name = (const char *)img.data() + ofs + 4;
+        const std::string nm(name, strnlen(name, 81));
+        for (uint32_t l = 0; l < nels; ++l) {
+            uint16_t d;
+            memcpy(&d, img.data() + ofs + kBhamChromFixed + 2 * (size_t)l, 2);
+            const int n = snprintf(line, sizeof(line), "\"%s\",%d,%d\n", nm.c_str(), (int)l, (int)d);
+            out.put(line, (size_t)n);
+        }
+    }
+    return out.close_sync(err);
 }
 
 }  // namespace k4bhost

@@ -42,6 +42,8 @@ def load():
         L.k4bh_sweep_range.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
         L.k4bh_merge_csv.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+        L.k4bh_csv_to_bham.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+        L.k4bh_bham_to_csv.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
         L.k4bh_parse_cli.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_int),
                                      ctypes.c_char_p]
         _lib = L
@@ -108,6 +110,14 @@ def node_sweep_range(genome_len: int, num_chroms: int, watson_only: bool, num_no
 
 def merge_csv(src: str, into: str):
     _check(load().k4bh_merge_csv(src.encode(), into.encode()))
+
+
+def csv_to_bham(csv: str, bham: str):
+    _check(load().k4bh_csv_to_bham(csv.encode(), bham.encode()))
+
+
+def bham_to_csv(bham: str, csv: str):
+    _check(load().k4bh_bham_to_csv(bham.encode(), csv.encode()))
 
 
 CLI_INT_FIELDS = ("mode", "sensitivity", "resformat", "crick", "intrainterboth", "rhamm", "numnodes", "node",

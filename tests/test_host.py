@@ -118,3 +118,23 @@ def test_cli_binary_exit_codes():
     assert subprocess.run([exe], capture_output=True).returncode == 1            # -i is required
     assert subprocess.run([exe, "hammings", "-m1", "-K5", "-i", "x"], capture_output=True).returncode == 1
     assert subprocess.run([exe, "-m0", "-K32", "-r9", "-i", "x"], capture_output=True).returncode == 1  # K/(R+1) < 4
+
+
+def test_bham_round_trip(tmp_path):
+    """-m4 then -m5: every "chrom",loci,dist row survives; the CSV carries the reference's -m5 header."""
+    src = os.path.join(GOLDEN, "tiny2.K25c.csv")
+    b, back = str(tmp_path / "h.bham"), str(tmp_path / "back.csv")
+    hostlib.csv_to_bham(src, b)
+    raw = open(b, "rb").read()
+    assert raw[:4] == b"bham" and int.from_bytes(raw[8:12], "little") == len(raw)
+    hostlib.bham_to_csv(b, back)
+    got = open(back).read().split("\n")
+    want = open(src).read().split("\n")
+    assert got[0] == '"Chrom","Loci","Hamming"'
+    assert got[1:] == want[1:]  # the "G,2,G" descriptor row is dropped, as in the reference
+    import subprocess
+    exe = hostlib.cli_path()
+    b2, back2 = str(tmp_path / "h2.bham"), str(tmp_path / "back2.csv")
+    assert subprocess.run([exe, "-m4", "-i", src, "-o", b2], capture_output=True).returncode == 0
+    assert subprocess.run([exe, "-m5", "-i", b2, "-o", back2], capture_output=True).returncode == 0
+    assert open(b2, "rb").read() == raw and open(back2).read() == open(back).read()
