@@ -159,22 +159,28 @@ struct k4b_packed {
     uint32_t *d_image = nullptr;
     bool owns = false;
     int device = 0;
-    uint32_t len = 0, K = 0, nw = 0, nwp = 0;
+    uint32_t len = 0, K = 0, nw = 0, stride = 0;
     int has_non_acgt = 0;
     uint64_t num_kmers = 0;
-    uint32_t *d_rc_planes = nullptr;  // lazily built: reverse-complemented planes (K > 128 path)
-    ImageView view() const { return ImageView{d_image, nwp, len}; }
+    uint32_t *d_rc_planes = nullptr;  // lazily built: reverse-complemented planes (same geometry)
+    ImageView view() const {
+        return ImageView{d_image + kFrontPadWords, stride, stride - (uint32_t)kFrontPadWords, len};
+    }
+    ImageView rc_view() const {
+        return ImageView{d_rc_planes + kFrontPadWords, stride, stride - (uint32_t)kFrontPadWords, len};
+    }
 };
 
-static uint32_t padded_words(uint32_t len) {
+// words per array: front pad + sequence rounded up to whole tiles + back pad
+static uint32_t array_stride(uint32_t len) {
     const uint32_t nw = (len + 31) / 32;
-    return (nw + kTileGroups - 1) / kTileGroups * kTileGroups + kTileGroups;
+    return kFrontPadWords + (nw + kTileGroups - 1) / kTileGroups * kTileGroups + kBackPadWords;
 }
 extern "C" size_t k4b_packed_image_bytes(uint32_t concat_len) {
-    return (size_t)padded_words(concat_len) * 4 * sizeof(uint32_t);
+    return (size_t)array_stride(concat_len) * 4 * sizeof(uint32_t);
 }
 extern "C" void *k4b_packed_image_ptr(k4b_packed *p) { return p ? p->d_image : nullptr; }
-extern "C" size_t k4b_packed_image_size(k4b_packed *p) { return p ? (size_t)p->nwp * 16 : 0; }
+extern "C" size_t k4b_packed_image_size(k4b_packed *p) { return p ? (size_t)p->stride * 16 : 0; }
 extern "C" int k4b_packed_has_non_acgt(k4b_packed *p) { return p ? p->has_non_acgt : 0; }
 extern "C" uint64_t k4b_packed_num_kmers(k4b_packed *p) { return p ? p->num_kmers : 0; }
 extern "C" void k4b_packed_free(k4b_packed *p) {
@@ -208,7 +214,7 @@ static int pack_into(const void *d_concat, uint32_t concat_len, uint32_t K, uint
     p->len = concat_len;
     p->K = K;
     p->nw = (concat_len + 31) / 32;
-    p->nwp = padded_words(concat_len);
+    p->stride = array_stride(concat_len);
     p->owns = owns;
     p->d_image = image;
     struct Scratch {
@@ -221,8 +227,8 @@ static int pack_into(const void *d_concat, uint32_t concat_len, uint32_t K, uint
     cudaError_t e = cudaMalloc(&d_s, sizeof(Scratch));
     if (e == cudaSuccess) e = cudaMemsetAsync(d_s, 0, sizeof(Scratch), st);
     if (e == cudaSuccess)
-        e = launch_pack((const uint8_t *)d_concat, concat_len, p->d_image, p->nwp, &d_s->flags, st);
-    if (e == cudaSuccess) e = launch_valid(p->d_image, p->nwp, concat_len, K, &d_s->count, st);
+        e = launch_pack((const uint8_t *)d_concat, p->view(), &d_s->flags, st);
+    if (e == cudaSuccess) e = launch_valid(p->view(), K, &d_s->count, st);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(&h_s, d_s, sizeof(Scratch), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -304,7 +310,7 @@ extern "C" int k4b_packed_from_image(void *d_image, size_t image_bytes, uint32_t
     p->len = concat_len;
     p->K = K;
     p->nw = (concat_len + 31) / 32;
-    p->nwp = padded_words(concat_len);
+    p->stride = array_stride(concat_len);
     p->has_non_acgt = has_non_acgt;
     p->num_kmers = 0;
     *out = p;
@@ -365,8 +371,8 @@ static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_stra
     const bool generic = W > (uint32_t)kMaxRegW;
 
     if (generic && crick && !queries->d_rc_planes) {
-        CU(cudaMalloc(&queries->d_rc_planes, (size_t)queries->nwp * 12));
-        CU(launch_revcomp_planes(queries->view(), queries->d_rc_planes, st));
+        CU(cudaMalloc(&queries->d_rc_planes, (size_t)queries->stride * 12));
+        CU(launch_revcomp_planes(queries->view(), queries->rc_view(), st));
     }
     if (g_ev_dev != queries->device) {
         if (g_ev0) {
@@ -408,8 +414,8 @@ static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_stra
         if (!generic)
             e = launch_allpairs(prm, three, crick, st, nullptr);
         else
-            e = launch_allpairs_generic(prm, three, crick, queries->d_rc_planes, queries->nwp, st,
-                                        nullptr);
+            e = launch_allpairs_generic(prm, three, crick,
+                                        crick ? queries->rc_view() : queries->view(), st, nullptr);
     }
     if (e == cudaSuccess) e = cudaEventRecord(g_ev1, st);
     if (e == cudaSuccess)

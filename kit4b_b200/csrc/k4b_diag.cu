@@ -1,0 +1,281 @@
+// k4b_diag.cu - diagonal-band engine for the exhaustive all-vs-all minimum (sm_100a).
+//
+// The reference walks one diagonal of the K-mer pair matrix at a time and updates the
+// distance incrementally: +1 for a mismatch entering at the 3' end, -1 for one leaving at the
+// 5' end, and every cell lowers the minima of BOTH K-mers of the pair
+// (ngskit4b/hammings.cpp:3183-3287 GHamDistWatson, :3300-3489 GHamDistCrick).  This kernel
+// keeps that O(1)-per-pair recurrence and that symmetry but runs 32 diagonals per thread in
+// bit-sliced form:
+//   * a thread owns 32 consecutive diagonals s0..s0+31; the 32 running distances live as
+//     NP bit-planes c[0..NP) ("vertical counters"), one bit per diagonal per plane;
+//   * one row step: the entering base A[e] is compared with the 32 column bases
+//     B[e+s0 .. e+s0+31] in two LOP3 (bit-plane XOR/OR against the broadcast row base), the
+//     same for the leaving base A[e-K]; the +1/-1/0 update of all 32 counters is a ripple of
+//     2 LOP3 per plane; no POPC, no per-pair minimum;
+//   * counters are stored biased so that "distance < T" is simply "top plane bit clear":
+//     T is an upper bound of every running minimum this warp can still improve (max over
+//     256-position blocks, refreshed between launches).  Only flagged cells - a few per
+//     million on non-repetitive sequence - take the slow path that rebuilds the exact
+//     distance and issues atomicMin on both K-mers of the pair;
+//   * a warp = 32 threads = 1024 consecutive diagonals over the same rows, so column words are
+//     read fully coalesced and row words are warp-uniform; a CTA = 8 such warps.
+// Watson: A = B = sequence, diagonals s >= 1.  Crick: B = reverse-complemented sequence Y
+// (Y[a] = cpl(x[len-1-a])), so that d(i, rc j) = HD(x-Kmer i, Y-Kmer M-j); the diagonal
+// s = j' - i is mirror symmetric about its middle, only its first half is walked.
+// Exact, bit-identical results; measured against the same oracle as the POPC engine.
+#include "k4b_kernels.cuh"
+
+namespace k4b {
+
+constexpr int kDiagWarps = 8;        // super-bands (of 1024 diagonals) per CTA
+constexpr int kSuperBand = 1024;     // diagonals per warp
+constexpr int kGroupDiags = kDiagWarps * kSuperBand;
+
+__device__ __forceinline__ uint32_t sext_bit(uint32_t x, uint32_t t) {
+    return (uint32_t)((int32_t)(x << (31u - t)) >> 31);
+}
+
+// running-minimum upper bounds per 2^shift positions (valid K-mer starts only)
+__global__ void __launch_bounds__(256) blockmax_kernel(const uint32_t *__restrict__ best, ImageView a,
+                                                       uint32_t n_pos, uint32_t shift,
+                                                       uint32_t *__restrict__ blockmax, uint32_t n_blocks) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_blocks) return;
+    const uint32_t base = warp << shift, span = 1u << shift;
+    uint32_t m = 0;
+    for (uint32_t o = lane; o < span; o += 32) {
+        const uint32_t pos = base + o;
+        if (pos < n_pos && ((a.valid()[pos >> 5] >> (pos & 31)) & 1u)) m = max(m, best[pos]);
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane == 0) blockmax[warp] = m;
+}
+
+template <int P>
+struct SideWords {      // words of one side (enter or leave) for a block of up to 32 row steps
+    uint32_t ra[P];     // row bases: bit t = plane bit of A[idx + t]           (warp uniform)
+    uint32_t xa[P];     // column window: bits [idx+s0, idx+s0+32) of B planes   (per lane)
+    uint32_t xb[P];     //                bits [idx+s0+32, idx+s0+64)
+};
+
+template <int P>
+__device__ __forceinline__ void load_side(const ImageView &a, const ImageView &b, long long idx,
+                                          long long s0, SideWords<P> &w) {
+    const uint32_t wi = (uint32_t)(idx >> 5), sh = (uint32_t)(idx & 31);
+    const long long wb = idx + s0;
+    const long long wj = wb >> 5;  // floor: may be slightly negative (front pad)
+    const uint32_t ws = (uint32_t)(wb & 31);
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const uint32_t *ap = a.plane(p) + wi;
+        w.ra[p] = __funnelshift_r(__ldg(ap), __ldg(ap + 1), sh);
+        const uint32_t *bp = b.plane(p) + wj;
+        const uint32_t w0 = __ldg(bp), w1 = __ldg(bp + 1), w2 = __ldg(bp + 2);
+        w.xa[p] = __funnelshift_r(w0, w1, ws);
+        w.xb[p] = __funnelshift_r(w1, w2, ws);
+    }
+}
+
+// mismatch word of row step t: bit k = [A[idx+t] != B[idx+t+s0+k]]
+template <int P>
+__device__ __forceinline__ uint32_t mism_word(const SideWords<P> &w, uint32_t t) {
+    uint32_t m = __funnelshift_r(w.xa[0], w.xb[0], t) ^ sext_bit(w.ra[0], t);
+    m |= __funnelshift_r(w.xa[1], w.xb[1], t) ^ sext_bit(w.ra[1], t);
+    if (P == 3) m |= __funnelshift_r(w.xa[2], w.xb[2], t) ^ sext_bit(w.ra[2], t);
+    return m;
+}
+
+template <int NP, int P>
+__global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagParams prm) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t grp_local = blockIdx.x / prm.n_seg, seg = blockIdx.x - grp_local * prm.n_seg;
+    const long long grp = (long long)prm.grp_first + (long long)grp_local * prm.grp_step;
+    const long long S0cta = prm.s_first + grp * kGroupDiags;
+    const long long S1cta = S0cta + kGroupDiags - 1;
+    const long long M = prm.M;
+    long long row_lo, row_hi;
+    if (!prm.crick) {
+        row_lo = 0;
+        row_hi = M - S0cta;
+    } else {  // half of every mirror-symmetric diagonal: rows max(0,-s) .. (M-s)/2
+        row_lo = S1cta < 0 ? -S1cta : 0;
+        row_hi = (M - S0cta) >> 1;
+        if (row_hi > M) row_hi = M;
+    }
+    const long long r_start = row_lo + (long long)seg * prm.rows_per_seg;
+    if (r_start > row_hi) return;
+    long long r_end = r_start + prm.rows_per_seg;
+    if (r_end > row_hi + 1) r_end = row_hi + 1;
+    const long long S0w = S0cta + (long long)warp * kSuperBand;
+    const long long s0 = S0w + lane * 32;
+    const uint32_t K = prm.K;
+
+    // ---- threshold: upper bound of every minimum this warp can still lower ----
+    uint32_t tmax = 0;
+    {
+        auto scan = [&](long long lo, long long hi) {
+            if (lo < 0) lo = 0;
+            if (hi > M) hi = M;
+            if (lo > hi) return;
+            for (long long bk = (lo >> prm.bm_shift) + lane; bk <= (hi >> prm.bm_shift); bk += 32)
+                tmax = max(tmax, __ldg(prm.blockmax + bk));
+        };
+        scan(r_start, r_end - 1);
+        const long long c_lo = r_start + S0w, c_hi = r_end - 1 + S0w + kSuperBand - 1;
+        if (!prm.crick) scan(c_lo, c_hi);
+        else scan(M - c_hi, M - c_lo);
+        tmax = __reduce_max_sync(0xffffffffu, tmax);
+    }
+    if (tmax == 0) return;  // every K-mer in reach already sits at the floor 0
+    const uint32_t T = tmax;
+    const uint32_t bias = (1u << (NP - 1)) - T;  // stored = distance + bias; distance < T <=> top bit clear
+
+    uint32_t c[NP];
+#pragma unroll
+    for (int b = 0; b < NP; ++b) c[b] = ((bias >> b) & 1u) ? 0xffffffffu : 0u;
+
+    // slow path: exact distance of the flagged diagonals of `row`, min-update of both K-mers
+    auto flush = [&](uint32_t flags, long long row) {
+        while (flags) {
+            const uint32_t k = __ffs(flags) - 1;
+            flags &= flags - 1;
+            uint32_t val = 0;
+#pragma unroll
+            for (int b = 0; b < NP; ++b) val |= ((c[b] >> k) & 1u) << b;
+            const uint32_t d = val - bias;
+            const long long jc = row + s0 + k;
+            long long j;
+            bool ok;
+            if (!prm.crick) {
+                j = jc;
+                ok = j <= M;
+            } else {
+                j = M - jc;
+                ok = jc >= 0 && jc <= M;
+            }
+            if (!ok || row > M) continue;
+            const uint32_t *v = prm.a.valid();
+            if (!((v[row >> 5] >> (row & 31)) & (v[j >> 5] >> (j & 31)) & 1u)) continue;
+            if (d < prm.best[row]) atomicMin(&prm.best[row], d);
+            if (d < prm.best[j]) atomicMin(&prm.best[j], d);
+        }
+    };
+
+    // ---- warm-up: the first K bases of the window enter, nothing leaves ----
+    long long e = r_start;
+    {
+        uint32_t remaining = K;
+        while (remaining) {
+            const uint32_t n = remaining < 32 ? remaining : 32;
+            SideWords<P> we;
+            load_side<P>(prm.a, prm.b, e, s0, we);
+#pragma unroll 1
+            for (uint32_t t = 0; t < n; ++t) {
+                uint32_t act = mism_word<P>(we, t);
+#pragma unroll
+                for (int b = 0; b < NP; ++b) {  // ripple increment
+                    const uint32_t old = c[b];
+                    c[b] = old ^ act;
+                    act &= old;
+                }
+            }
+            e += n;
+            remaining -= n;
+        }
+    }
+    {
+        const uint32_t f = ~c[NP - 1];
+        if (f) flush(f, r_start);
+    }
+
+    // ---- main: row r: base r+K-1 enters, base r-1 leaves ----
+    long long row = r_start + 1;
+    while (row < r_end) {
+        const long long left = r_end - row;
+        SideWords<P> we, wl;
+        load_side<P>(prm.a, prm.b, row + K - 1, s0, we);
+        load_side<P>(prm.a, prm.b, row - 1, s0, wl);
+        if (left >= 32) {
+#pragma unroll
+            for (uint32_t t = 0; t < 32; ++t) {
+                const uint32_t en = mism_word<P>(we, t), lv = mism_word<P>(wl, t);
+                const uint32_t plus = en & ~lv;
+                uint32_t act = en ^ lv;
+#pragma unroll
+                for (int b = 0; b < NP; ++b) {  // ripple +1 where plus, -1 elsewhere in act
+                    const uint32_t old = c[b];
+                    c[b] = old ^ act;
+                    act &= ~(old ^ plus);
+                }
+                const uint32_t f = ~c[NP - 1];
+                if (__builtin_expect(f != 0, 0)) flush(f, row + t);
+            }
+            row += 32;
+        } else {
+#pragma unroll 1
+            for (uint32_t t = 0; t < (uint32_t)left; ++t) {
+                const uint32_t en = mism_word<P>(we, t), lv = mism_word<P>(wl, t);
+                const uint32_t plus = en & ~lv;
+                uint32_t act = en ^ lv;
+#pragma unroll
+                for (int b = 0; b < NP; ++b) {
+                    const uint32_t old = c[b];
+                    c[b] = old ^ act;
+                    act &= ~(old ^ plus);
+                }
+                const uint32_t f = ~c[NP - 1];
+                if (f) flush(f, row + t);
+            }
+            row += left;
+        }
+    }
+}
+
+cudaError_t launch_blockmax(const uint32_t *d_best, ImageView a, uint32_t n_pos, uint32_t shift,
+                            uint32_t *d_blockmax, uint32_t n_blocks, cudaStream_t st) {
+    if (!n_blocks) return cudaSuccess;
+    const uint32_t threads = n_blocks * 32;
+    blockmax_kernel<<<(threads + 255) / 256, 256, 0, st>>>(d_best, a, n_pos, shift, d_blockmax, n_blocks);
+    return cudaGetLastError();
+}
+
+int diag_planes_for_k(uint32_t K) {
+    int b = 0;
+    while ((1u << b) < K + 1) ++b;  // 2^b >= K+1 >= any threshold T
+    return b + 1;
+}
+
+template <int P>
+static cudaError_t launch_diag_p(const DiagParams &p, int np, dim3 grid, cudaStream_t st) {
+    switch (np) {
+#define K4B_DIAG_CASE(N) \
+    case N: diag_min_kernel<N, P><<<grid, kDiagWarps * 32, 0, st>>>(p); break
+        K4B_DIAG_CASE(5);
+        K4B_DIAG_CASE(6);
+        K4B_DIAG_CASE(7);
+        K4B_DIAG_CASE(8);
+        K4B_DIAG_CASE(9);
+        K4B_DIAG_CASE(10);
+        K4B_DIAG_CASE(11);
+        K4B_DIAG_CASE(12);
+        K4B_DIAG_CASE(13);
+        K4B_DIAG_CASE(14);
+#undef K4B_DIAG_CASE
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_diag(const DiagParams &p, bool three_planes, uint32_t n_groups, cudaStream_t st,
+                        unsigned long long *n_ctas) {
+    if (n_ctas) *n_ctas = 0;
+    if (!n_groups || !p.n_seg) return cudaSuccess;
+    const unsigned long long total = (unsigned long long)n_groups * p.n_seg;
+    if (total > 0x7fffffffull) return cudaErrorInvalidValue;
+    if (n_ctas) *n_ctas = total;
+    const int np = diag_planes_for_k(p.K);
+    dim3 grid((unsigned)total);
+    return three_planes ? launch_diag_p<3>(p, np, grid, st) : launch_diag_p<2>(p, np, grid, st);
+}
+
+}  // namespace k4b

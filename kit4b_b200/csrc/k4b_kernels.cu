@@ -54,14 +54,16 @@ __device__ __forceinline__ uint32_t gather4(uint32_t x, int p) {
     return (t * 0x10204080u) >> 28;
 }
 
-__global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ concat, uint32_t len,
-                                                   uint32_t *__restrict__ image, uint32_t nwp,
-                                                   uint32_t *__restrict__ flags) {
-    // thread i packs bases [16i, 16i+16) into 16 bits per plane; lane pairs merge to a word
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ concat, ImageView img,
+                                                   uint32_t *__restrict__ image, uint32_t *__restrict__ flags) {
+    // thread i packs 16 bases into 16 bits per plane; lane pairs merge to a word.  Array words
+    // run from -kFrontPadWords to nwl-1 (logical), i.e. `image` points at the first pad word.
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t b0 = (uint64_t)i * 16;
+    const uint32_t w_abs = i >> 1;
+    const long long b0 = ((long long)w_abs - kFrontPadWords) * 32 + (long long)(i & 1) * 16;
+    const long long len = img.len;
     uint32_t x[4];
-    if (b0 + 16 <= len) {
+    if (b0 >= 0 && b0 + 16 <= len) {
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(concat + b0));
         x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
     } else {
@@ -70,8 +72,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ c
             uint32_t w = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const uint64_t pos = b0 + 4 * k + j;
-                const uint32_t c = pos < len ? (uint32_t)concat[pos] : 7u;
+                const long long pos = b0 + 4 * k + j;
+                const uint32_t c = (pos >= 0 && pos < len) ? (uint32_t)concat[pos] : 7u;
                 w |= c << (8 * j);
             }
             x[k] = w;
@@ -89,10 +91,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ c
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
         const uint32_t hi = __shfl_down_sync(0xffffffffu, frag[p], 1);
-        if ((threadIdx.x & 1) == 0) {
-            const uint32_t w = i >> 1;
-            if (w < nwp) image[(size_t)p * nwp + w] = frag[p] | (hi << 16);
-        }
+        if ((threadIdx.x & 1) == 0 && w_abs < img.stride)
+            image[(size_t)p * img.stride + w_abs] = frag[p] | (hi << 16);
     }
 }
 
@@ -101,46 +101,49 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ c
 // i.e. the K-mer lies inside one chromosome (hammings.cpp:3084-3094 NumSubSeqs, :3260 EOS
 // counter).  Also counts the valid K-mers.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t eos_word(const uint32_t *img, uint32_t nwp, uint32_t w) {
-    if (w >= nwp) return 0xffffffffu;
-    return img[w] & img[(size_t)nwp + w] & img[(size_t)2 * nwp + w];
+__device__ __forceinline__ uint32_t eos_word(const ImageView &img, uint32_t w) {
+    if (w >= img.nwl) return 0xffffffffu;
+    return img.plane(0)[w] & img.plane(1)[w] & img.plane(2)[w];
 }
 // first EOS position >= pos found while scanning the words that overlap [pos, pos+K); kNoEos
 // when those words hold none (a hit may lie at or beyond pos+K: callers compare)
 constexpr uint64_t kNoEos = ~0ull;
-__device__ uint64_t next_eos(const uint32_t *img, uint32_t nwp, uint64_t pos, uint32_t K) {
+__device__ uint64_t next_eos(const ImageView &img, uint64_t pos, uint32_t K) {
     const uint64_t lim = pos + K;
     uint32_t w = (uint32_t)(pos >> 5);
-    uint32_t e = eos_word(img, nwp, w) & (0xffffffffu << (pos & 31));
+    uint32_t e = eos_word(img, w) & (0xffffffffu << (pos & 31));
     while (true) {
         if (e) return ((uint64_t)w << 5) + (__ffs(e) - 1);
         ++w;
         if (((uint64_t)w << 5) >= lim) return kNoEos;
-        e = eos_word(img, nwp, w);
+        e = eos_word(img, w);
     }
 }
 
-__global__ void __launch_bounds__(256) valid_kernel(uint32_t *__restrict__ image, uint32_t nwp,
-                                                    uint32_t len, uint32_t K,
-                                                    unsigned long long *__restrict__ count) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) valid_kernel(ImageView img, uint32_t *__restrict__ valid_arr,
+                                                    uint32_t K, unsigned long long *__restrict__ count) {
+    // thread per array word; valid_arr points at the first (front pad) word of the valid array
+    const uint32_t w_abs = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t v = 0;
-    if (g < nwp) {
-        const uint64_t base = (uint64_t)g << 5;
-        if (base < len) {
-            // common case: no EOS anywhere in [base, base+31+K) -> all 32 starts are valid
-            uint64_t ne = next_eos(image, nwp, base, K + 31);
-            if (ne == kNoEos || ne >= base + 31 + K) {
-                v = 0xffffffffu;
-            } else {
-                for (int i = 0; i < 32; ++i) {
-                    const uint64_t pos = base + i;
-                    if (ne == kNoEos || ne < pos) ne = next_eos(image, nwp, pos, K);
-                    if (ne == kNoEos || ne >= pos + K) v |= 1u << i;
+    if (w_abs < img.stride) {
+        if (w_abs >= (uint32_t)kFrontPadWords) {
+            const uint32_t g = w_abs - kFrontPadWords;
+            const uint64_t base = (uint64_t)g << 5;
+            if (base < img.len) {
+                // common case: no EOS anywhere in [base, base+31+K) -> all 32 starts are valid
+                uint64_t ne = next_eos(img, base, K + 31);
+                if (ne == kNoEos || ne >= base + 31 + K) {
+                    v = 0xffffffffu;
+                } else {
+                    for (int i = 0; i < 32; ++i) {
+                        const uint64_t pos = base + i;
+                        if (ne == kNoEos || ne < pos) ne = next_eos(img, pos, K);
+                        if (ne == kNoEos || ne >= pos + K) v |= 1u << i;
+                    }
                 }
             }
         }
-        image[(size_t)3 * nwp + g] = v;
+        valid_arr[w_abs] = v;
     }
     uint32_t c = __popc(v);
 #pragma unroll
@@ -435,8 +438,7 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_kernel(const AllPair
 // ---------------------------------------------------------------------------------------
 template <int P, bool CRICK, bool WILD>
 __global__ void __launch_bounds__(kThreads, 2) allpairs_min_generic_kernel(const AllPairsParams prm,
-                                                                           const uint32_t *__restrict__ q_rc_image,
-                                                                           uint32_t q_rc_nwp) {
+                                                                           const ImageView rcq) {
     // q_rc_image: 3 planes of the reverse-complemented query concat (position i of the rc
     // sequence is base len-1-i complemented) so rc(K-mer at pos) = K-mer at len-K-pos.
     constexpr int S = CRICK ? 2 : 1;
@@ -448,8 +450,8 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_generic_kernel(const
     const bool q_ok = qpos < prm.q_end && qpos + K <= prm.q.len;
     uint32_t best = q_ok ? prm.out[qpos - prm.q_begin] : 0u;
     const uint32_t qp[2] = {q_ok ? qpos : 0u, q_ok ? prm.q.len - K - qpos : 0u};
-    const uint32_t *qimg[2] = {prm.q.base, q_rc_image};
-    const uint32_t qnwp[2] = {prm.q.nwp, q_rc_nwp};
+    const uint32_t *qimg[2] = {prm.q.base, rcq.base};
+    const uint32_t qnwp[2] = {prm.q.stride, rcq.stride};
 
     const uint32_t g_begin = blockIdx.x * prm.tiles_per_chunk * kTileGroups;
     uint32_t g_end = g_begin + prm.tiles_per_chunk * kTileGroups;
@@ -541,43 +543,44 @@ __device__ __forceinline__ uint32_t bits_at(const uint32_t *pl, int64_t start) {
     const uint32_t wi = (uint32_t)(start >> 5), sh = (uint32_t)(start & 31);
     return __funnelshift_r(pl[wi], pl[wi + 1], sh);
 }
-__global__ void __launch_bounds__(256) revcomp_planes_kernel(ImageView q, uint32_t *__restrict__ rc) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= q.nwp) return;
-    const int64_t start = (int64_t)q.len - 32 * ((int64_t)j + 1);
-    uint32_t o[3];
-#pragma unroll
-    for (int p = 0; p < 3; ++p) o[p] = __brev(bits_at(q.plane(p), start));
-    // bits of this word that lie inside the sequence
-    const int64_t first = (int64_t)j * 32;
+__global__ void __launch_bounds__(256) revcomp_planes_kernel(ImageView q, uint32_t *__restrict__ rc_arr) {
+    // thread per array word; rc_arr points at the first (front pad) word of rc plane 0
+    const uint32_t w_abs = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w_abs >= q.stride) return;
+    const long long j = (long long)w_abs - kFrontPadWords;  // logical word of the rc sequence
+    uint32_t o[3] = {0, 0, 0};
     uint32_t in = 0;
-    if (first < (int64_t)q.len) {
-        const int64_t n = (int64_t)q.len - first;
-        in = n >= 32 ? 0xffffffffu : ((1u << (uint32_t)n) - 1u);
-    }
-    const uint32_t flip = ~o[2] & in;
-    o[0] ^= flip;
-    o[1] ^= flip;
+    if (j >= 0 && j * 32 < (long long)q.len) {
+        const int64_t start = (int64_t)q.len - 32 * (j + 1);
 #pragma unroll
-    for (int p = 0; p < 3; ++p) rc[(size_t)p * q.nwp + j] = o[p] | ~in;
+        for (int p = 0; p < 3; ++p) o[p] = __brev(bits_at(q.plane(p), start));
+        const int64_t n = (int64_t)q.len - j * 32;
+        in = n >= 32 ? 0xffffffffu : ((1u << (uint32_t)n) - 1u);
+        const uint32_t flip = ~o[2] & in;
+        o[0] ^= flip;
+        o[1] ^= flip;
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p) rc_arr[(size_t)p * q.stride + w_abs] = o[p] | ~in;
 }
 
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
-cudaError_t launch_revcomp_planes(ImageView q, uint32_t *d_rc_planes, cudaStream_t st) {
-    revcomp_planes_kernel<<<(q.nwp + 255) / 256, 256, 0, st>>>(q, d_rc_planes);
+cudaError_t launch_revcomp_planes(ImageView q, ImageView rc, cudaStream_t st) {
+    revcomp_planes_kernel<<<(q.stride + 255) / 256, 256, 0, st>>>(
+        q, const_cast<uint32_t *>(rc.base) - kFrontPadWords);
     return cudaGetLastError();
 }
-cudaError_t launch_pack(const uint8_t *d_concat, uint32_t len, uint32_t *d_image, uint32_t nwp,
-                        uint32_t *d_flags, cudaStream_t st) {
-    const uint32_t threads = nwp * 2;
-    pack_kernel<<<(threads + 255) / 256, 256, 0, st>>>(d_concat, len, d_image, nwp, d_flags);
+cudaError_t launch_pack(const uint8_t *d_concat, ImageView img, uint32_t *d_flags, cudaStream_t st) {
+    const uint32_t threads = img.stride * 2;
+    pack_kernel<<<(threads + 255) / 256, 256, 0, st>>>(
+        d_concat, img, const_cast<uint32_t *>(img.base) - kFrontPadWords, d_flags);
     return cudaGetLastError();
 }
-cudaError_t launch_valid(uint32_t *d_image, uint32_t nwp, uint32_t len, uint32_t K,
-                         unsigned long long *d_count, cudaStream_t st) {
-    valid_kernel<<<(nwp + 255) / 256, 256, 0, st>>>(d_image, nwp, len, K, d_count);
+cudaError_t launch_valid(ImageView img, uint32_t K, unsigned long long *d_count, cudaStream_t st) {
+    valid_kernel<<<(img.stride + 255) / 256, 256, 0, st>>>(
+        img, const_cast<uint32_t *>(img.valid()) - kFrontPadWords, K, d_count);
     return cudaGetLastError();
 }
 cudaError_t launch_fill_u32(uint32_t *d, uint32_t n, uint32_t v, cudaStream_t st) {
@@ -647,8 +650,7 @@ cudaError_t launch_allpairs(const AllPairsParams &p, bool three_planes, bool cri
 }
 
 cudaError_t launch_allpairs_generic(const AllPairsParams &p, bool three_planes, bool crick,
-                                    const uint32_t *d_q_rc_image, uint32_t q_rc_nwp,
-                                    cudaStream_t st, int *n_ctas) {
+                                    ImageView rc, cudaStream_t st, int *n_ctas) {
     const uint32_t nq = p.q_end - p.q_begin;
     const uint32_t qb = (nq + kThreads - 1) / kThreads;
     const uint32_t chunks = (p.tiles_total + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
@@ -656,14 +658,14 @@ cudaError_t launch_allpairs_generic(const AllPairsParams &p, bool three_planes, 
     if (n_ctas) *n_ctas = (int)(chunks * qb);
     if (!nq || !chunks) return cudaSuccess;
     if (three_planes && p.wildcard) {
-        if (crick) allpairs_min_generic_kernel<3, true, true><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
-        else allpairs_min_generic_kernel<3, false, true><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
+        if (crick) allpairs_min_generic_kernel<3, true, true><<<grid, kThreads, 0, st>>>(p, rc);
+        else allpairs_min_generic_kernel<3, false, true><<<grid, kThreads, 0, st>>>(p, rc);
     } else if (three_planes) {
-        if (crick) allpairs_min_generic_kernel<3, true, false><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
-        else allpairs_min_generic_kernel<3, false, false><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
+        if (crick) allpairs_min_generic_kernel<3, true, false><<<grid, kThreads, 0, st>>>(p, rc);
+        else allpairs_min_generic_kernel<3, false, false><<<grid, kThreads, 0, st>>>(p, rc);
     } else {
-        if (crick) allpairs_min_generic_kernel<2, true, false><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
-        else allpairs_min_generic_kernel<2, false, false><<<grid, kThreads, 0, st>>>(p, d_q_rc_image, q_rc_nwp);
+        if (crick) allpairs_min_generic_kernel<2, true, false><<<grid, kThreads, 0, st>>>(p, rc);
+        else allpairs_min_generic_kernel<2, false, false><<<grid, kThreads, 0, st>>>(p, rc);
     }
     return cudaGetLastError();
 }

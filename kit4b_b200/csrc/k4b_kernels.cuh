@@ -24,13 +24,19 @@ constexpr int kTileWords = kTileGroups + kTilePad;
 constexpr int kMaxRegW = 4;          // W (words per K-mer) handled by the register-resident path
 constexpr uint32_t kNoDist = 0xffffu;
 
-// Layout of one packed image: 4 arrays of nwp words: plane0, plane1, plane2, valid.
+constexpr int kFrontPadWords = 320;  // EOS-filled words before logical position 0 (diagonal engine
+                                     // reads columns at slightly negative offsets)
+constexpr int kBackPadWords = 576;   // EOS-filled words after the last sequence word
+
+// Layout of one packed image: 4 arrays (plane0, plane1, plane2, valid) of `stride` words each;
+// logical word 0 of an array sits kFrontPadWords into it.
 struct ImageView {
-    const uint32_t *base;  // device pointer
-    uint32_t nwp;          // padded words per array
+    const uint32_t *base;  // device pointer to logical word 0 of plane 0
+    uint32_t stride;       // words between consecutive arrays
+    uint32_t nwl;          // words addressable from logical word 0 (sequence + back pad)
     uint32_t len;          // bases (incl. EOS separators)
-    __host__ __device__ const uint32_t *plane(int p) const { return base + (size_t)p * nwp; }
-    __host__ __device__ const uint32_t *valid() const { return base + (size_t)3 * nwp; }
+    __host__ __device__ const uint32_t *plane(int p) const { return base + (size_t)p * stride; }
+    __host__ __device__ const uint32_t *valid() const { return base + (size_t)3 * stride; }
 };
 
 struct AllPairsParams {
@@ -50,11 +56,31 @@ struct AllPairsParams {
     long long w_lo, w_hi, c1_lo, c1_hi, c2_lo, c2_hi;
 };
 
+// diagonal-band engine (k4b_diag.cu)
+struct DiagParams {
+    ImageView a;             // row sequence: planes + valid-start plane (also validates columns)
+    ImageView b;             // column sequence planes: a itself (Watson) or its reverse complement (Crick)
+    uint32_t K;
+    uint32_t M;              // last K-mer start position, len - K
+    int crick;
+    long long s_first;       // diagonal (column - row) of lane 0 of group 0
+    uint32_t grp_first, grp_step;  // CTA group g of this launch = grp_first + local * grp_step
+    uint32_t n_seg, rows_per_seg;  // row segments per group
+    uint32_t *best;          // running minima per position (atomicMin)
+    const uint32_t *blockmax;  // max of best over 2^bm_shift positions (valid starts only)
+    uint32_t bm_shift;
+};
+constexpr int kDiagGroupDiagonals = 8 * 1024;  // diagonals per CTA group (8 warps x 1024)
+cudaError_t launch_blockmax(const uint32_t *d_best, ImageView a, uint32_t n_pos, uint32_t shift,
+                            uint32_t *d_blockmax, uint32_t n_blocks, cudaStream_t st);
+cudaError_t launch_diag(const DiagParams &p, bool three_planes, uint32_t n_groups, cudaStream_t st,
+                        unsigned long long *n_ctas);
+int diag_planes_for_k(uint32_t K);
+
 // host-callable launchers (defined in k4b_kernels.cu)
-cudaError_t launch_pack(const uint8_t *d_concat, uint32_t len, uint32_t *d_image, uint32_t nwp,
-                        uint32_t *d_flags, cudaStream_t st);
-cudaError_t launch_valid(uint32_t *d_image, uint32_t nwp, uint32_t len, uint32_t K,
-                         unsigned long long *d_count, cudaStream_t st);
+// img.base must point into a writable allocation (the launchers cast constness away)
+cudaError_t launch_pack(const uint8_t *d_concat, ImageView img, uint32_t *d_flags, cudaStream_t st);
+cudaError_t launch_valid(ImageView img, uint32_t K, unsigned long long *d_count, cudaStream_t st);
 cudaError_t launch_fill_u32(uint32_t *d, uint32_t n, uint32_t v, cudaStream_t st);
 cudaError_t launch_finalize(const uint32_t *d_min32, ImageView q, uint32_t q_begin, uint32_t n,
                             uint32_t K, uint32_t clamp, int max_wild, uint16_t *d_out16,
@@ -62,11 +88,11 @@ cudaError_t launch_finalize(const uint32_t *d_min32, ImageView q, uint32_t q_beg
 // returns cudaErrorInvalidValue when K needs more than the supported words
 cudaError_t launch_allpairs(const AllPairsParams &p, bool three_planes, bool crick,
                             cudaStream_t st, int *n_ctas);
-// K > 32*kMaxRegW: d_q_rc_planes = 3 reverse-complemented planes of the query set (nwp words each)
+// K > 32*kMaxRegW: rc = 3 reverse-complemented planes of the query set (same geometry as q)
 cudaError_t launch_allpairs_generic(const AllPairsParams &p, bool three_planes, bool crick,
-                                    const uint32_t *d_q_rc_planes, uint32_t q_rc_nwp,
-                                    cudaStream_t st, int *n_ctas);
-cudaError_t launch_revcomp_planes(ImageView q, uint32_t *d_rc_planes, cudaStream_t st);
+                                    ImageView rc, cudaStream_t st, int *n_ctas);
+// rc.base: logical word 0 of a 3-array allocation with q's stride and pads
+cudaError_t launch_revcomp_planes(ImageView q, ImageView rc, cudaStream_t st);
 int queries_per_thread(uint32_t W, bool three_planes);
 cudaError_t launch_microbench(int which, int iters, uint32_t *d_sink, int *blocks, int *threads,
                               int *ops_per_thread_iter, cudaStream_t st);
