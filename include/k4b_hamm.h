@@ -139,6 +139,23 @@ int k4b_allpairs_min_device(k4b_packed *queries, k4b_packed *targets, int both_s
  * CUDA events on the launching stream (blocks until that kernel has finished) */
 float k4b_last_kernel_ms(void);
 
+/* ---- engine selection and the diagonal-band engine on device-resident data ------------------- */
+/* Two exact engines produce the exhaustive minima: 1 = POPC all-pairs (queries in registers,
+ * XOR / fold / POPC per 32 bases), 2 = diagonal bands (the reference's O(1)-per-pair sliding
+ * recurrence, 32 diagonals per thread in bit-sliced counters, every cell serving both K-mers
+ * of the pair).  0 = automatic (bands for full sweeps of >= 200 kb, all-pairs otherwise; sweep
+ * sub-ranges, query shards and the targeted mode always use all-pairs).  Env: K4B_ENGINE=popc|diag. */
+int k4b_set_engine(int engine);
+int k4b_get_engine(void);
+/* d_best: DEVICE uint32[len] running minima.  init fills K+1; k4b_exhaustive_diag_device lowers
+ * them for part `part` of `nparts` of the pair matrix (parts are independent and combine by an
+ * element-wise minimum, e.g. ncclAllReduce(min)); finalize converts to the uint16 layout of
+ * k4b_allpairs_min_device (K+1 where no K-mer starts). All asynchronous on `stream`. */
+int k4b_best_init_device(uint32_t *d_best, uint32_t n, uint32_t K, void *stream);
+int k4b_exhaustive_diag_device(k4b_packed *g, int both_strands, uint32_t part, uint32_t nparts,
+                               uint32_t *d_best, void *stream, int *launches);
+int k4b_best_finalize_device(k4b_packed *g, const uint32_t *d_best, uint16_t *d_out_min, void *stream);
+
 /* ---- integer-pipe roofline microbenchmark ----------------------------------- */
 /* which: 0 POPC only, 1 LOP3 only, 2 engine mix (2 LOP3 + 1 POPC + min), 3 IADD3 only.
  * Returns giga warp-lane-ops per second (ops/s / 1e9) on the current device in *gops. */

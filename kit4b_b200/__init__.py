@@ -10,6 +10,8 @@ from .hamm import (  # noqa: F401
     Packed,
     allpairs_min_device,
     exhaustive,
+    set_engine,
+    get_engine,
     exhaustive_shard,
     gpu_count,
     gpu_init,

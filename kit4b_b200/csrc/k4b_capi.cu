@@ -62,9 +62,13 @@ struct NcclApi {
     int (*GroupEnd)() = nullptr;
     int (*Broadcast)(const void *, void *, size_t, int /*ncclDataType_t*/, int /*root*/,
                      ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int /*ncclDataType_t*/, int /*ncclRedOp_t*/,
+                     ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
-constexpr int kNcclUint8 = 1;  // ncclUint8 in nccl.h
+constexpr int kNcclUint8 = 1;   // ncclUint8 in nccl.h
+constexpr int kNcclUint32 = 3;  // ncclUint32
+constexpr int kNcclMin = 3;     // ncclMin
 
 struct Engine {
     std::vector<int> devs;
@@ -92,6 +96,7 @@ static int load_nccl(NcclApi &n) {
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(Broadcast, "ncclBroadcast");
+    SYM(AllReduce, "ncclAllReduce");
     SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
     return 0;
@@ -428,6 +433,153 @@ static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_stra
 }
 
 // ------------------------------------------------------------------------------------------
+// diagonal-band engine on device-resident data
+// ------------------------------------------------------------------------------------------
+static int g_engine = -1;  // 0 auto, 1 POPC all-pairs, 2 diagonal bands; -1 = read K4B_ENGINE
+static int engine_setting() {
+    if (g_engine < 0) {
+        const char *e = getenv("K4B_ENGINE");
+        g_engine = !e ? 0 : (!strcmp(e, "popc") ? 1 : (!strcmp(e, "diag") ? 2 : 0));
+    }
+    return g_engine;
+}
+extern "C" int k4b_set_engine(int engine) {
+    if (engine < 0 || engine > 2) return fail(K4B_ERR_PARAMS, "engine must be 0 (auto), 1 (popc) or 2 (diag)");
+    g_engine = engine;
+    return K4B_OK;
+}
+extern "C" int k4b_get_engine(void) { return engine_setting(); }
+
+extern "C" int k4b_best_init_device(uint32_t *d_best, uint32_t n, uint32_t K, void *stream) {
+    if (!d_best) return fail(K4B_ERR_PARAMS, "d_best is NULL");
+    CU(launch_fill_u32(d_best, n, K + 1, (cudaStream_t)stream));
+    return K4B_OK;
+}
+
+extern "C" int k4b_best_finalize_device(k4b_packed *g, const uint32_t *d_best, uint16_t *d_out_min,
+                                        void *stream) {
+    if (!g || !d_best || !d_out_min) return fail(K4B_ERR_PARAMS, "NULL argument");
+    CU(cudaSetDevice(g->device));
+    CU(launch_finalize(d_best, g->view(), 0, g->len, g->K, 0, -1, d_out_min, (cudaStream_t)stream));
+    return K4B_OK;
+}
+
+static thread_local int g_diag_launches = 0;
+
+// All-vs-all minima of `g` by diagonal bands; this call covers part `part` of `nparts`
+// (interleaved CTA groups of 8192 diagonals) and lowers d_best (uint32[len], initialised to
+// K+1 by the caller) with atomicMin.  Parts are independent; their d_best arrays combine with
+// an element-wise minimum (ncclAllReduce / torch.distributed all_reduce MIN).
+extern "C" int k4b_exhaustive_diag_device(k4b_packed *g, int both_strands, uint32_t part,
+                                          uint32_t nparts, uint32_t *d_best, void *stream,
+                                          int *launches) {
+    if (launches) *launches = 0;
+    if (!g || !d_best) return fail(K4B_ERR_PARAMS, "NULL argument");
+    if (!nparts || part >= nparts) return fail(K4B_ERR_PARAMS, "part %u of %u", part, nparts);
+    CU(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t K = g->K, len = g->len;
+    int nl = 0;
+    if (len < K) return K4B_OK;
+    const uint32_t M = len - K;
+    const bool three = g->has_non_acgt != 0;
+    const bool crick = both_strands != 0;
+    const uint32_t W = (K + 31) / 32;
+    if (crick && !g->d_rc_planes) {
+        CU(cudaMalloc(&g->d_rc_planes, (size_t)g->stride * 12));
+        CU(launch_revcomp_planes(g->view(), g->rc_view(), st));
+        ++nl;
+    }
+    if (g_ev_dev != g->device) {
+        if (g_ev0) {
+            cudaEventDestroy(g_ev0);
+            cudaEventDestroy(g_ev1);
+        }
+        CU(cudaEventCreate(&g_ev0));
+        CU(cudaEventCreate(&g_ev1));
+        g_ev_dev = g->device;
+    }
+    // ---- bootstrap: every K-mer against a small sample of targets with the POPC engine, so
+    //      that the thresholds of the band kernel start near the final minima ----
+    {
+        AllPairsParams bp;
+        bp.q = g->view();
+        bp.t = g->view();
+        bp.K = K;
+        bp.q_begin = 0;
+        bp.q_end = len;
+        const uint32_t tiles_all = (g->nw + kTileGroups - 1) / kTileGroups;
+        const char *bt = getenv("K4B_BOOT_TILES");
+        const uint32_t boot_tiles = bt ? (uint32_t)atoi(bt) : 8u;  // 8 x 8192 candidate starts
+        bp.tiles_total = std::min(tiles_all, std::max(1u, boot_tiles));
+        bp.out = d_best;
+        bp.self_exclude = 1;
+        bp.wildcard = 0;
+        bp.ranged = 0;
+        bp.w_lo = bp.w_hi = bp.c1_lo = bp.c1_hi = bp.c2_lo = bp.c2_hi = 0;
+        const bool generic = W > (uint32_t)kMaxRegW;
+        const uint32_t qpt = generic ? 1u : (uint32_t)queries_per_thread(W, three);
+        const uint32_t qblocks = (len + kThreads * qpt - 1) / (kThreads * qpt);
+        uint32_t want = std::max(1u, std::min((4736 + qblocks - 1) / qblocks, bp.tiles_total));
+        bp.tiles_per_chunk = (bp.tiles_total + want - 1) / want;
+        cudaError_t e = generic ? launch_allpairs_generic(bp, three, crick, crick ? g->rc_view() : g->view(), st, nullptr)
+                                : launch_allpairs(bp, three, crick, st, nullptr);
+        if (e != cudaSuccess) return fail(cuda_code(e), "bootstrap launch: %s", cudaGetErrorString(e));
+        ++nl;
+    }
+    // ---- diagonal bands in slabs; thresholds (block maxima of d_best) refreshed per slab ----
+    const uint32_t bm_shift = 8;
+    const uint32_t n_blocks = (M >> bm_shift) + 1;
+    uint32_t *d_bm = nullptr;
+    CU(cudaMallocAsync(&d_bm, (size_t)n_blocks * 4, st));
+    const char *rs = getenv("K4B_DIAG_ROWS");
+    const uint32_t rows_per_seg = rs ? (uint32_t)atoi(rs) : 4096u;
+    const uint64_t gw = ((uint64_t)M + kDiagGroupDiagonals - 1) / kDiagGroupDiagonals;            // s = 1..M
+    const uint64_t gc = crick ? (2ull * M + 1 + kDiagGroupDiagonals - 1) / kDiagGroupDiagonals : 0;  // s = -M..M
+    const char *sl = getenv("K4B_DIAG_SLABS");
+    uint32_t n_slabs = sl ? (uint32_t)atoi(sl) : 8u;
+    n_slabs = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_slabs, (gw + gc) / (4ull * nparts) + 1));
+    DiagParams dp;
+    dp.a = g->view();
+    dp.K = K;
+    dp.M = M;
+    dp.rows_per_seg = rows_per_seg;
+    dp.n_seg = (uint32_t)(((uint64_t)M + 1 + rows_per_seg - 1) / rows_per_seg);
+    dp.best = d_best;
+    dp.blockmax = d_bm;
+    dp.bm_shift = bm_shift;
+    dp.grp_step = nparts * n_slabs;
+    cudaError_t e = cudaEventRecord(g_ev0, st);
+    for (uint32_t slab = 0; slab < n_slabs && e == cudaSuccess; ++slab) {
+        e = launch_blockmax(d_best, g->view(), M + 1, bm_shift, d_bm, n_blocks, st);
+        ++nl;
+        dp.grp_first = part + nparts * slab;
+        for (int strand = 0; strand < (crick ? 2 : 1) && e == cudaSuccess; ++strand) {
+            const uint64_t ngroups_all = strand ? gc : gw;
+            if (dp.grp_first >= ngroups_all) continue;
+            const uint32_t ng = (uint32_t)((ngroups_all - dp.grp_first + dp.grp_step - 1) / dp.grp_step);
+            dp.crick = strand;
+            dp.b = strand ? g->rc_view() : g->view();
+            dp.s_first = strand ? -(long long)M : 1;
+            // the 1-D grid is limited to 2^31-1 CTAs: split very large launches by groups
+            const uint32_t max_groups = std::max(1u, 0x7fffffffu / dp.n_seg);
+            DiagParams q = dp;
+            for (uint32_t done = 0; done < ng && e == cudaSuccess; done += max_groups) {
+                q.grp_first = dp.grp_first + done * dp.grp_step;
+                e = launch_diag(q, three, std::min(max_groups, ng - done), st, nullptr);
+                ++nl;
+            }
+        }
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(g_ev1, st);
+    cudaFreeAsync(d_bm, st);
+    if (e != cudaSuccess) return fail(cuda_code(e), "diagonal engine launch: %s", cudaGetErrorString(e));
+    if (launches) *launches = nl;
+    g_diag_launches = nl;
+    return K4B_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // host-buffer entry points
 // ------------------------------------------------------------------------------------------
 namespace {
@@ -614,6 +766,91 @@ int make_sweep(uint32_t len, uint32_t K, uint32_t sweep_start, uint32_t sweep_en
 }
 }  // namespace
 
+// full-sweep exhaustive run on the diagonal engine: the pair matrix (not the queries) is
+// partitioned over the devices, each keeps a complete array of running minima, and the arrays
+// meet in ONE ncclAllReduce(min) - the single exchange step of the symmetric formulation
+static int run_exhaustive_diag(const uint8_t *concat, uint32_t len, uint32_t K, int both,
+                               uint16_t *out_min) {
+    RC(ensure_init());
+    const int n = (int)g_eng.devs.size();
+    PhaseTrace trace;
+    std::vector<k4b_packed *> imgs;
+    std::vector<uint32_t *> bests(n, nullptr);
+    uint16_t *d_out = nullptr, *h_out = nullptr;
+    int rc = 0;
+    do {
+        CU(cudaSetDevice(g_eng.devs[0]));
+        k4b_packed *g0 = nullptr;
+        if ((rc = k4b_pack_host(concat, len, K, &g0))) break;
+        rc = broadcast_packed(g0, imgs);
+        if (imgs.empty()) imgs.push_back(g0);
+        if (rc) break;
+        trace.mark("H2D + pack (+bcast)");
+        for (int i = 0; i < n && !rc; ++i) {
+            cudaError_t e = cudaSetDevice(g_eng.devs[i]);
+            if (e == cudaSuccess) e = cudaMalloc(&bests[i], (size_t)len * 4);
+            if (e != cudaSuccess) {
+                rc = fail(cuda_code(e), "minima buffer: %s", cudaGetErrorString(e));
+                break;
+            }
+            rc = k4b_best_init_device(bests[i], len, K, g_eng.streams[i]);
+            if (!rc) rc = k4b_exhaustive_diag_device(imgs[i], both, (uint32_t)i, (uint32_t)n, bests[i], g_eng.streams[i], nullptr);
+        }
+        if (rc) break;
+        trace.mark("launch");
+        if (n > 1) {
+            int nr = g_eng.nccl.GroupStart();
+            for (int i = 0; i < n && !nr; ++i)
+                nr = g_eng.nccl.AllReduce(bests[i], bests[i], len, kNcclUint32, kNcclMin, g_eng.comms[i], g_eng.streams[i]);
+            const int nr2 = g_eng.nccl.GroupEnd();
+            if (nr || nr2) {
+                rc = fail(K4B_ERR_NCCL, "ncclAllReduce(min): %s", g_eng.nccl.GetErrorString(nr ? nr : nr2));
+                break;
+            }
+        }
+        cudaError_t e = cudaSetDevice(g_eng.devs[0]);
+        if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)len * 2);
+        if (e == cudaSuccess) e = cudaMallocHost(&h_out, (size_t)len * 2);
+        if (e != cudaSuccess) {
+            rc = fail(cuda_code(e), "result buffers: %s", cudaGetErrorString(e));
+            break;
+        }
+        if ((rc = k4b_best_finalize_device(imgs[0], bests[0], d_out, g_eng.streams[0]))) break;
+        e = cudaMemcpyAsync(h_out, d_out, (size_t)len * 2, cudaMemcpyDeviceToHost, g_eng.streams[0]);
+        for (int i = 0; i < n; ++i) {
+            cudaSetDevice(g_eng.devs[i]);
+            const cudaError_t e2 = cudaStreamSynchronize(g_eng.streams[i]);
+            if (e2 != cudaSuccess && e == cudaSuccess) e = e2;
+        }
+        if (e != cudaSuccess) {
+            rc = fail(cuda_code(e), "diagonal engine: %s", cudaGetErrorString(e));
+            break;
+        }
+        trace.mark("kernels + D2H");
+        for (uint32_t p = 0; p < len; ++p)
+            if (h_out[p] <= K && h_out[p] < out_min[p]) out_min[p] = h_out[p];
+        trace.mark("host gather");
+    } while (0);
+    for (int i = 0; i < n; ++i) {
+        cudaSetDevice(g_eng.devs[i]);
+        if (bests[i]) cudaFree(bests[i]);
+        if ((size_t)i < imgs.size() && imgs[i]) k4b_packed_free(imgs[i]);
+    }
+    cudaSetDevice(g_eng.devs[0]);
+    if (d_out) cudaFree(d_out);
+    if (h_out) cudaFreeHost(h_out);
+    return rc;
+}
+
+// auto: the band engine pays off once the pair matrix is large; tiny inputs stay on the
+// all-pairs kernel (one launch)
+static bool use_diag_engine(uint32_t len, uint32_t K) {
+    const int e = engine_setting();
+    if (e == 1) return false;
+    if (e == 2) return len >= K;
+    return len >= 200000u;
+}
+
 extern "C" int k4b_hamm_exhaustive_shard(const uint8_t *concat, uint32_t concat_len, uint32_t K,
                                          int both_strands, uint32_t q_begin, uint32_t q_end,
                                          uint16_t *out_min) {
@@ -632,6 +869,8 @@ extern "C" int k4b_hamm_exhaustive(const uint8_t *concat, uint32_t concat_len, u
     RC(check_k(K, K4B_MIN_K, K4B_MAX_K));
     SweepRange sweep;
     RC(make_sweep(concat_len, K, sweep_start, sweep_end, sweep));
+    if (!sweep.ranged && use_diag_engine(concat_len, K))
+        return run_exhaustive_diag(concat, concat_len, K, both_strands, out_min);
     return run_sharded(concat, concat_len, nullptr, 0, K, both_strands, 1, 0, concat_len, 0, 1,
                        sweep, [&](uint32_t pos, uint16_t v) {
                            if (v <= K && v < out_min[pos]) out_min[pos] = v;

@@ -85,6 +85,40 @@ __device__ __forceinline__ uint32_t mism_word(const SideWords<P> &w, uint32_t t)
     return m;
 }
 
+// slow path, out of line so that the unrolled hot loop stays small: exact distance of the
+// flagged diagonals of `row`, then min-update of both K-mers of each pair
+template <int NP>
+struct Counters {
+    uint32_t c[NP];
+};
+template <int NP>
+__device__ __noinline__ void diag_flush(Counters<NP> cs, uint32_t flags, uint32_t bias, long long row,
+                                        long long s0, long long M, int crick,
+                                        const uint32_t *__restrict__ valid, uint32_t *__restrict__ best) {
+    while (flags) {
+        const uint32_t k = __ffs(flags) - 1;
+        flags &= flags - 1;
+        uint32_t val = 0;
+#pragma unroll
+        for (int b = 0; b < NP; ++b) val |= ((cs.c[b] >> k) & 1u) << b;
+        const uint32_t d = val - bias;
+        const long long jc = row + s0 + k;
+        long long j;
+        bool ok;
+        if (!crick) {
+            j = jc;
+            ok = j <= M;
+        } else {
+            j = M - jc;
+            ok = jc >= 0 && jc <= M;
+        }
+        if (!ok || row > M) continue;
+        if (!((valid[row >> 5] >> (row & 31)) & (valid[j >> 5] >> (j & 31)) & 1u)) continue;
+        if (d < best[row]) atomicMin(&best[row], d);
+        if (d < best[j]) atomicMin(&best[j], d);
+    }
+}
+
 template <int NP, int P>
 __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagParams prm) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,31 +168,14 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
 #pragma unroll
     for (int b = 0; b < NP; ++b) c[b] = ((bias >> b) & 1u) ? 0xffffffffu : 0u;
 
-    // slow path: exact distance of the flagged diagonals of `row`, min-update of both K-mers
+    const uint32_t *valid = prm.a.valid();
+    uint32_t *best = prm.best;
+    const int crick = prm.crick;
     auto flush = [&](uint32_t flags, long long row) {
-        while (flags) {
-            const uint32_t k = __ffs(flags) - 1;
-            flags &= flags - 1;
-            uint32_t val = 0;
+        Counters<NP> cs;
 #pragma unroll
-            for (int b = 0; b < NP; ++b) val |= ((c[b] >> k) & 1u) << b;
-            const uint32_t d = val - bias;
-            const long long jc = row + s0 + k;
-            long long j;
-            bool ok;
-            if (!prm.crick) {
-                j = jc;
-                ok = j <= M;
-            } else {
-                j = M - jc;
-                ok = jc >= 0 && jc <= M;
-            }
-            if (!ok || row > M) continue;
-            const uint32_t *v = prm.a.valid();
-            if (!((v[row >> 5] >> (row & 31)) & (v[j >> 5] >> (j & 31)) & 1u)) continue;
-            if (d < prm.best[row]) atomicMin(&prm.best[row], d);
-            if (d < prm.best[j]) atomicMin(&prm.best[j], d);
-        }
+        for (int b = 0; b < NP; ++b) cs.c[b] = c[b];
+        diag_flush<NP>(cs, flags, bias, row, s0, M, crick, valid, best);
     };
 
     // ---- warm-up: the first K bases of the window enter, nothing leaves ----

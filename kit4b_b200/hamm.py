@@ -60,6 +60,12 @@ SIGNATURES = {
     "k4b_allpairs_min_device": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32,
                                                ctypes.c_uint32, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
     "k4b_last_kernel_ms": (ctypes.c_float, []),
+    "k4b_set_engine": (ctypes.c_int, [ctypes.c_int]),
+    "k4b_get_engine": (ctypes.c_int, []),
+    "k4b_best_init_device": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, _vp]),
+    "k4b_exhaustive_diag_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp,
+                                                  ctypes.POINTER(ctypes.c_int)]),
+    "k4b_best_finalize_device": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "k4b_microbench_intpipe": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
 }
 
@@ -213,6 +219,34 @@ def allpairs_min_device(queries: Packed, targets: Packed, both_strands: bool, se
     _check(load_lib().k4b_allpairs_min_device(queries.handle, targets.handle, int(both_strands), int(self_exclude),
                                               q_begin, q_end, clamp, _vp(d_out_ptr), _vp(stream), ctypes.byref(n)))
     return n.value
+
+
+ENGINE_AUTO, ENGINE_POPC, ENGINE_DIAG = 0, 1, 2
+
+
+def set_engine(engine: int) -> None:
+    """0 automatic, 1 POPC all-pairs, 2 diagonal bands (exhaustive full sweeps only)."""
+    _check(load_lib().k4b_set_engine(engine))
+
+
+def get_engine() -> int:
+    return load_lib().k4b_get_engine()
+
+
+def best_init_device(d_best_ptr: int, n: int, K: int, stream: int = 0) -> None:
+    _check(load_lib().k4b_best_init_device(_vp(d_best_ptr), n, K, _vp(stream)))
+
+
+def exhaustive_diag_device(g: Packed, both_strands: bool, part: int, nparts: int, d_best_ptr: int,
+                           stream: int = 0) -> int:
+    n = ctypes.c_int(0)
+    _check(load_lib().k4b_exhaustive_diag_device(g.handle, int(both_strands), part, nparts, _vp(d_best_ptr),
+                                                 _vp(stream), ctypes.byref(n)))
+    return n.value
+
+
+def best_finalize_device(g: Packed, d_best_ptr: int, d_out_ptr: int, stream: int = 0) -> None:
+    _check(load_lib().k4b_best_finalize_device(g.handle, _vp(d_best_ptr), _vp(d_out_ptr), _vp(stream)))
 
 
 def packed_image_bytes(length: int) -> int:
