@@ -5,11 +5,11 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (config.workload): BASELINE.json configs[1] - `hammings -m1 -K50 -c` all-vs-all over a
-10 Mbp synthetic bacterial-scale multifasta.  A full pass is 2e14 K-mer comparisons (minutes
-on one GPU), so one *step* is one query batch: `--batch` consecutive query K-mers per GPU
-against ALL 10 M target K-mers on both strands.  Work per query is uniform, so batch
-throughput equals whole-job throughput.  With N GPUs every rank takes its own batch (weak
-scaling: per-GPU work fixed) after ONE NCCL broadcast of the packed target set from rank 0.
+10 Mbp synthetic bacterial-scale multifasta: 2e14 K-mer comparisons.  One *step* is that WHOLE
+job on the diagonal-band engine (about 5 s on one B200).  With N GPUs the pair matrix of the
+same job is partitioned over the ranks (strong scaling) after ONE NCCL broadcast of the packed
+sequence set; the per-rank minima meet in all_reduce(MIN).  `--engine popc` benchmarks the
+XOR/fold/POPC all-pairs kernel alone on query batches (a full pass would take minutes).
 
 Printed JSON (one line, rank 0):
   value     Gcmp/s with inputs resident in HBM (CUDA events around exactly K steps, max over
@@ -17,10 +17,10 @@ Printed JSON (one line, rank 0):
   e2e       same metric through the host-buffer C ABI / distributed host API: every step
             copies the 1-byte/base concat host->device, packs, (broadcasts), compares, and
             reads the minima back
-  roofline  integer-pipe roofline of the dominant kernel (allpairs_min): achieved = word-compares
-            (32-base XOR/fold/POPC units) per second over the kernel's own CUDA-event time;
-            peak = POPC issue rate measured live by the register-resident microbenchmark
-            (1 POPC per word-compare)
+  roofline  integer-pipe roofline of the dominant kernel: bands - ALU-pipe thread-ops (SHF/LOP3 per
+            32-cell row step, counted from SASS) per second over the band launches' own CUDA-event
+            time vs the LOP3 rate measured live; popc - word-compares per second vs the POPC rate
+            measured live (1 POPC per 32-base word-compare)
   cpu_baseline  the reference's own CPU engine (oracle/_ref, unmodified sources) timed on this
             host on a bounded sample of the same workload
 `--impl reference` times only that CPU engine, with all host threads, on the same config.
@@ -224,13 +224,10 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
-def run_ours(args):
+def _setup(args):
     import torch
     import torch.distributed as dist
     import kit4b_b200 as k4b
-    from kit4b_b200 import hamm
-    from kit4b_b200.dist import CudaEngine, exhaustive_distributed, shard_bounds
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -241,6 +238,24 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     k4b.gpu_init(1, [local])
+    return torch, dist, k4b, world, rank, local, dev
+
+
+def _traffic(key):
+    tr_path = os.path.join(ROOT, "profiles", "dram_bytes.json")
+    try:
+        return json.load(open(tr_path)).get(key)
+    except Exception:
+        return None
+
+
+def run_ours_bands(args):
+    """Default: one step = the WHOLE all-vs-all job of the workload on the diagonal-band engine
+    (sharded bootstrap -> all_reduce(MIN) -> this rank's part of the pair matrix -> all_reduce(MIN)
+    -> finalize).  N GPUs split the same job: strong scaling."""
+    torch, dist, k4b, world, rank, local, dev = _setup(args)
+    from kit4b_b200 import hamm
+    from kit4b_b200.dist import CudaEngine, exhaustive_distributed_bands, shard_bounds
 
     def barrier():
         if world > 1:
@@ -250,12 +265,9 @@ def run_ours(args):
     concat, chroms, K, both = synth_genome(args.workload)
     L = len(concat)
     S = 2 if both else 1
-    W = (K + 31) // 32
-    Nt = valid_count(chroms, K)
-    B = min(args.batch, L)
+    Nv = valid_count(chroms, K)
     engine = CudaEngine(dev)
-
-    # ---- setup (untimed): rank 0 packs, ONE NCCL broadcast of the packed target set ----
+    # ---- setup (untimed): rank 0 packs, ONE NCCL broadcast of the packed sequence set ----
     if rank == 0:
         image, packed, non_acgt = engine.pack(concat, K)
         flag = torch.tensor([int(non_acgt)], dtype=torch.int64, device=dev)
@@ -269,6 +281,164 @@ def run_ours(args):
         packed = engine.adopt(image, L, K, bool(flag.item()))
     torch.cuda.synchronize()
 
+    best = torch.empty(L, dtype=torch.int32, device=dev)
+    out = torch.empty(L, dtype=torch.int16, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream(dev)
+    qb, qe = shard_bounds(0, L, world)[rank]
+
+    def step():
+        n = 1
+        hamm.best_init_device(best.data_ptr(), L, K, stream.cuda_stream)
+        hamm.diag_bootstrap_device(packed, both, qb, qe, best.data_ptr(), stream.cuda_stream)
+        n += 1
+        if world > 1:
+            dist.all_reduce(best, op=dist.ReduceOp.MIN)
+        n += hamm.diag_bands_device(packed, both, rank, world, best.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.all_reduce(best, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            hamm.best_finalize_device(packed, best.data_ptr(), out.data_ptr(), stream.cuda_stream)
+            n += 1
+        return n
+
+    for i in range(args.warmup):
+        flush.fill_(i & 0xFF)
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches, band_ms = 0, []
+    ev0.record(stream)
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (inside the bracket: ~0.1 ms)
+        launches += step() + 1
+        band_ms.append(hamm.last_kernel_ms())  # CUDA events around this rank's band launches
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    cmps_per_step = float(Nv) * float(Nv) * S
+    value = cmps_per_step * args.steps / (ms_max * 1e-3) / 1e9
+    checksum = int(out.to(torch.int64).sum().item()) if rank == 0 else 0
+
+    # roofline of the dominant kernel (this rank's band launches of one step)
+    k_ms = float(np.mean(band_ms))
+    np_planes = 1
+    while (1 << (np_planes - 1)) < K + 1:
+        np_planes += 1
+    ops_per_rowstep = 10 + 2 * np_planes           # per-thread ALU-pipe instructions per 32-cell row step (SASS)
+    cells = cmps_per_step / 2.0 / world            # every cell serves the two K-mers of a pair
+    achieved = cells / 32.0 * ops_per_rowstep / (k_ms * 1e-3) / 1e9
+    peak = hamm.microbench_intpipe(1, 4000)        # measured LOP3 thread-ops/s on this GPU
+    roofline = {"bound": "int_pipe(alu: lop3/shf)", "achieved": achieved, "peak": peak, "unit": "Gop/s",
+                "frac": achieved / peak, "traffic": _traffic(args.workload + "_bands"),
+                "kernel": "diag_min_kernel<NP=%d,P=2> (all band launches of one step on this rank)" % np_planes,
+                "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / ms if ms > 0 else None,
+                "ops_model": "%d ALU-pipe thread-ops per 32-cell row step (4 SHF + 4 LOP3 mismatch words, %d LOP3 "
+                             "ripple, 1 ISETP; row-base sign extension runs on the uniform pipe); cells = "
+                             "valid pairs, each serving 2 comparisons" % (ops_per_rowstep, 2 * np_planes + 1),
+                "peak_source": "measured live: register-resident LOP3 microbenchmark (k4b_microbench_intpipe), "
+                               "nominal 64 lanes/clk/SM x 148 SMs x 1.965 GHz = 18614",
+                "hbm_note": "planes (%.1f MB) are L2 resident; HBM is not the bound" % (hamm.packed_image_bytes(L) / 1e6)}
+
+    # ---- end-to-end through the host-buffer API ----
+    e2e_steps = args.e2e_steps if args.e2e_steps is not None else args.steps
+    pinned = torch.from_numpy(concat).pin_memory()
+    h_concat = pinned.numpy()
+
+    def e2e_step():
+        if world == 1:
+            return hamm.exhaustive(h_concat, K, both)          # k4b_hamm_exhaustive, host buffers
+        return exhaustive_distributed_bands(h_concat if rank == 0 else None, K, both, engine=engine)
+
+    e2e_sum = None
+    for i in range(args.warmup if e2e_steps else 0):
+        e2e_step()
+        engine.keep.clear()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        r = e2e_step()
+        engine.keep.clear()
+        if rank == 0:
+            e2e_sum = int(r.astype(np.int64).sum())
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_val = cmps_per_step * e2e_steps / float(tt.item()) / 1e9 if e2e_steps else None
+    e2e = {"value": e2e_val, "unit": "Gcmp/s", "h2d_bytes_per_step": int(L), "d2h_bytes_per_step": int(2 * L),
+           "steps": e2e_steps, "result_checksum_equals_resident_run": (e2e_sum == checksum) if e2e_steps else None,
+           "api": "k4b_hamm_exhaustive (host buffers)" if world == 1 else
+                  "kit4b_b200.dist.exhaustive_distributed_bands (rank-0 host buffer, NCCL broadcast + 2 all_reduce MIN)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_reference_sample(args.workload, target_seconds=args.cpu_seconds)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": "kmer_comparisons_per_sec", "value": value, "unit": "Gcmp/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / max(1, args.steps),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESCR[args.workload], "K": K, "both_strands": both,
+                       "genome_bases": int(L), "kmers": int(Nv),
+                       "step": "the whole all-vs-all job: every K-mer vs every K-mer, %s (%.3g comparisons)"
+                               % ("both strands" if both else "Watson only", cmps_per_step),
+                       "engine": "diagonal bands (bit-sliced sliding counters) bootstrapped by the POPC all-pairs kernel",
+                       "parallelism": "pair-matrix partition x%d + all_reduce(MIN)" % world,
+                       "l2": "256 MB flush write between timed steps", "result_checksum": checksum},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    k4b.gpu_shutdown()
+
+
+def run_ours_popc(args):
+    """--engine popc: the XOR/fold/POPC all-pairs kernel alone.  A full pass takes minutes, so a
+    step is one query batch per GPU against all targets (per-query work is uniform); weak scaling."""
+    torch, dist, k4b, world, rank, local, dev = _setup(args)
+    from kit4b_b200 import hamm
+    from kit4b_b200.dist import CudaEngine, exhaustive_distributed, shard_bounds
+    hamm.set_engine(hamm.ENGINE_POPC)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    concat, chroms, K, both = synth_genome(args.workload)
+    L = len(concat)
+    S = 2 if both else 1
+    W = (K + 31) // 32
+    Nt = valid_count(chroms, K)
+    B = min(args.batch, L)
+    engine = CudaEngine(dev)
+    if rank == 0:
+        image, packed, non_acgt = engine.pack(concat, K)
+        flag = torch.tensor([int(non_acgt)], dtype=torch.int64, device=dev)
+    else:
+        image = engine.empty_image(L)
+        flag = torch.zeros(1, dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(flag, src=0)
+        dist.broadcast(image, src=0)
+    if rank != 0:
+        packed = engine.adopt(image, L, K, bool(flag.item()))
+    torch.cuda.synchronize()
     lo, hi = shard_bounds(0, L, world)[rank]
 
     def batch_range(i):
@@ -277,7 +447,7 @@ def run_ours(args):
         return b, min(b + B, hi)
 
     out = torch.empty(B, dtype=torch.int16, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def step(i):
@@ -285,7 +455,6 @@ def run_ours(args):
         n = engine.compute(packed, both, b, e, out)
         return n, valid_count(chroms, K, b, e)
 
-    # ---- device-resident timing: W warm-up, exactly K timed steps ----
     for i in range(args.warmup):
         flush.fill_(i & 0xFF)
         step(i)
@@ -296,11 +465,11 @@ def run_ours(args):
     launches, nq_total, kernel_ms = 0, 0, []
     ev0.record(stream)
     for i in range(args.steps):
-        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (inside the bracket: ~0.1 ms)
+        flush.fill_(i & 0xFF)
         n, nq = step(args.warmup + i)
         launches += n + 1
         nq_total += nq
-        kernel_ms.append(hamm.last_kernel_ms())  # CUDA events around the allpairs kernel itself
+        kernel_ms.append(hamm.last_kernel_ms())
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -311,31 +480,16 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(q, op=dist.ReduceOp.SUM)
     ms_max, nq_all = float(t.item()), float(q.item())
-    cmps = nq_all * Nt * S
-    value = cmps / (ms_max * 1e-3) / 1e9
-
-    # roofline of the dominant kernel on this rank
+    value = nq_all * Nt * S / (ms_max * 1e-3) / 1e9
     k_ms = float(np.mean(kernel_ms))
-    wc_per_launch = (nq_total / max(1, args.steps)) * Nt * S * W
-    achieved = wc_per_launch / (k_ms * 1e-3) / 1e9
-    peak = hamm.microbench_intpipe(0, 4000)  # measured POPC lanes/s on this GPU
-    traffic = None
-    tr_path = os.path.join(ROOT, "profiles", "allpairs_dram_bytes.json")
-    if os.path.exists(tr_path):
-        try:
-            traffic = json.load(open(tr_path)).get(args.workload)
-        except Exception:
-            traffic = None
+    achieved = (nq_total / max(1, args.steps)) * Nt * S * W / (k_ms * 1e-3) / 1e9
+    peak = hamm.microbench_intpipe(0, 4000)
     roofline = {"bound": "int_pipe(popc)", "achieved": achieved, "peak": peak, "unit": "Gwc/s",
-                "frac": achieved / peak, "traffic": traffic,
+                "frac": achieved / peak, "traffic": _traffic(args.workload + "_popc"),
                 "kernel": "allpairs_min_kernel<W=%d>" % W, "kernel_ms": k_ms,
                 "kernel_share_of_step": k_ms * args.steps / ms if ms > 0 else None,
-                "peak_source": "measured live: register-resident POPC microbenchmark (k4b_microbench_intpipe), "
-                               "1 POPC per 32-base word-compare; nominal 16 lanes/clk/SM x 148 SMs x 1.965 GHz = 4654",
-                "hbm_note": "target planes (%.1f MB) stay L2-resident; HBM is not the bound"
-                            % (hamm.packed_image_bytes(L) / 1e6)}
-
-    # ---- end-to-end through the host-buffer API (H2D concat + pack + compare + D2H) ----
+                "peak_source": "measured live: register-resident POPC microbenchmark, 1 POPC per 32-base "
+                               "word-compare; nominal 16 lanes/clk/SM x 148 SMs x 1.965 GHz = 4654"}
     e2e_steps = args.e2e_steps if args.e2e_steps is not None else args.steps
     pinned = torch.from_numpy(concat).pin_memory()
     h_concat = pinned.numpy()
@@ -346,14 +500,13 @@ def run_ours(args):
             b, e = batch_range(i)
             hamm.exhaustive_shard(h_concat, K, both, b, e, host_out)
             return valid_count(chroms, K, b, e), (e - b) * 2
-        # N ranks: global batch of world*B queries starting at a step-dependent offset
         gb = (i * world * B) % max(1, L - world * B)
         ge = min(gb + world * B, L)
         exhaustive_distributed(h_concat if rank == 0 else None, K, both, gb, ge, engine=engine)
         engine.keep.clear()
         return valid_count(chroms, K, gb, ge), (ge - gb) * 2
 
-    for i in range(args.warmup if e2e_steps else 0):  # first calls pay one-off allocations
+    for i in range(args.warmup if e2e_steps else 0):
         e2e_step(i)
     barrier()
     t0 = time.perf_counter()
@@ -367,17 +520,14 @@ def run_ours(args):
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e_val = (nq_e2e * Nt * S) / float(tt.item()) / 1e9 if e2e_steps else None
-    e2e = {"value": e2e_val, "unit": "Gcmp/s", "h2d_bytes_per_step": int(L), "d2h_bytes_per_step": int(d2h),
-           "steps": e2e_steps,
+    e2e = {"value": (nq_e2e * Nt * S) / float(tt.item()) / 1e9 if e2e_steps else None, "unit": "Gcmp/s",
+           "h2d_bytes_per_step": int(L), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
            "api": "k4b_hamm_exhaustive_shard (host buffers)" if world == 1 else
                   "kit4b_b200.dist.exhaustive_distributed (rank-0 host buffer, NCCL broadcast, gather)"}
-
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_reference_sample(args.workload, target_seconds=args.cpu_seconds)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-
     if rank == 0:
         line = {
             "metric": "kmer_comparisons_per_sec", "value": value, "unit": "Gcmp/s", "n_gpus": world,
@@ -387,6 +537,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD_DESCR[args.workload], "K": K, "both_strands": both,
                        "genome_bases": int(L), "target_kmers": int(Nt),
                        "step": "query batch of %d K-mers per GPU vs all targets, both strands" % B,
+                       "engine": "POPC all-pairs kernel only (--engine popc)",
                        "global_batch_queries": int(B * world), "parallelism": "query-shard x%d" % world,
                        "l2": "256 MB flush write between timed steps"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
@@ -406,7 +557,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=131072, help="query K-mers per GPU per step")
+    ap.add_argument("--engine", default="bands", choices=["bands", "popc"],
+                    help="bands: diagonal-band engine, step = whole job (default); popc: all-pairs POPC kernel, step = query batch")
+    ap.add_argument("--batch", type=int, default=131072, help="--engine popc: query K-mers per GPU per step")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the reference sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -415,8 +568,10 @@ def main():
         args.warmup = 3 if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.engine == "popc":
+        run_ours_popc(args)
     else:
-        run_ours(args)
+        run_ours_bands(args)
 
 
 if __name__ == "__main__":

@@ -155,6 +155,14 @@ int k4b_best_init_device(uint32_t *d_best, uint32_t n, uint32_t K, void *stream)
 int k4b_exhaustive_diag_device(k4b_packed *g, int both_strands, uint32_t part, uint32_t nparts,
                                uint32_t *d_best, void *stream, int *launches);
 int k4b_best_finalize_device(k4b_packed *g, const uint32_t *d_best, uint16_t *d_out_min, void *stream);
+/* The two phases of k4b_exhaustive_diag_device, for multi-GPU runs that shard both:
+ * bootstrap = K-mers starting in [q_begin,q_end) against a small target sample (POPC engine);
+ * bands = part `part` of `nparts` of the pair matrix.  Combine d_best across ranks by an
+ * element-wise minimum after each phase. */
+int k4b_diag_bootstrap_device(k4b_packed *g, int both_strands, uint32_t q_begin, uint32_t q_end,
+                              uint32_t *d_best, void *stream);
+int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t part, uint32_t nparts,
+                          uint32_t *d_best, void *stream, int *launches);
 
 /* ---- integer-pipe roofline microbenchmark ----------------------------------- */
 /* which: 0 POPC only, 1 LOP3 only, 2 engine mix (2 LOP3 + 1 POPC + min), 3 IADD3 only.

@@ -464,31 +464,12 @@ extern "C" int k4b_best_finalize_device(k4b_packed *g, const uint32_t *d_best, u
     return K4B_OK;
 }
 
-static thread_local int g_diag_launches = 0;
-
-// All-vs-all minima of `g` by diagonal bands; this call covers part `part` of `nparts`
-// (interleaved CTA groups of 8192 diagonals) and lowers d_best (uint32[len], initialised to
-// K+1 by the caller) with atomicMin.  Parts are independent; their d_best arrays combine with
-// an element-wise minimum (ncclAllReduce / torch.distributed all_reduce MIN).
-extern "C" int k4b_exhaustive_diag_device(k4b_packed *g, int both_strands, uint32_t part,
-                                          uint32_t nparts, uint32_t *d_best, void *stream,
-                                          int *launches) {
-    if (launches) *launches = 0;
-    if (!g || !d_best) return fail(K4B_ERR_PARAMS, "NULL argument");
-    if (!nparts || part >= nparts) return fail(K4B_ERR_PARAMS, "part %u of %u", part, nparts);
+static int diag_prepare(k4b_packed *g, bool crick, cudaStream_t st, int *nl) {
     CU(cudaSetDevice(g->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    const uint32_t K = g->K, len = g->len;
-    int nl = 0;
-    if (len < K) return K4B_OK;
-    const uint32_t M = len - K;
-    const bool three = g->has_non_acgt != 0;
-    const bool crick = both_strands != 0;
-    const uint32_t W = (K + 31) / 32;
     if (crick && !g->d_rc_planes) {
         CU(cudaMalloc(&g->d_rc_planes, (size_t)g->stride * 12));
         CU(launch_revcomp_planes(g->view(), g->rc_view(), st));
-        ++nl;
+        ++*nl;
     }
     if (g_ev_dev != g->device) {
         if (g_ev0) {
@@ -499,35 +480,64 @@ extern "C" int k4b_exhaustive_diag_device(k4b_packed *g, int both_strands, uint3
         CU(cudaEventCreate(&g_ev1));
         g_ev_dev = g->device;
     }
-    // ---- bootstrap: every K-mer against a small sample of targets with the POPC engine, so
-    //      that the thresholds of the band kernel start near the final minima ----
-    {
-        AllPairsParams bp;
-        bp.q = g->view();
-        bp.t = g->view();
-        bp.K = K;
-        bp.q_begin = 0;
-        bp.q_end = len;
-        const uint32_t tiles_all = (g->nw + kTileGroups - 1) / kTileGroups;
-        const char *bt = getenv("K4B_BOOT_TILES");
-        const uint32_t boot_tiles = bt ? (uint32_t)atoi(bt) : 8u;  // 8 x 8192 candidate starts
-        bp.tiles_total = std::min(tiles_all, std::max(1u, boot_tiles));
-        bp.out = d_best;
-        bp.self_exclude = 1;
-        bp.wildcard = 0;
-        bp.ranged = 0;
-        bp.w_lo = bp.w_hi = bp.c1_lo = bp.c1_hi = bp.c2_lo = bp.c2_hi = 0;
-        const bool generic = W > (uint32_t)kMaxRegW;
-        const uint32_t qpt = generic ? 1u : (uint32_t)queries_per_thread(W, three);
-        const uint32_t qblocks = (len + kThreads * qpt - 1) / (kThreads * qpt);
-        uint32_t want = std::max(1u, std::min((4736 + qblocks - 1) / qblocks, bp.tiles_total));
-        bp.tiles_per_chunk = (bp.tiles_total + want - 1) / want;
-        cudaError_t e = generic ? launch_allpairs_generic(bp, three, crick, crick ? g->rc_view() : g->view(), st, nullptr)
-                                : launch_allpairs(bp, three, crick, st, nullptr);
-        if (e != cudaSuccess) return fail(cuda_code(e), "bootstrap launch: %s", cudaGetErrorString(e));
-        ++nl;
-    }
-    // ---- diagonal bands in slabs; thresholds (block maxima of d_best) refreshed per slab ----
+    return 0;
+}
+
+// Bootstrap of the band engine: the K-mers starting in [q_begin, q_end) against a small sample
+// of targets with the POPC engine, so that the thresholds of the band kernel start near the
+// final minima.  Shards of queries are independent (combine d_best by element-wise minimum).
+extern "C" int k4b_diag_bootstrap_device(k4b_packed *g, int both_strands, uint32_t q_begin,
+                                         uint32_t q_end, uint32_t *d_best, void *stream) {
+    if (!g || !d_best) return fail(K4B_ERR_PARAMS, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t K = g->K, len = g->len;
+    if (q_end > len) q_end = len;
+    if (len < K || q_begin >= q_end) return K4B_OK;
+    const bool three = g->has_non_acgt != 0, crick = both_strands != 0;
+    int nl = 0;
+    RC(diag_prepare(g, crick, st, &nl));
+    const uint32_t W = (K + 31) / 32;
+    AllPairsParams bp;
+    bp.q = g->view();
+    bp.t = g->view();
+    bp.K = K;
+    bp.q_begin = q_begin;
+    bp.q_end = q_end;
+    const uint32_t tiles_all = (g->nw + kTileGroups - 1) / kTileGroups;
+    const char *bt = getenv("K4B_BOOT_TILES");
+    const uint32_t boot_tiles = bt ? (uint32_t)atoi(bt) : 2u;  // 2 x 8192 candidate starts (profiles/r01_diag_tune_cfg2.log)
+    bp.tiles_total = std::min(tiles_all, std::max(1u, boot_tiles));
+    bp.out = d_best + q_begin;  // the kernel indexes out[] relative to q_begin
+    bp.self_exclude = 1;
+    bp.wildcard = 0;
+    bp.ranged = 0;
+    bp.w_lo = bp.w_hi = bp.c1_lo = bp.c1_hi = bp.c2_lo = bp.c2_hi = 0;
+    const bool generic = W > (uint32_t)kMaxRegW;
+    const uint32_t qpt = generic ? 1u : (uint32_t)queries_per_thread(W, three);
+    const uint32_t nq = q_end - q_begin;
+    const uint32_t qblocks = (nq + kThreads * qpt - 1) / (kThreads * qpt);
+    const uint32_t want = std::max(1u, std::min((4736 + qblocks - 1) / qblocks, bp.tiles_total));
+    bp.tiles_per_chunk = (bp.tiles_total + want - 1) / want;
+    const cudaError_t e = generic ? launch_allpairs_generic(bp, three, crick, crick ? g->rc_view() : g->view(), st, nullptr)
+                                  : launch_allpairs(bp, three, crick, st, nullptr);
+    if (e != cudaSuccess) return fail(cuda_code(e), "bootstrap launch: %s", cudaGetErrorString(e));
+    return K4B_OK;
+}
+
+// Diagonal bands: part `part` of `nparts` of the pair matrix (interleaved CTA groups of 8192
+// diagonals), in slabs with the thresholds (block maxima of d_best) refreshed per slab.
+extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t part, uint32_t nparts,
+                                     uint32_t *d_best, void *stream, int *launches) {
+    if (launches) *launches = 0;
+    if (!g || !d_best) return fail(K4B_ERR_PARAMS, "NULL argument");
+    if (!nparts || part >= nparts) return fail(K4B_ERR_PARAMS, "part %u of %u", part, nparts);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t K = g->K, len = g->len;
+    if (len < K) return K4B_OK;
+    const uint32_t M = len - K;
+    const bool three = g->has_non_acgt != 0, crick = both_strands != 0;
+    int nl = 0;
+    RC(diag_prepare(g, crick, st, &nl));
     const uint32_t bm_shift = 8;
     const uint32_t n_blocks = (M >> bm_shift) + 1;
     uint32_t *d_bm = nullptr;
@@ -537,7 +547,7 @@ extern "C" int k4b_exhaustive_diag_device(k4b_packed *g, int both_strands, uint3
     const uint64_t gw = ((uint64_t)M + kDiagGroupDiagonals - 1) / kDiagGroupDiagonals;            // s = 1..M
     const uint64_t gc = crick ? (2ull * M + 1 + kDiagGroupDiagonals - 1) / kDiagGroupDiagonals : 0;  // s = -M..M
     const char *sl = getenv("K4B_DIAG_SLABS");
-    uint32_t n_slabs = sl ? (uint32_t)atoi(sl) : 8u;
+    uint32_t n_slabs = sl ? (uint32_t)atoi(sl) : 16u;
     n_slabs = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_slabs, (gw + gc) / (4ull * nparts) + 1));
     DiagParams dp;
     dp.a = g->view();
@@ -575,7 +585,19 @@ extern "C" int k4b_exhaustive_diag_device(k4b_packed *g, int both_strands, uint3
     cudaFreeAsync(d_bm, st);
     if (e != cudaSuccess) return fail(cuda_code(e), "diagonal engine launch: %s", cudaGetErrorString(e));
     if (launches) *launches = nl;
-    g_diag_launches = nl;
+    return K4B_OK;
+}
+
+// bootstrap of every K-mer + this part's bands (single-call form)
+extern "C" int k4b_exhaustive_diag_device(k4b_packed *g, int both_strands, uint32_t part,
+                                          uint32_t nparts, uint32_t *d_best, void *stream,
+                                          int *launches) {
+    if (launches) *launches = 0;
+    if (!g) return fail(K4B_ERR_PARAMS, "NULL argument");
+    RC(k4b_diag_bootstrap_device(g, both_strands, 0, g->len, d_best, stream));
+    int nl = 0;
+    RC(k4b_diag_bands_device(g, both_strands, part, nparts, d_best, stream, &nl));
+    if (launches) *launches = nl + 1;
     return K4B_OK;
 }
 
@@ -794,20 +816,28 @@ static int run_exhaustive_diag(const uint8_t *concat, uint32_t len, uint32_t K, 
                 break;
             }
             rc = k4b_best_init_device(bests[i], len, K, g_eng.streams[i]);
-            if (!rc) rc = k4b_exhaustive_diag_device(imgs[i], both, (uint32_t)i, (uint32_t)n, bests[i], g_eng.streams[i], nullptr);
+            // bootstrap: every device takes a shard of the queries
+            const uint32_t qb = (uint32_t)((uint64_t)len * i / n), qe = (uint32_t)((uint64_t)len * (i + 1) / n);
+            if (!rc) rc = k4b_diag_bootstrap_device(imgs[i], both, qb, qe, bests[i], g_eng.streams[i]);
         }
         if (rc) break;
-        trace.mark("launch");
-        if (n > 1) {
+        auto allreduce_min = [&]() -> int {
+            if (n == 1) return 0;
             int nr = g_eng.nccl.GroupStart();
             for (int i = 0; i < n && !nr; ++i)
                 nr = g_eng.nccl.AllReduce(bests[i], bests[i], len, kNcclUint32, kNcclMin, g_eng.comms[i], g_eng.streams[i]);
             const int nr2 = g_eng.nccl.GroupEnd();
-            if (nr || nr2) {
-                rc = fail(K4B_ERR_NCCL, "ncclAllReduce(min): %s", g_eng.nccl.GetErrorString(nr ? nr : nr2));
-                break;
-            }
+            if (nr || nr2) return fail(K4B_ERR_NCCL, "ncclAllReduce(min): %s", g_eng.nccl.GetErrorString(nr ? nr : nr2));
+            return 0;
+        };
+        if ((rc = allreduce_min())) break;
+        for (int i = 0; i < n && !rc; ++i) {
+            cudaSetDevice(g_eng.devs[i]);
+            rc = k4b_diag_bands_device(imgs[i], both, (uint32_t)i, (uint32_t)n, bests[i], g_eng.streams[i], nullptr);
         }
+        if (rc) break;
+        trace.mark("launch");
+        if ((rc = allreduce_min())) break;
         cudaError_t e = cudaSetDevice(g_eng.devs[0]);
         if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)len * 2);
         if (e == cudaSuccess) e = cudaMallocHost(&h_out, (size_t)len * 2);

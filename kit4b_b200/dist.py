@@ -59,6 +59,69 @@ class CudaEngine:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         return hamm.allpairs_min_device(packed, packed, both, True, b, e, out.data_ptr(), 0, stream)
 
+    # ---- diagonal-band engine: the pair matrix is partitioned, minima meet in all_reduce(MIN) ----
+    def new_best(self, length: int, K: int) -> torch.Tensor:
+        best = torch.empty(length, dtype=torch.int32, device=self.device)
+        hamm.best_init_device(best.data_ptr(), length, K, torch.cuda.current_stream(self.device).cuda_stream)
+        return best
+
+    def bootstrap(self, packed, both: bool, b: int, e: int, best: torch.Tensor) -> int:
+        hamm.diag_bootstrap_device(packed, both, b, e, best.data_ptr(),
+                                   torch.cuda.current_stream(self.device).cuda_stream)
+        return 1
+
+    def bands(self, packed, both: bool, part: int, nparts: int, best: torch.Tensor) -> int:
+        return hamm.diag_bands_device(packed, both, part, nparts, best.data_ptr(),
+                                      torch.cuda.current_stream(self.device).cuda_stream)
+
+    def finalize(self, packed, best: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(best.numel(), dtype=torch.int16, device=self.device)
+        hamm.best_finalize_device(packed, best.data_ptr(), out.data_ptr(),
+                                  torch.cuda.current_stream(self.device).cuda_stream)
+        return out
+
+
+def exhaustive_distributed_bands(concat: Optional[np.ndarray], K: int, both: bool, engine=None,
+                                 group=None) -> Optional[np.ndarray]:
+    """Full all-vs-all minima on the diagonal-band engine over the ranks of `group`.
+
+    The symmetric formulation visits every unordered pair once and lowers both K-mers, so the
+    PAIR MATRIX (interleaved groups of diagonals) is partitioned instead of the queries; every
+    rank keeps a complete minima array and the arrays meet in all_reduce(MIN) - once after the
+    sharded bootstrap, once after the bands.  rank 0 passes the concat and gets
+    uint16[len(concat)] (K+1 where no K-mer starts); other ranks get None."""
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    if engine is None:
+        engine = CudaEngine(torch.device("cuda", torch.cuda.current_device()))
+    dev = engine.device
+    meta = torch.zeros(2, dtype=torch.int64, device=dev)
+    packed = None
+    image = None
+    if rank == 0:
+        image, packed, non_acgt = engine.pack(concat, K)
+        meta = torch.tensor([len(concat), int(non_acgt)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(meta, src=0, group=group)
+    length, non_acgt = (int(v) for v in meta.tolist())
+    if rank != 0:
+        image = engine.empty_image(length)
+    if world > 1:
+        dist.broadcast(image, src=0, group=group)  # the one broadcast of the packed sequence set
+    if rank != 0:
+        packed = engine.adopt(image, length, K, bool(non_acgt))
+    best = engine.new_best(length, K)
+    b, e = shard_bounds(0, length, world)[rank]
+    engine.bootstrap(packed, both, b, e, best)
+    if world > 1:
+        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
+    engine.bands(packed, both, rank, world, best)
+    if world > 1:
+        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
+    if rank != 0:
+        return None
+    return engine.finalize(packed, best).cpu().numpy().view(np.uint16)
+
 
 def exhaustive_distributed(concat: Optional[np.ndarray], K: int, both: bool, q_begin: int = 0,
                            q_end: Optional[int] = None, engine=None, group=None) -> Optional[np.ndarray]:

@@ -66,6 +66,9 @@ SIGNATURES = {
     "k4b_exhaustive_diag_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp,
                                                   ctypes.POINTER(ctypes.c_int)]),
     "k4b_best_finalize_device": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "k4b_diag_bootstrap_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
+    "k4b_diag_bands_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp,
+                                             ctypes.POINTER(ctypes.c_int)]),
     "k4b_microbench_intpipe": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
 }
 
@@ -242,6 +245,19 @@ def exhaustive_diag_device(g: Packed, both_strands: bool, part: int, nparts: int
     n = ctypes.c_int(0)
     _check(load_lib().k4b_exhaustive_diag_device(g.handle, int(both_strands), part, nparts, _vp(d_best_ptr),
                                                  _vp(stream), ctypes.byref(n)))
+    return n.value
+
+
+def diag_bootstrap_device(g: Packed, both_strands: bool, q_begin: int, q_end: int, d_best_ptr: int,
+                          stream: int = 0) -> None:
+    _check(load_lib().k4b_diag_bootstrap_device(g.handle, int(both_strands), q_begin, q_end, _vp(d_best_ptr),
+                                                _vp(stream)))
+
+
+def diag_bands_device(g: Packed, both_strands: bool, part: int, nparts: int, d_best_ptr: int, stream: int = 0) -> int:
+    n = ctypes.c_int(0)
+    _check(load_lib().k4b_diag_bands_device(g.handle, int(both_strands), part, nparts, _vp(d_best_ptr), _vp(stream),
+                                            ctypes.byref(n)))
     return n.value
 
 

@@ -22,6 +22,12 @@ class OracleEngine:
         self.device = torch.device("cpu")
         self.K = None
 
+    @classmethod
+    def for_k(cls, K):
+        e = cls()
+        e.K = K
+        return e
+
     def empty_image(self, length):
         return torch.empty(length, dtype=torch.uint8)
 
@@ -40,6 +46,25 @@ class OracleEngine:
         out[: e - b] = torch.from_numpy(hd[b:e].view(np.int16).copy())
         return 1
 
+    # band-engine stand-ins: bootstrap = nothing learnt yet, bands = this rank's share of the
+    # reference's sweep offsets (a partition of the pair matrix), answered by the oracle
+    def new_best(self, length, K):
+        return torch.full((length,), K + 1, dtype=torch.int32)
+
+    def bootstrap(self, packed, both, b, e, best):
+        return 0
+
+    def bands(self, packed, both, part, nparts, best):
+        from oracle import hamm_oracle as ho
+        n = len(packed)
+        for s in range(1 + part, n + 2, nparts):
+            hd = ho.exhaustive_sliding_sweep(packed, self.K, both, s, s)
+            torch.minimum(best, torch.from_numpy(hd.astype(np.int32)), out=best)
+        return 1
+
+    def finalize(self, packed, best):
+        return best.to(torch.int16)
+
 
 def _worker(rank, world, port, K, both, qb, qe, ret):
     sys.path.insert(0, ROOT)
@@ -49,6 +74,22 @@ def _worker(rank, world, port, K, both, qb, qe, ret):
     from kit4b_b200.dist import exhaustive_distributed
     concat = random_genome(77, [900, 41, 700]) if rank == 0 else None
     res = exhaustive_distributed(concat, K, both, qb, qe, engine=OracleEngine())
+    if rank == 0:
+        ret["res"] = res
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _worker_bands(rank, world, port, K, both, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from kit4b_b200.dist import exhaustive_distributed_bands
+    concat = random_genome(78, [300, 30, 260]) if rank == 0 else None
+    res = exhaustive_distributed_bands(concat, K, both, engine=OracleEngine.for_k(K))
     if rank == 0:
         ret["res"] = res
     else:
@@ -83,3 +124,13 @@ def test_shard_bounds_partition():
         assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
         sizes = [hi - lo for lo, hi in b]
         assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("K,both", [(20, True), (25, False)])
+def test_two_rank_pair_matrix_partition_with_min_allreduce(oracle, K, both):
+    """exhaustive_distributed_bands: partitioned pair matrix + all_reduce(MIN) == full result."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_bands, args=(2, _free_port(), K, both, ret), nprocs=2, join=True)
+    concat = random_genome(78, [300, 30, 260])
+    assert np.array_equal(ret["res"], oracle.exhaustive_brute(concat, K, both))

@@ -221,6 +221,18 @@ def test_in_process_multi_gpu_shards(oracle):
         c = random_genome(601, [30000, 12000, 9000])
         for K, both in [(25, True), (100, False)]:
             assert np.array_equal(k4b.exhaustive(c, K, both), oracle.exhaustive_sliding(c, K, both))
+        # diagonal-band engine: pair matrix partitioned over the devices + ncclAllReduce(min)
+        from kit4b_b200 import hamm
+        k4b.set_engine(hamm.ENGINE_DIAG)
+        try:
+            for K, both in [(25, True), (50, True), (100, False)]:
+                assert np.array_equal(k4b.exhaustive(c, K, both), oracle.exhaustive_sliding(c, K, both))
+            big = random_genome(603, [400000, 150000])
+            got = k4b.exhaustive(big, 32, True)
+            k4b.set_engine(hamm.ENGINE_POPC)
+            assert np.array_equal(got, k4b.exhaustive(big, 32, True))
+        finally:
+            k4b.set_engine(hamm.ENGINE_AUTO)
         target = random_genome(602, [40000])
         probes = np.ascontiguousarray(np.concatenate([target[100:900], [7], target[5000:5600]]), dtype=np.uint8)
         probes[50] = (probes[50] + 1) % 4
