@@ -164,6 +164,14 @@ int k4b_diag_bootstrap_device(k4b_packed *g, int both_strands, uint32_t q_begin,
 int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t part, uint32_t nparts,
                           uint32_t *d_best, void *stream, int *launches);
 
+/* Targeted (probes vs assembly, -m0 -I) on the band engine: rows = probe K-mers, columns = target
+ * K-mers, fixed threshold = clamp (the "not found" value), targeted wildcard rules.  d_best:
+ * DEVICE uint32[probe len] initialised by k4b_best_init_device; part/nparts as above. */
+int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets, int both_strands, uint32_t clamp,
+                             uint32_t part, uint32_t nparts, uint32_t *d_best, void *stream, int *launches);
+int k4b_targeted_finalize_device(k4b_packed *probes, const uint32_t *d_best, uint32_t clamp,
+                                 uint16_t *d_out_min, void *stream);
+
 /* ---- integer-pipe roofline microbenchmark ----------------------------------- */
 /* which: 0 POPC only, 1 LOP3 only, 2 engine mix (2 LOP3 + 1 POPC + min), 3 IADD3 only.
  * Returns giga warp-lane-ops per second (ops/s / 1e9) on the current device in *gops. */

@@ -551,8 +551,14 @@ extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t p
     n_slabs = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_slabs, (gw + gc) / (4ull * nparts) + 1));
     DiagParams dp;
     dp.a = g->view();
+    dp.va = g->view();
+    dp.vb = g->view();
     dp.K = K;
-    dp.M = M;
+    dp.Mrow = dp.Mcol = M;
+    dp.row_flip = 0;
+    dp.update_cols = 1;
+    dp.wild = 0;
+    dp.t_fixed = 0;
     dp.rows_per_seg = rows_per_seg;
     dp.n_seg = (uint32_t)(((uint64_t)M + 1 + rows_per_seg - 1) / rows_per_seg);
     dp.best = d_best;
@@ -568,7 +574,8 @@ extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t p
             const uint64_t ngroups_all = strand ? gc : gw;
             if (dp.grp_first >= ngroups_all) continue;
             const uint32_t ng = (uint32_t)((ngroups_all - dp.grp_first + dp.grp_step - 1) / dp.grp_step);
-            dp.crick = strand;
+            dp.mode = strand ? kDiagCrick : kDiagWatson;
+            dp.col_flip = strand;
             dp.b = strand ? g->rc_view() : g->view();
             dp.s_first = strand ? -(long long)M : 1;
             // the 1-D grid is limited to 2^31-1 CTAs: split very large launches by groups
@@ -585,6 +592,72 @@ extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t p
     cudaFreeAsync(d_bm, st);
     if (e != cudaSuccess) return fail(cuda_code(e), "diagonal engine launch: %s", cudaGetErrorString(e));
     if (launches) *launches = nl;
+    return K4B_OK;
+}
+
+// Targeted (probes vs assembly) on the band engine: rows = probe K-mers (forward, then their
+// reverse complement), columns = target K-mers, fixed threshold = the "not found" clamp, rows
+// only.  Part `part` of `nparts` of the diagonals; parts combine by element-wise minimum.
+extern "C" int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets, int both_strands,
+                                        uint32_t clamp, uint32_t part, uint32_t nparts,
+                                        uint32_t *d_best, void *stream, int *launches) {
+    if (launches) *launches = 0;
+    if (!probes || !targets || !d_best) return fail(K4B_ERR_PARAMS, "NULL argument");
+    if (probes->K != targets->K) return fail(K4B_ERR_PARAMS, "probe/target K differ");
+    if (probes->device != targets->device) return fail(K4B_ERR_PARAMS, "images live on different devices");
+    if (!nparts || part >= nparts || !clamp) return fail(K4B_ERR_PARAMS, "bad part/clamp");
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t K = probes->K;
+    if (probes->len < K || targets->len < K) return K4B_OK;
+    const bool three = probes->has_non_acgt || targets->has_non_acgt, crick = both_strands != 0;
+    int nl = 0;
+    RC(diag_prepare(probes, crick, st, &nl));
+    const char *rs = getenv("K4B_DIAG_ROWS");
+    DiagParams dp;
+    dp.b = targets->view();
+    dp.va = probes->view();
+    dp.vb = targets->view();
+    dp.K = K;
+    dp.Mrow = probes->len - K;
+    dp.Mcol = targets->len - K;
+    dp.mode = kDiagRect;
+    dp.col_flip = 0;
+    dp.update_cols = 0;
+    dp.wild = three ? 1 : 0;
+    dp.t_fixed = std::min(clamp, K + 1);
+    dp.rows_per_seg = rs ? (uint32_t)atoi(rs) : 4096u;
+    dp.n_seg = (uint32_t)(((uint64_t)dp.Mrow + 1 + dp.rows_per_seg - 1) / dp.rows_per_seg);
+    dp.best = d_best;
+    dp.blockmax = nullptr;
+    dp.bm_shift = 0;
+    dp.s_first = -(long long)dp.Mrow;
+    dp.grp_step = nparts;
+    const uint64_t groups = ((uint64_t)dp.Mrow + dp.Mcol + 1 + kDiagGroupDiagonals - 1) / kDiagGroupDiagonals;
+    cudaError_t e = cudaEventRecord(g_ev0, st);
+    for (int strand = 0; strand < (crick ? 2 : 1) && e == cudaSuccess; ++strand) {
+        if (part >= groups) break;
+        dp.a = strand ? probes->rc_view() : probes->view();
+        dp.row_flip = strand;
+        const uint32_t ng = (uint32_t)((groups - part + nparts - 1) / nparts);
+        const uint32_t max_groups = std::max(1u, 0x7fffffffu / dp.n_seg);
+        for (uint32_t done = 0; done < ng && e == cudaSuccess; done += max_groups) {
+            dp.grp_first = part + done * nparts;
+            e = launch_diag(dp, three, std::min(max_groups, ng - done), st, nullptr);
+            ++nl;
+        }
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(g_ev1, st);
+    if (e != cudaSuccess) return fail(cuda_code(e), "targeted band launch: %s", cudaGetErrorString(e));
+    if (launches) *launches = nl;
+    return K4B_OK;
+}
+
+// minima -> uint16 with the targeted rules applied (cap at clamp, > 4 wildcards -> 0)
+extern "C" int k4b_targeted_finalize_device(k4b_packed *probes, const uint32_t *d_best, uint32_t clamp,
+                                            uint16_t *d_out_min, void *stream) {
+    if (!probes || !d_best || !d_out_min) return fail(K4B_ERR_PARAMS, "NULL argument");
+    CU(cudaSetDevice(probes->device));
+    CU(launch_finalize(d_best, probes->view(), 0, probes->len, probes->K, clamp, 4, d_out_min, (cudaStream_t)stream));
     return K4B_OK;
 }
 
@@ -872,6 +945,91 @@ static int run_exhaustive_diag(const uint8_t *concat, uint32_t len, uint32_t K, 
     return rc;
 }
 
+// probes-vs-assembly on the band engine over all devices (diagonals partitioned, one
+// ncclAllReduce(min) at the end)
+static int run_targeted_diag(const uint8_t *t_concat, uint32_t t_len, const uint8_t *q_concat, uint32_t q_len,
+                             uint32_t K, int both, uint32_t clamp, uint8_t *out_h) {
+    RC(ensure_init());
+    const int n = (int)g_eng.devs.size();
+    PhaseTrace trace;
+    std::vector<k4b_packed *> qs, ts;
+    std::vector<uint32_t *> bests(n, nullptr);
+    uint16_t *d_out = nullptr, *h_out = nullptr;
+    int rc = 0;
+    do {
+        CU(cudaSetDevice(g_eng.devs[0]));
+        k4b_packed *q0 = nullptr, *t0 = nullptr;
+        if ((rc = k4b_pack_host(q_concat, q_len, K, &q0))) break;
+        qs.push_back(q0);
+        if ((rc = k4b_pack_host(t_concat, t_len, K, &t0))) break;
+        ts.push_back(t0);
+        if (n > 1) {
+            qs.clear();
+            ts.clear();
+            rc = broadcast_packed(q0, qs);
+            if (!rc) rc = broadcast_packed(t0, ts);
+            if (rc) {
+                if (qs.empty()) qs.push_back(q0);
+                if (ts.empty()) ts.push_back(t0);
+                break;
+            }
+        }
+        trace.mark("H2D + pack (+bcast)");
+        for (int i = 0; i < n && !rc; ++i) {
+            cudaError_t e = cudaSetDevice(g_eng.devs[i]);
+            if (e == cudaSuccess) e = cudaMalloc(&bests[i], (size_t)q_len * 4);
+            if (e != cudaSuccess) {
+                rc = fail(cuda_code(e), "minima buffer: %s", cudaGetErrorString(e));
+                break;
+            }
+            rc = k4b_best_init_device(bests[i], q_len, K, g_eng.streams[i]);
+            if (!rc) rc = k4b_targeted_diag_device(qs[i], ts[i], both, clamp, (uint32_t)i, (uint32_t)n, bests[i], g_eng.streams[i], nullptr);
+        }
+        if (rc) break;
+        if (n > 1) {
+            int nr = g_eng.nccl.GroupStart();
+            for (int i = 0; i < n && !nr; ++i)
+                nr = g_eng.nccl.AllReduce(bests[i], bests[i], q_len, kNcclUint32, kNcclMin, g_eng.comms[i], g_eng.streams[i]);
+            const int nr2 = g_eng.nccl.GroupEnd();
+            if (nr || nr2) {
+                rc = fail(K4B_ERR_NCCL, "ncclAllReduce(min): %s", g_eng.nccl.GetErrorString(nr ? nr : nr2));
+                break;
+            }
+        }
+        cudaError_t e = cudaSetDevice(g_eng.devs[0]);
+        if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)q_len * 2);
+        if (e == cudaSuccess) e = cudaMallocHost(&h_out, (size_t)q_len * 2);
+        if (e != cudaSuccess) {
+            rc = fail(cuda_code(e), "result buffers: %s", cudaGetErrorString(e));
+            break;
+        }
+        if ((rc = k4b_targeted_finalize_device(qs[0], bests[0], clamp, d_out, g_eng.streams[0]))) break;
+        e = cudaMemcpyAsync(h_out, d_out, (size_t)q_len * 2, cudaMemcpyDeviceToHost, g_eng.streams[0]);
+        for (int i = 0; i < n; ++i) {
+            cudaSetDevice(g_eng.devs[i]);
+            const cudaError_t e2 = cudaStreamSynchronize(g_eng.streams[i]);
+            if (e2 != cudaSuccess && e == cudaSuccess) e = e2;
+        }
+        if (e != cudaSuccess) {
+            rc = fail(cuda_code(e), "targeted band engine: %s", cudaGetErrorString(e));
+            break;
+        }
+        trace.mark("kernels + D2H");
+        for (uint32_t p = 0; p < q_len; ++p)
+            if (h_out[p] <= K) out_h[p] = (uint8_t)h_out[p];
+    } while (0);
+    for (int i = 0; i < n; ++i) {
+        cudaSetDevice(g_eng.devs[i]);
+        if (bests[i]) cudaFree(bests[i]);
+        if ((size_t)i < qs.size() && qs[i]) k4b_packed_free(qs[i]);
+        if ((size_t)i < ts.size() && ts[i]) k4b_packed_free(ts[i]);
+    }
+    cudaSetDevice(g_eng.devs[0]);
+    if (d_out) cudaFree(d_out);
+    if (h_out) cudaFreeHost(h_out);
+    return rc;
+}
+
 // auto: the band engine pays off once the pair matrix is large; tiny inputs stay on the
 // all-pairs kernel (one launch)
 static bool use_diag_engine(uint32_t len, uint32_t K) {
@@ -933,6 +1091,14 @@ extern "C" int k4b_hamm_targeted(const uint8_t *target_concat, uint64_t target_l
                            });
     }
     if (q_end == 0 || q_end > probe_len) q_end = probe_len;
+    {
+        const int eng = engine_setting();
+        const bool whole = q_begin == 0 && q_end == probe_len;
+        const bool big = (uint64_t)probe_len * target_len >= (1ull << 32);
+        if (whole && eng != 1 && (eng == 2 || big))
+            return run_targeted_diag(target_concat, (uint32_t)target_len, probe_concat, probe_len, K,
+                                     both_strands, notfound, out_h);
+    }
     return run_sharded(probe_concat, probe_len, target_concat, (uint32_t)target_len, K,
                        both_strands, 0, q_begin, q_end, notfound, 1, SweepRange(),
                        [&](uint32_t pos, uint16_t v) {

@@ -76,12 +76,17 @@ __device__ __forceinline__ void load_side(const ImageView &a, const ImageView &b
     }
 }
 
-// mismatch word of row step t: bit k = [A[idx+t] != B[idx+t+s0+k]]
-template <int P>
+// mismatch word of row step t: bit k = [A[idx+t] != B[idx+t+s0+k]].  WILD (targeted rules):
+// a row symbol >= N matches any column ACGT base but never a column N (SfxArray.cpp:4266-4296)
+template <int P, bool WILD>
 __device__ __forceinline__ uint32_t mism_word(const SideWords<P> &w, uint32_t t) {
     uint32_t m = __funnelshift_r(w.xa[0], w.xb[0], t) ^ sext_bit(w.ra[0], t);
     m |= __funnelshift_r(w.xa[1], w.xb[1], t) ^ sext_bit(w.ra[1], t);
-    if (P == 3) m |= __funnelshift_r(w.xa[2], w.xb[2], t) ^ sext_bit(w.ra[2], t);
+    if (P == 3) {
+        const uint32_t xn = __funnelshift_r(w.xa[2], w.xb[2], t), bn = sext_bit(w.ra[2], t);
+        if (WILD) m = (m & ~bn) | xn;
+        else m |= xn ^ bn;
+    }
     return m;
 }
 
@@ -91,51 +96,48 @@ template <int NP>
 struct Counters {
     uint32_t c[NP];
 };
+struct FlushCtx {  // what the slow path needs, by value
+    const uint32_t *valid_row, *valid_col;
+    uint32_t *best;
+    long long Mrow, Mcol;
+    int row_flip, col_flip, update_cols;
+};
 template <int NP>
 __device__ __noinline__ void diag_flush(Counters<NP> cs, uint32_t flags, uint32_t bias, long long row,
-                                        long long s0, long long M, int crick,
-                                        const uint32_t *__restrict__ valid, uint32_t *__restrict__ best) {
+                                        long long s0, FlushCtx fc) {
+    if (row > fc.Mrow) return;
+    const long long prow = fc.row_flip ? fc.Mrow - row : row;
+    if (!((fc.valid_row[prow >> 5] >> (prow & 31)) & 1u)) return;
     while (flags) {
         const uint32_t k = __ffs(flags) - 1;
         flags &= flags - 1;
+        const long long col = row + s0 + k;
+        if (col < 0 || col > fc.Mcol) continue;
+        const long long pcol = fc.col_flip ? fc.Mcol - col : col;
+        if (!((fc.valid_col[pcol >> 5] >> (pcol & 31)) & 1u)) continue;
         uint32_t val = 0;
 #pragma unroll
         for (int b = 0; b < NP; ++b) val |= ((cs.c[b] >> k) & 1u) << b;
         const uint32_t d = val - bias;
-        const long long jc = row + s0 + k;
-        long long j;
-        bool ok;
-        if (!crick) {
-            j = jc;
-            ok = j <= M;
-        } else {
-            j = M - jc;
-            ok = jc >= 0 && jc <= M;
-        }
-        if (!ok || row > M) continue;
-        if (!((valid[row >> 5] >> (row & 31)) & (valid[j >> 5] >> (j & 31)) & 1u)) continue;
-        if (d < best[row]) atomicMin(&best[row], d);
-        if (d < best[j]) atomicMin(&best[j], d);
+        if (d < fc.best[prow]) atomicMin(&fc.best[prow], d);
+        if (fc.update_cols && d < fc.best[pcol]) atomicMin(&fc.best[pcol], d);
     }
 }
 
-template <int NP, int P>
+template <int NP, int P, bool WILD>
 __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagParams prm) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t grp_local = blockIdx.x / prm.n_seg, seg = blockIdx.x - grp_local * prm.n_seg;
     const long long grp = (long long)prm.grp_first + (long long)grp_local * prm.grp_step;
     const long long S0cta = prm.s_first + grp * kGroupDiags;
     const long long S1cta = S0cta + kGroupDiags - 1;
-    const long long M = prm.M;
-    long long row_lo, row_hi;
-    if (!prm.crick) {
-        row_lo = 0;
-        row_hi = M - S0cta;
-    } else {  // half of every mirror-symmetric diagonal: rows max(0,-s) .. (M-s)/2
-        row_lo = S1cta < 0 ? -S1cta : 0;
-        row_hi = (M - S0cta) >> 1;
-        if (row_hi > M) row_hi = M;
-    }
+    const long long Mrow = prm.Mrow, Mcol = prm.Mcol;
+    // rows of diagonal s: max(0,-s) .. min(Mrow, Mcol-s); the CTA takes the union over its
+    // diagonals (cells outside a diagonal's own range are invalid or mirror duplicates)
+    long long row_lo = S1cta < 0 ? -S1cta : 0;
+    long long row_hi = Mcol - S0cta;
+    if (prm.mode == kDiagCrick) row_hi >>= 1;  // first half of every mirror-symmetric diagonal
+    if (row_hi > Mrow) row_hi = Mrow;
     const long long r_start = row_lo + (long long)seg * prm.rows_per_seg;
     if (r_start > row_hi) return;
     long long r_end = r_start + prm.rows_per_seg;
@@ -145,19 +147,19 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
     const uint32_t K = prm.K;
 
     // ---- threshold: upper bound of every minimum this warp can still lower ----
-    uint32_t tmax = 0;
-    {
-        auto scan = [&](long long lo, long long hi) {
+    uint32_t tmax = prm.t_fixed;
+    if (prm.mode != kDiagRect) {
+        auto scan = [&](long long lo, long long hi, long long top) {
             if (lo < 0) lo = 0;
-            if (hi > M) hi = M;
+            if (hi > top) hi = top;
             if (lo > hi) return;
             for (long long bk = (lo >> prm.bm_shift) + lane; bk <= (hi >> prm.bm_shift); bk += 32)
                 tmax = max(tmax, __ldg(prm.blockmax + bk));
         };
-        scan(r_start, r_end - 1);
+        scan(r_start, r_end - 1, Mrow);
         const long long c_lo = r_start + S0w, c_hi = r_end - 1 + S0w + kSuperBand - 1;
-        if (!prm.crick) scan(c_lo, c_hi);
-        else scan(M - c_hi, M - c_lo);
+        if (!prm.col_flip) scan(c_lo, c_hi, Mcol);
+        else scan(Mcol - c_hi, Mcol - c_lo, Mcol);
         tmax = __reduce_max_sync(0xffffffffu, tmax);
     }
     if (tmax == 0) return;  // every K-mer in reach already sits at the floor 0
@@ -168,14 +170,20 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
 #pragma unroll
     for (int b = 0; b < NP; ++b) c[b] = ((bias >> b) & 1u) ? 0xffffffffu : 0u;
 
-    const uint32_t *valid = prm.a.valid();
-    uint32_t *best = prm.best;
-    const int crick = prm.crick;
+    FlushCtx fc;
+    fc.valid_row = prm.va.valid();
+    fc.valid_col = prm.vb.valid();
+    fc.best = prm.best;
+    fc.Mrow = Mrow;
+    fc.Mcol = Mcol;
+    fc.row_flip = prm.row_flip;
+    fc.col_flip = prm.col_flip;
+    fc.update_cols = prm.update_cols;
     auto flush = [&](uint32_t flags, long long row) {
         Counters<NP> cs;
 #pragma unroll
         for (int b = 0; b < NP; ++b) cs.c[b] = c[b];
-        diag_flush<NP>(cs, flags, bias, row, s0, M, crick, valid, best);
+        diag_flush<NP>(cs, flags, bias, row, s0, fc);
     };
 
     // ---- warm-up: the first K bases of the window enter, nothing leaves ----
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
             load_side<P>(prm.a, prm.b, e, s0, we);
 #pragma unroll 1
             for (uint32_t t = 0; t < n; ++t) {
-                uint32_t act = mism_word<P>(we, t);
+                uint32_t act = mism_word<P, WILD>(we, t);
 #pragma unroll
                 for (int b = 0; b < NP; ++b) {  // ripple increment
                     const uint32_t old = c[b];
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
         if (left >= 32) {
 #pragma unroll
             for (uint32_t t = 0; t < 32; ++t) {
-                const uint32_t en = mism_word<P>(we, t), lv = mism_word<P>(wl, t);
+                const uint32_t en = mism_word<P, WILD>(we, t), lv = mism_word<P, WILD>(wl, t);
                 const uint32_t plus = en & ~lv;
                 uint32_t act = en ^ lv;
 #pragma unroll
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
         } else {
 #pragma unroll 1
             for (uint32_t t = 0; t < (uint32_t)left; ++t) {
-                const uint32_t en = mism_word<P>(we, t), lv = mism_word<P>(wl, t);
+                const uint32_t en = mism_word<P, WILD>(we, t), lv = mism_word<P, WILD>(wl, t);
                 const uint32_t plus = en & ~lv;
                 uint32_t act = en ^ lv;
 #pragma unroll
@@ -262,11 +270,11 @@ int diag_planes_for_k(uint32_t K) {
     return b + 1;
 }
 
-template <int P>
+template <int P, bool WILD>
 static cudaError_t launch_diag_p(const DiagParams &p, int np, dim3 grid, cudaStream_t st) {
     switch (np) {
 #define K4B_DIAG_CASE(N) \
-    case N: diag_min_kernel<N, P><<<grid, kDiagWarps * 32, 0, st>>>(p); break
+    case N: diag_min_kernel<N, P, WILD><<<grid, kDiagWarps * 32, 0, st>>>(p); break
         K4B_DIAG_CASE(5);
         K4B_DIAG_CASE(6);
         K4B_DIAG_CASE(7);
@@ -292,7 +300,8 @@ cudaError_t launch_diag(const DiagParams &p, bool three_planes, uint32_t n_group
     if (n_ctas) *n_ctas = total;
     const int np = diag_planes_for_k(p.K);
     dim3 grid((unsigned)total);
-    return three_planes ? launch_diag_p<3>(p, np, grid, st) : launch_diag_p<2>(p, np, grid, st);
+    if (!three_planes) return launch_diag_p<2, false>(p, np, grid, st);
+    return p.wild ? launch_diag_p<3, true>(p, np, grid, st) : launch_diag_p<3, false>(p, np, grid, st);
 }
 
 }  // namespace k4b

@@ -57,12 +57,23 @@ struct AllPairsParams {
 };
 
 // diagonal-band engine (k4b_diag.cu)
+enum DiagMode : int {
+    kDiagWatson = 0,  // A = B = sequence, diagonals s >= 1, every cell lowers both K-mers
+    kDiagCrick = 1,   // B = reverse complement of A; first half of each mirror-symmetric diagonal
+    kDiagRect = 2,    // A = probes (or their reverse complement), B = targets; rows only
+};
 struct DiagParams {
-    ImageView a;             // row sequence: planes + valid-start plane (also validates columns)
-    ImageView b;             // column sequence planes: a itself (Watson) or its reverse complement (Crick)
+    ImageView a;             // row sequence planes
+    ImageView b;             // column sequence planes
+    ImageView va, vb;        // images whose valid-start planes validate row / column POSITIONS
     uint32_t K;
-    uint32_t M;              // last K-mer start position, len - K
-    int crick;
+    uint32_t Mrow, Mcol;     // last K-mer start of the row / column sequence (len - K)
+    int mode;                // DiagMode
+    int row_flip, col_flip;  // position of a row (column) index r is Mrow - r (Mcol - c): the
+                             // sequence in a (b) is the reverse complement of the one indexed by best[]
+    int update_cols;         // also lower best[] at the column position (symmetric modes)
+    int wild;                // row symbols >= N are wildcards (targeted rules, needs 3 planes)
+    uint32_t t_fixed;        // kDiagRect: fixed threshold (the clamp); else thresholds come from blockmax
     long long s_first;       // diagonal (column - row) of lane 0 of group 0
     uint32_t grp_first, grp_step;  // CTA group g of this launch = grp_first + local * grp_step
     uint32_t n_seg, rows_per_seg;  // row segments per group

@@ -66,6 +66,9 @@ SIGNATURES = {
     "k4b_exhaustive_diag_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp,
                                                   ctypes.POINTER(ctypes.c_int)]),
     "k4b_best_finalize_device": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "k4b_targeted_diag_device": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32,
+                                                ctypes.c_uint32, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
+    "k4b_targeted_finalize_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, _vp]),
     "k4b_diag_bootstrap_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
     "k4b_diag_bands_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp,
                                              ctypes.POINTER(ctypes.c_int)]),
@@ -259,6 +262,18 @@ def diag_bands_device(g: Packed, both_strands: bool, part: int, nparts: int, d_b
     _check(load_lib().k4b_diag_bands_device(g.handle, int(both_strands), part, nparts, _vp(d_best_ptr), _vp(stream),
                                             ctypes.byref(n)))
     return n.value
+
+
+def targeted_diag_device(probes: Packed, targets: Packed, both_strands: bool, clamp: int, part: int, nparts: int,
+                         d_best_ptr: int, stream: int = 0) -> int:
+    n = ctypes.c_int(0)
+    _check(load_lib().k4b_targeted_diag_device(probes.handle, targets.handle, int(both_strands), clamp, part, nparts,
+                                               _vp(d_best_ptr), _vp(stream), ctypes.byref(n)))
+    return n.value
+
+
+def targeted_finalize_device(probes: Packed, d_best_ptr: int, clamp: int, d_out_ptr: int, stream: int = 0) -> None:
+    _check(load_lib().k4b_targeted_finalize_device(probes.handle, _vp(d_best_ptr), clamp, _vp(d_out_ptr), _vp(stream)))
 
 
 def best_finalize_device(g: Packed, d_best_ptr: int, d_out_ptr: int, stream: int = 0) -> None:

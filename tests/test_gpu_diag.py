@@ -91,3 +91,55 @@ def test_diag_engine_config1_output_md5(tmp_path):
                        capture_output=True, text=True)
     assert p.returncode == 0, p.stdout[-2000:]
     assert hashlib.md5(open(out, "rb").read()).hexdigest() == "f1b2e85a8f64dc68dcc60cc2403cfb1a"
+
+
+def _targeted_runs():
+    m = golden_manifest()["__targeted__"]
+    return [(m, r) for r in m["runs"]]
+
+
+@pytest.mark.parametrize("mr", _targeted_runs(), ids=lambda mr: mr[1]["out"])
+def test_band_engine_targeted_equals_reference_files(oracle, mr):
+    """-m0 -I on the band engine (rectangular mode, fixed threshold, wildcard rules)."""
+    m, r = mr
+    _, tseq = oracle.read_sfx(os.path.join(GOLDEN, m["sfx"]))
+    concat, chroms, _ = oracle.concat_entries(oracle.read_bioseq(os.path.join(GOLDEN, m["probes"][r["probes"]]["bioseq"])))
+    got = k4b.targeted(tseq, concat, r["K"], r["R"], r["both"])
+    rep = oracle.restricted_report(chroms, r["K"], r["R"], oracle.restricted_per_loci(chroms, got), r["fmt"], out_name=r["out"])
+    assert rep == open(os.path.join(GOLDEN, r["out"]), "rb").read()
+
+
+def test_band_engine_targeted_matches_oracle_with_wildcards(oracle):
+    rng = np.random.default_rng(501)
+    target = random_genome(502, [6000, 4000]).copy()
+    target[1000:1003] = 4
+    target[2500] = 6
+    probes = target[900:1500].copy()
+    for p in (50, 130, 131, 200, 260, 261, 262, 263, 264, 400):
+        probes[p] = 4
+    probes[300] = 5
+    probes = np.ascontiguousarray(np.concatenate([probes, [7], rng.integers(0, 5, size=400, dtype=np.uint8),
+                                                  [7], oracle.CPL[target[7000:7300][::-1]]]), dtype=np.uint8)
+    for K, R, both in [(32, 3, True), (25, 2, False), (64, 5, True), (140, 9, True), (20, 1, True)]:
+        assert np.array_equal(k4b.targeted(target, probes, K, R, both), oracle.targeted_brute(target, probes, K, R, both)), (K, R)
+
+
+def test_band_engine_targeted_equals_popc_engine_at_scale():
+    rng = np.random.default_rng(77)
+    target = random_genome(78, [1500000, 500000])
+    parts = []
+    for start, nmut in [(1000, 0), (200000, 3), (900000, 10), (1600000, 25)]:
+        seg = target[start:start + 3000].copy()
+        idx = rng.choice(3000, size=nmut * 10, replace=False)
+        seg[idx] = (seg[idx] + 1 + rng.integers(0, 3, size=len(idx))) % 4
+        parts += [seg, np.array([7], np.uint8)]
+    parts.append(rng.integers(0, 4, size=20000, dtype=np.uint8))
+    probes = np.ascontiguousarray(np.concatenate(parts), dtype=np.uint8)
+    got = k4b.targeted(target, probes, 32, 3, True)
+    k4b.set_engine(hamm.ENGINE_POPC)
+    try:
+        want = k4b.targeted(target, probes, 32, 3, True)
+    finally:
+        k4b.set_engine(hamm.ENGINE_DIAG)
+    assert np.array_equal(got, want)
+    assert (got[:2900] == 0).all() and got[got != 0xFF].max() <= 4 and (got == 0xFF).sum() < 5 * 32
