@@ -540,15 +540,21 @@ extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t p
     RC(diag_prepare(g, crick, st, &nl));
     const uint32_t bm_shift = 8;
     const uint32_t n_blocks = (M >> bm_shift) + 1;
-    uint32_t *d_bm = nullptr;
-    CU(cudaMallocAsync(&d_bm, (size_t)n_blocks * 4, st));
+    uint32_t *d_bm = nullptr;  // [n_blocks] block maxima + [n_slabs] global maxima (one per slab)
+    CU(cudaMallocAsync(&d_bm, ((size_t)n_blocks + 64) * 4, st));
+    CU(cudaMemsetAsync(d_bm + n_blocks, 0, 64 * 4, st));
     const char *rs = getenv("K4B_DIAG_ROWS");
     const uint32_t rows_per_seg = rs ? (uint32_t)atoi(rs) : 4096u;
     const uint64_t gw = ((uint64_t)M + kDiagGroupDiagonals - 1) / kDiagGroupDiagonals;            // s = 1..M
     const uint64_t gc = crick ? (2ull * M + 1 + kDiagGroupDiagonals - 1) / kDiagGroupDiagonals : 0;  // s = -M..M
+    // slabs: more slabs = tighter thresholds, fewer = longer launches (less tail); keep at least
+    // ~40 waves of resident CTAs (148 SMs x 8) per launch
+    const uint64_t n_seg64 = ((uint64_t)M + 1 + rows_per_seg - 1) / rows_per_seg;
+    const uint64_t ctas_watson = gw * n_seg64 / 2 + 1;
     const char *sl = getenv("K4B_DIAG_SLABS");
-    uint32_t n_slabs = sl ? (uint32_t)atoi(sl) : 16u;
-    n_slabs = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_slabs, (gw + gc) / (4ull * nparts) + 1));
+    uint32_t n_slabs = sl ? (uint32_t)atoi(sl)
+                          : (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(2, ctas_watson / ((uint64_t)nparts * 1184 * 40)));
+    n_slabs = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min(n_slabs, 64u), (gw + gc) / (4ull * nparts) + 1));
     DiagParams dp;
     dp.a = g->view();
     dp.va = g->view();
@@ -565,9 +571,16 @@ extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t p
     dp.blockmax = d_bm;
     dp.bm_shift = bm_shift;
     dp.grp_step = nparts * n_slabs;
+    // counter width: one plane fewer whenever every threshold of the slab fits (checked on the
+    // device against the slab's global maximum, so nothing waits for the host)
+    const int np_full = diag_planes_for_k(K);
+    const int np_small = (np_full - 1 >= 5 && !getenv("K4B_DIAG_FULLNP")) ? np_full - 1 : 0;
     cudaError_t e = cudaEventRecord(g_ev0, st);
     for (uint32_t slab = 0; slab < n_slabs && e == cudaSuccess; ++slab) {
-        e = launch_blockmax(d_best, g->view(), M + 1, bm_shift, d_bm, n_blocks, st);
+        uint32_t *d_tmax = d_bm + n_blocks + slab;
+        e = launch_blockmax(d_best, g->view(), M + 1, bm_shift, d_bm, n_blocks, d_tmax, st);
+        dp.tmax_ptr = d_tmax;
+        dp.sel_limit = np_small ? (1u << (np_small - 1)) : 0u;
         ++nl;
         dp.grp_first = part + nparts * slab;
         for (int strand = 0; strand < (crick ? 2 : 1) && e == cudaSuccess; ++strand) {
@@ -583,7 +596,16 @@ extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t p
             DiagParams q = dp;
             for (uint32_t done = 0; done < ng && e == cudaSuccess; done += max_groups) {
                 q.grp_first = dp.grp_first + done * dp.grp_step;
-                e = launch_diag(q, three, std::min(max_groups, ng - done), st, nullptr);
+                const uint32_t now = std::min(max_groups, ng - done);
+                if (np_small) {
+                    q.sel = 1;
+                    e = launch_diag(q, three, np_small, now, st, nullptr);
+                    ++nl;
+                    q.sel = 2;
+                } else {
+                    q.sel = 0;
+                }
+                if (e == cudaSuccess) e = launch_diag(q, three, np_full, now, st, nullptr);
                 ++nl;
             }
         }
@@ -630,8 +652,13 @@ extern "C" int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets,
     dp.best = d_best;
     dp.blockmax = nullptr;
     dp.bm_shift = 0;
+    dp.tmax_ptr = nullptr;
+    dp.sel = 0;
+    dp.sel_limit = 0;
     dp.s_first = -(long long)dp.Mrow;
     dp.grp_step = nparts;
+    int np = diag_planes_for_k(K);
+    if (np - 1 >= 5 && dp.t_fixed <= (1u << (np - 2))) --np;  // the clamp is tiny: narrow counters
     const uint64_t groups = ((uint64_t)dp.Mrow + dp.Mcol + 1 + kDiagGroupDiagonals - 1) / kDiagGroupDiagonals;
     cudaError_t e = cudaEventRecord(g_ev0, st);
     for (int strand = 0; strand < (crick ? 2 : 1) && e == cudaSuccess; ++strand) {
@@ -642,7 +669,7 @@ extern "C" int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets,
         const uint32_t max_groups = std::max(1u, 0x7fffffffu / dp.n_seg);
         for (uint32_t done = 0; done < ng && e == cudaSuccess; done += max_groups) {
             dp.grp_first = part + done * nparts;
-            e = launch_diag(dp, three, std::min(max_groups, ng - done), st, nullptr);
+            e = launch_diag(dp, three, np, std::min(max_groups, ng - done), st, nullptr);
             ++nl;
         }
     }

@@ -38,7 +38,8 @@ __device__ __forceinline__ uint32_t sext_bit(uint32_t x, uint32_t t) {
 // running-minimum upper bounds per 2^shift positions (valid K-mer starts only)
 __global__ void __launch_bounds__(256) blockmax_kernel(const uint32_t *__restrict__ best, ImageView a,
                                                        uint32_t n_pos, uint32_t shift,
-                                                       uint32_t *__restrict__ blockmax, uint32_t n_blocks) {
+                                                       uint32_t *__restrict__ blockmax, uint32_t n_blocks,
+                                                       uint32_t *__restrict__ tmax) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_blocks) return;
     const uint32_t base = warp << shift, span = 1u << shift;
@@ -48,7 +49,10 @@ __global__ void __launch_bounds__(256) blockmax_kernel(const uint32_t *__restric
         if (pos < n_pos && ((a.valid()[pos >> 5] >> (pos & 31)) & 1u)) m = max(m, best[pos]);
     }
     m = __reduce_max_sync(0xffffffffu, m);
-    if (lane == 0) blockmax[warp] = m;
+    if (lane == 0) {
+        blockmax[warp] = m;
+        if (tmax && m) atomicMax(tmax, m);
+    }
 }
 
 template <int P>
@@ -126,6 +130,10 @@ __device__ __noinline__ void diag_flush(Counters<NP> cs, uint32_t flags, uint32_
 
 template <int NP, int P, bool WILD>
 __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagParams prm) {
+    if (prm.sel) {  // device-side choice between the narrow- and the full-counter instance
+        const uint32_t tg = __ldg(prm.tmax_ptr);
+        if ((prm.sel == 1) != (tg <= prm.sel_limit)) return;
+    }
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t grp_local = blockIdx.x / prm.n_seg, seg = blockIdx.x - grp_local * prm.n_seg;
     const long long grp = (long long)prm.grp_first + (long long)grp_local * prm.grp_step;
@@ -163,7 +171,10 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
         tmax = __reduce_max_sync(0xffffffffu, tmax);
     }
     if (tmax == 0) return;  // every K-mer in reach already sits at the floor 0
-    const uint32_t T = tmax;
+    // a larger threshold is always safe (more flags, never a miss): lift it so that the biased
+    // maximum K + 2^(NP-1) - T still fits NP planes when the narrow-counter instance runs
+    const uint32_t t_floor = (K + 1 > (1u << (NP - 1))) ? K + 1 - (1u << (NP - 1)) : 0u;
+    const uint32_t T = tmax > t_floor ? tmax : t_floor;
     const uint32_t bias = (1u << (NP - 1)) - T;  // stored = distance + bias; distance < T <=> top bit clear
 
     uint32_t c[NP];
@@ -257,10 +268,10 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
 }
 
 cudaError_t launch_blockmax(const uint32_t *d_best, ImageView a, uint32_t n_pos, uint32_t shift,
-                            uint32_t *d_blockmax, uint32_t n_blocks, cudaStream_t st) {
+                            uint32_t *d_blockmax, uint32_t n_blocks, uint32_t *d_tmax, cudaStream_t st) {
     if (!n_blocks) return cudaSuccess;
     const uint32_t threads = n_blocks * 32;
-    blockmax_kernel<<<(threads + 255) / 256, 256, 0, st>>>(d_best, a, n_pos, shift, d_blockmax, n_blocks);
+    blockmax_kernel<<<(threads + 255) / 256, 256, 0, st>>>(d_best, a, n_pos, shift, d_blockmax, n_blocks, d_tmax);
     return cudaGetLastError();
 }
 
@@ -291,14 +302,15 @@ static cudaError_t launch_diag_p(const DiagParams &p, int np, dim3 grid, cudaStr
     return cudaGetLastError();
 }
 
-cudaError_t launch_diag(const DiagParams &p, bool three_planes, uint32_t n_groups, cudaStream_t st,
+cudaError_t launch_diag(const DiagParams &p, bool three_planes, int np, uint32_t n_groups, cudaStream_t st,
                         unsigned long long *n_ctas) {
     if (n_ctas) *n_ctas = 0;
     if (!n_groups || !p.n_seg) return cudaSuccess;
     const unsigned long long total = (unsigned long long)n_groups * p.n_seg;
     if (total > 0x7fffffffull) return cudaErrorInvalidValue;
     if (n_ctas) *n_ctas = total;
-    const int np = diag_planes_for_k(p.K);
+    if (np < 5) np = 5;
+    if ((1u << np) < p.K + 1) return cudaErrorInvalidValue;  // K + bias would not fit
     dim3 grid((unsigned)total);
     if (!three_planes) return launch_diag_p<2, false>(p, np, grid, st);
     return p.wild ? launch_diag_p<3, true>(p, np, grid, st) : launch_diag_p<3, false>(p, np, grid, st);

@@ -80,11 +80,18 @@ struct DiagParams {
     uint32_t *best;          // running minima per position (atomicMin)
     const uint32_t *blockmax;  // max of best over 2^bm_shift positions (valid starts only)
     uint32_t bm_shift;
+    // kernel-variant selection without a host round trip: the same launch is enqueued with two
+    // counter widths and each instance checks the global maximum threshold on the device
+    const uint32_t *tmax_ptr;  // max over all blockmax entries (written by blockmax_kernel)
+    uint32_t sel_limit;
+    int sel;                   // 0 run always, 1 run iff *tmax_ptr <= sel_limit, 2 iff > sel_limit
 };
 constexpr int kDiagGroupDiagonals = 8 * 1024;  // diagonals per CTA group (8 warps x 1024)
+// d_tmax (nullable): receives the maximum over all blocks; must be zeroed by the caller
 cudaError_t launch_blockmax(const uint32_t *d_best, ImageView a, uint32_t n_pos, uint32_t shift,
-                            uint32_t *d_blockmax, uint32_t n_blocks, cudaStream_t st);
-cudaError_t launch_diag(const DiagParams &p, bool three_planes, uint32_t n_groups, cudaStream_t st,
+                            uint32_t *d_blockmax, uint32_t n_blocks, uint32_t *d_tmax, cudaStream_t st);
+// np = number of counter planes (5..14); thresholds must fit 2^(np-1)
+cudaError_t launch_diag(const DiagParams &p, bool three_planes, int np, uint32_t n_groups, cudaStream_t st,
                         unsigned long long *n_ctas);
 int diag_planes_for_k(uint32_t K);
 
