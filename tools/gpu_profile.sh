@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
 echo "ncu launches rc=$?"
 SHORT2="python bench.py --workload cfg2 --steps 1 --warmup 3 --no-cpu --e2e-steps 0"
 $SHORT2 > gpurun_out/plain_short2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:diag_min -s 40 -c 2 \
+ncu --set full --clock-control none --import-source on -k regex:diag_min -s 40 -c 4 \
     -o gpurun_out/prof_diag -f $SHORT2 > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
 ls -la gpurun_out | tail -12
