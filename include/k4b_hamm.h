@@ -164,6 +164,11 @@ int k4b_diag_bootstrap_device(k4b_packed *g, int both_strands, uint32_t q_begin,
 int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t part, uint32_t nparts,
                           uint32_t *d_best, void *stream, int *launches);
 
+/* Counter widths of the most recent k4b_diag_bands_device run of this thread: planes of the full
+ * and of the narrow kernel instance (0 = none), number of slabs, and how many slabs ran narrow
+ * (chosen on the device from the slab's largest threshold).  Blocks until that run finished. */
+int k4b_last_diag_info(uint32_t *np_full, uint32_t *np_small, uint32_t *slabs, uint32_t *narrow_slabs);
+
 /* Targeted (probes vs assembly, -m0 -I) on the band engine: rows = probe K-mers, columns = target
  * K-mers, fixed threshold = clamp (the "not found" value), targeted wildcard rules.  d_best:
  * DEVICE uint32[probe len] initialised by k4b_best_init_device; part/nparts as above. */

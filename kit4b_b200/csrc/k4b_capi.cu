@@ -524,6 +524,25 @@ extern "C" int k4b_diag_bootstrap_device(k4b_packed *g, int both_strands, uint32
     return K4B_OK;
 }
 
+// bookkeeping of the most recent band run of this thread (which counter width each slab used)
+static thread_local uint32_t *g_h_tmax = nullptr;  // pinned, 64 entries
+static thread_local uint32_t g_info_slabs = 0, g_info_np_full = 0, g_info_np_small = 0, g_info_limit = 0;
+
+extern "C" int k4b_last_diag_info(uint32_t *np_full, uint32_t *np_small, uint32_t *slabs,
+                                  uint32_t *narrow_slabs) {
+    if (!g_ev1 || !g_h_tmax) return fail(K4B_ERR_PARAMS, "no band run recorded on this thread");
+    CU(cudaEventSynchronize(g_ev1));
+    CU(cudaDeviceSynchronize());
+    uint32_t narrow = 0;
+    for (uint32_t i = 0; i < g_info_slabs; ++i)
+        if (g_info_np_small && g_h_tmax[i] <= g_info_limit) ++narrow;
+    if (np_full) *np_full = g_info_np_full;
+    if (np_small) *np_small = g_info_np_small;
+    if (slabs) *slabs = g_info_slabs;
+    if (narrow_slabs) *narrow_slabs = narrow;
+    return K4B_OK;
+}
+
 // Diagonal bands: part `part` of `nparts` of the pair matrix (interleaved CTA groups of 8192
 // diagonals), in slabs with the thresholds (block maxima of d_best) refreshed per slab.
 extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t part, uint32_t nparts,
@@ -611,6 +630,13 @@ extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t p
         }
     }
     if (e == cudaSuccess) e = cudaEventRecord(g_ev1, st);
+    if (e == cudaSuccess && !g_h_tmax) e = cudaMallocHost(&g_h_tmax, 64 * sizeof(uint32_t));
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(g_h_tmax, d_bm + n_blocks, 64 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    g_info_slabs = n_slabs;
+    g_info_np_full = (uint32_t)np_full;
+    g_info_np_small = (uint32_t)np_small;
+    g_info_limit = np_small ? (1u << (np_small - 1)) : 0u;
     cudaFreeAsync(d_bm, st);
     if (e != cudaSuccess) return fail(cuda_code(e), "diagonal engine launch: %s", cudaGetErrorString(e));
     if (launches) *launches = nl;

@@ -66,6 +66,7 @@ SIGNATURES = {
     "k4b_exhaustive_diag_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp,
                                                   ctypes.POINTER(ctypes.c_int)]),
     "k4b_best_finalize_device": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "k4b_last_diag_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint32)] * 4),
     "k4b_targeted_diag_device": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32,
                                                 ctypes.c_uint32, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
     "k4b_targeted_finalize_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, _vp]),
@@ -274,6 +275,12 @@ def targeted_diag_device(probes: Packed, targets: Packed, both_strands: bool, cl
 
 def targeted_finalize_device(probes: Packed, d_best_ptr: int, clamp: int, d_out_ptr: int, stream: int = 0) -> None:
     _check(load_lib().k4b_targeted_finalize_device(probes.handle, _vp(d_best_ptr), clamp, _vp(d_out_ptr), _vp(stream)))
+
+
+def last_diag_info() -> dict:
+    v = [ctypes.c_uint32(0) for _ in range(4)]
+    _check(load_lib().k4b_last_diag_info(*[ctypes.byref(x) for x in v]))
+    return dict(zip(("np_full", "np_small", "slabs", "narrow_slabs"), (x.value for x in v)))
 
 
 def best_finalize_device(g: Packed, d_best_ptr: int, d_out_ptr: int, stream: int = 0) -> None:
