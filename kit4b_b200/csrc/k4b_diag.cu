@@ -31,6 +31,13 @@ constexpr int kDiagWarps = 8;        // super-bands (of 1024 diagonals) per CTA
 constexpr int kSuperBand = 1024;     // diagonals per warp
 constexpr int kGroupDiags = kDiagWarps * kSuperBand;
 
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return r;
+}
+
 __device__ __forceinline__ uint32_t sext_bit(uint32_t x, uint32_t t) {
     return (uint32_t)((int32_t)(x << (31u - t)) >> 31);
 }
@@ -106,9 +113,10 @@ struct FlushCtx {  // what the slow path needs, by value
     long long Mrow, Mcol;
     int row_flip, col_flip, update_cols;
 };
+// one row of the slow path: flagged diagonals k of `row`, distance = stored - bias + bit k of adj
 template <int NP>
-__device__ __noinline__ void diag_flush(Counters<NP> cs, uint32_t flags, uint32_t bias, long long row,
-                                        long long s0, FlushCtx fc) {
+__device__ __forceinline__ void diag_flush_row(const Counters<NP> &cs, uint32_t flags, uint32_t bias,
+                                               long long row, long long s0, uint32_t adj, const FlushCtx &fc) {
     if (row > fc.Mrow) return;
     const long long prow = fc.row_flip ? fc.Mrow - row : row;
     if (!((fc.valid_row[prow >> 5] >> (prow & 31)) & 1u)) return;
@@ -122,10 +130,18 @@ __device__ __noinline__ void diag_flush(Counters<NP> cs, uint32_t flags, uint32_
         uint32_t val = 0;
 #pragma unroll
         for (int b = 0; b < NP; ++b) val |= ((cs.c[b] >> k) & 1u) << b;
-        const uint32_t d = val - bias;
+        const uint32_t d = val - bias + ((adj >> k) & 1u);
         if (d < fc.best[prow]) atomicMin(&fc.best[prow], d);
         if (fc.update_cols && d < fc.best[pcol]) atomicMin(&fc.best[pcol], d);
     }
+}
+// The counters hold min(d(row), d(row+1)) of a row pair (see diag_min_kernel): d(row) = stored +
+// adj0 bit, d(row+1) = stored + adj1 bit.  rows = 1: single row, the counters hold d(row) itself.
+template <int NP>
+__device__ __noinline__ void diag_flush(Counters<NP> cs, uint32_t flags, uint32_t bias, long long row,
+                                        long long s0, uint32_t adj0, uint32_t adj1, int rows, FlushCtx fc) {
+    diag_flush_row<NP>(cs, flags, bias, row, s0, adj0, fc);
+    if (rows == 2) diag_flush_row<NP>(cs, flags, bias, row + 1, s0, adj1, fc);
 }
 
 template <int NP, int P, bool WILD>
@@ -190,11 +206,11 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
     fc.row_flip = prm.row_flip;
     fc.col_flip = prm.col_flip;
     fc.update_cols = prm.update_cols;
-    auto flush = [&](uint32_t flags, long long row) {
+    auto flush = [&](uint32_t flags, long long row, uint32_t adj0, uint32_t adj1, int rows) {
         Counters<NP> cs;
 #pragma unroll
         for (int b = 0; b < NP; ++b) cs.c[b] = c[b];
-        diag_flush<NP>(cs, flags, bias, row, s0, fc);
+        diag_flush<NP>(cs, flags, bias, row, s0, adj0, adj1, rows, fc);
     };
 
     // ---- warm-up: the first K bases of the window enter, nothing leaves ----
@@ -221,10 +237,43 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
     }
     {
         const uint32_t f = ~c[NP - 1];
-        if (f) flush(f, r_start);
+        if (f) flush(f, r_start, 0u, 0u, 1);
     }
 
-    // ---- main: row r: base r+K-1 enters, base r-1 leaves ----
+    // ---- main: row r: base r+K-1 enters (mismatch word en), base r-1 leaves (lv) ----
+    // Rows are taken in PAIRS (r, r+1) and the counters hold C = min(d(r), d(r+1)) = d(r+1) - p,
+    // p = [the step r -> r+1 was +1]: one ripple and one threshold test serve two rows, and the
+    // test "C < T" is exact for both (no slack).  Update over a pair, from the previous pair's p:
+    //   C' = C + p_prev + (en1 - lv1) - q2,   q2 = [the step r -> r+1 is -1] = lv2 & ~en2
+    // i.e. a signed delta in [-2, 2], added in two's complement: 2 LOP3 per plane per PAIR.
+    // On a flag the slow path rebuilds d(r) = C + q2 and d(r+1) = C + p.
+    uint32_t pprev = 0;  // the counters start as d(r_start) itself
+    // Written as explicit LOP3s (a = 0xF0, b = 0xCC, c = 0xAA): left to itself the compiler
+    // re-associates the carry chain into a wider, longer form (34 instead of 28 LOP3 per pair).
+    auto pair_step = [&](uint32_t e1, uint32_t l1, uint32_t e2, uint32_t l2, uint32_t &q2) {
+        const uint32_t pn = lop3<0x30>(e2, l2, 0u);       // e2 & ~l2
+        q2 = lop3<0x30>(l2, e2, 0u);                      // l2 & ~e2
+        const uint32_t u0 = lop3<0x3c>(pprev, e1, 0u);    // u = p_prev + en1   (0..2)
+        const uint32_t u1 = lop3<0xc0>(pprev, e1, 0u);
+        const uint32_t v0 = lop3<0x3c>(l1, q2, 0u);       // v = lv1 + q2       (0..2)
+        const uint32_t v1 = lop3<0xc0>(l1, q2, 0u);
+        const uint32_t b0 = lop3<0x0c>(u0, v0, 0u);       // u - v: borrow out of bit 0 = ~u0 & v0
+        const uint32_t d1 = lop3<0x96>(u1, v1, b0);       // bit 1 of u - v
+        const uint32_t sg = lop3<0x8e>(u1, v1, b0);       // borrow out of bit 1 = sign = maj(~u1, v1, b0)
+        uint32_t old = c[0];
+        c[0] = lop3<0x96>(old, u0, v0);
+        uint32_t carry = lop3<0x60>(old, u0, v0);         // old & (u0 ^ v0)
+        old = c[1];
+        c[1] = lop3<0x96>(old, d1, carry);
+        carry = lop3<0xe8>(old, d1, carry);               // majority
+#pragma unroll
+        for (int b = 2; b < NP; ++b) {
+            old = c[b];
+            c[b] = lop3<0x96>(old, sg, carry);
+            if (b + 1 < NP) carry = lop3<0xe8>(old, sg, carry);
+        }
+        pprev = pn;
+    };
     long long row = r_start + 1;
     while (row < r_end) {
         const long long left = r_end - row;
@@ -233,34 +282,23 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
         load_side<P>(prm.a, prm.b, row - 1, s0, wl);
         if (left >= 32) {
 #pragma unroll
-            for (uint32_t t = 0; t < 32; ++t) {
-                const uint32_t en = mism_word<P, WILD>(we, t), lv = mism_word<P, WILD>(wl, t);
-                const uint32_t plus = en & ~lv;
-                uint32_t act = en ^ lv;
-#pragma unroll
-                for (int b = 0; b < NP; ++b) {  // ripple +1 where plus, -1 elsewhere in act
-                    const uint32_t old = c[b];
-                    c[b] = old ^ act;
-                    act &= ~(old ^ plus);
-                }
+            for (uint32_t t = 0; t < 32; t += 2) {
+                uint32_t q2;
+                pair_step(mism_word<P, WILD>(we, t), mism_word<P, WILD>(wl, t), mism_word<P, WILD>(we, t + 1),
+                          mism_word<P, WILD>(wl, t + 1), q2);
                 const uint32_t f = ~c[NP - 1];
-                if (__builtin_expect(f != 0, 0)) flush(f, row + t);
+                if (__builtin_expect(f != 0, 0)) flush(f, row + t, q2, pprev, 2);
             }
             row += 32;
         } else {
 #pragma unroll 1
-            for (uint32_t t = 0; t < (uint32_t)left; ++t) {
-                const uint32_t en = mism_word<P, WILD>(we, t), lv = mism_word<P, WILD>(wl, t);
-                const uint32_t plus = en & ~lv;
-                uint32_t act = en ^ lv;
-#pragma unroll
-                for (int b = 0; b < NP; ++b) {
-                    const uint32_t old = c[b];
-                    c[b] = old ^ act;
-                    act &= ~(old ^ plus);
-                }
+            for (uint32_t t = 0; t < (uint32_t)left; t += 2) {
+                const bool two = t + 1 < (uint32_t)left;
+                uint32_t q2;
+                pair_step(mism_word<P, WILD>(we, t), mism_word<P, WILD>(wl, t),
+                          two ? mism_word<P, WILD>(we, t + 1) : 0u, two ? mism_word<P, WILD>(wl, t + 1) : 0u, q2);
                 const uint32_t f = ~c[NP - 1];
-                if (f) flush(f, row + t);
+                if (f) flush(f, row + t, q2, pprev, two ? 2 : 1);
             }
             row += left;
         }
