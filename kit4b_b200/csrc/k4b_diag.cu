@@ -250,13 +250,8 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
     uint32_t pprev = 0;  // the counters start as d(r_start) itself
     // Written as explicit LOP3s (a = 0xF0, b = 0xCC, c = 0xAA): left to itself the compiler
     // re-associates the carry chain into a wider, longer form (34 instead of 28 LOP3 per pair).
-    auto pair_step = [&](uint32_t e1, uint32_t l1, uint32_t e2, uint32_t l2, uint32_t &q2) {
-        const uint32_t pn = lop3<0x30>(e2, l2, 0u);       // e2 & ~l2
-        q2 = lop3<0x30>(l2, e2, 0u);                      // l2 & ~e2
-        const uint32_t u0 = lop3<0x3c>(pprev, e1, 0u);    // u = p_prev + en1   (0..2)
-        const uint32_t u1 = lop3<0xc0>(pprev, e1, 0u);
-        const uint32_t v0 = lop3<0x3c>(l1, q2, 0u);       // v = lv1 + q2       (0..2)
-        const uint32_t v1 = lop3<0xc0>(l1, q2, 0u);
+    // (u1 u0) = p_prev + en1, (v1 v0) = lv1 + q2, both 0..2; pn = next pair's p_prev
+    auto pair_core = [&](uint32_t u0, uint32_t u1, uint32_t v0, uint32_t v1, uint32_t pn) {
         const uint32_t b0 = lop3<0x0c>(u0, v0, 0u);       // u - v: borrow out of bit 0 = ~u0 & v0
         const uint32_t d1 = lop3<0x96>(u1, v1, b0);       // bit 1 of u - v
         const uint32_t sg = lop3<0x8e>(u1, v1, b0);       // borrow out of bit 1 = sign = maj(~u1, v1, b0)
@@ -274,6 +269,20 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
         }
         pprev = pn;
     };
+    auto pair_step = [&](uint32_t e1, uint32_t l1, uint32_t e2, uint32_t l2, uint32_t &q2) {
+        const uint32_t pn = lop3<0x30>(e2, l2, 0u);       // e2 & ~l2
+        q2 = lop3<0x30>(l2, e2, 0u);                      // l2 & ~e2
+        pair_core(lop3<0x3c>(pprev, e1, 0u), lop3<0xc0>(pprev, e1, 0u), lop3<0x3c>(l1, q2, 0u),
+                  lop3<0xc0>(l1, q2, 0u), pn);
+    };
+    // Two-plane fast path: the XOR of a column window with the broadcast row bit runs on the FMA
+    // pipe, which this kernel otherwise leaves idle: x ^ R = x * s + R for R in {0, ~0}, s = R | 1
+    // (IMAD; measured to overlap LOP3 fully, profiles/r01_intpipe_microbench.json).  (R, s) of the
+    // 32 rows of a block come from a per-warp shared-memory table (one LDS.128 per row and side,
+    // broadcast) instead of 2 uniform-pipe shifts per word, and the OR of the two plane terms is
+    // folded into the LOP3s that consume the mismatch words: 2*NP + 18 ALU ops per row pair.
+    constexpr bool kFma = (P == 2 && !WILD);
+    __shared__ uint4 rowtab[kFma ? kDiagWarps : 1][32][2];
     long long row = r_start + 1;
     while (row < r_end) {
         const long long left = r_end - row;
@@ -281,13 +290,44 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
         load_side<P>(prm.a, prm.b, row + K - 1, s0, we);
         load_side<P>(prm.a, prm.b, row - 1, s0, wl);
         if (left >= 32) {
+            if constexpr (kFma) {
+                __syncwarp();
+                {
+                    const uint32_t e0 = sext_bit(we.ra[0], lane), e1 = sext_bit(we.ra[1], lane);
+                    const uint32_t l0 = sext_bit(wl.ra[0], lane), l1 = sext_bit(wl.ra[1], lane);
+                    rowtab[warp][lane][0] = make_uint4(e0, e0 | 1u, e1, e1 | 1u);
+                    rowtab[warp][lane][1] = make_uint4(l0, l0 | 1u, l1, l1 | 1u);
+                }
+                __syncwarp();
 #pragma unroll
-            for (uint32_t t = 0; t < 32; t += 2) {
-                uint32_t q2;
-                pair_step(mism_word<P, WILD>(we, t), mism_word<P, WILD>(wl, t), mism_word<P, WILD>(we, t + 1),
-                          mism_word<P, WILD>(wl, t + 1), q2);
-                const uint32_t f = ~c[NP - 1];
-                if (__builtin_expect(f != 0, 0)) flush(f, row + t, q2, pprev, 2);
+                for (uint32_t t = 0; t < 32; t += 2) {
+                    const uint4 E1 = rowtab[warp][t][0], L1 = rowtab[warp][t][1];
+                    const uint4 E2 = rowtab[warp][t + 1][0], L2 = rowtab[warp][t + 1][1];
+                    const uint32_t a1 = __funnelshift_r(we.xa[0], we.xb[0], t) * E1.y + E1.x;
+                    const uint32_t b1 = __funnelshift_r(we.xa[1], we.xb[1], t) * E1.w + E1.z;
+                    const uint32_t c1 = __funnelshift_r(wl.xa[0], wl.xb[0], t) * L1.y + L1.x;
+                    const uint32_t d1 = __funnelshift_r(wl.xa[1], wl.xb[1], t) * L1.w + L1.z;
+                    const uint32_t a2 = __funnelshift_r(we.xa[0], we.xb[0], t + 1) * E2.y + E2.x;
+                    const uint32_t b2 = __funnelshift_r(we.xa[1], we.xb[1], t + 1) * E2.w + E2.z;
+                    const uint32_t c2 = __funnelshift_r(wl.xa[0], wl.xb[0], t + 1) * L2.y + L2.x;
+                    const uint32_t d2 = __funnelshift_r(wl.xa[1], wl.xb[1], t + 1) * L2.w + L2.z;
+                    const uint32_t l2 = lop3<0xfc>(c2, d2, 0u);     // lv2 = c2 | d2
+                    const uint32_t pn = lop3<0x54>(a2, b2, l2);     // (a2 | b2) & ~lv2
+                    const uint32_t q2 = lop3<0x02>(a2, b2, l2);     // lv2 & ~(a2 | b2)
+                    pair_core(lop3<0x1e>(pprev, a1, b1), lop3<0xe0>(pprev, a1, b1), lop3<0x1e>(q2, c1, d1),
+                              lop3<0xe0>(q2, c1, d1), pn);
+                    const uint32_t f = ~c[NP - 1];
+                    if (__builtin_expect(f != 0, 0)) flush(f, row + t, q2, pprev, 2);
+                }
+            } else {
+#pragma unroll
+                for (uint32_t t = 0; t < 32; t += 2) {
+                    uint32_t q2;
+                    pair_step(mism_word<P, WILD>(we, t), mism_word<P, WILD>(wl, t), mism_word<P, WILD>(we, t + 1),
+                              mism_word<P, WILD>(wl, t + 1), q2);
+                    const uint32_t f = ~c[NP - 1];
+                    if (__builtin_expect(f != 0, 0)) flush(f, row + t, q2, pprev, 2);
+                }
             }
             row += 32;
         } else {

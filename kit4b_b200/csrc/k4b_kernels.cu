@@ -697,8 +697,22 @@ __global__ void __launch_bounds__(256) microbench_kernel(int iters, uint32_t *si
                     asm volatile("lop3.b32 %0, %1, %2, %3, 0xbe;" : "=r"(m) : "r"(b), "r"(x[k]), "r"(t));
                     asm volatile("popc.b32 %0, %1;" : "=r"(d) : "r"(m));
                     asm volatile("min.u32 %0, %0, %1;" : "+r"(x[k]) : "r"(d));
-                } else {
+                } else if (WHICH == 3) {
                     asm volatile("add.u32 %0, %0, %1;" : "+r"(x[k]) : "r"(a));
+                } else if (WHICH == 4) {  // IMAD alone (FMA pipe)
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(a), "r"(b));
+                } else if (WHICH == 5) {  // LOP3 and IMAD 1:1 - do the ALU and FMA pipes overlap?
+                    if (k & 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(a), "r"(b));
+                    else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[k]) : "r"(a), "r"(b));
+                } else if (WHICH == 6) {  // funnel shift alone
+                    asm volatile("shf.r.wrap.b32 %0, %0, %1, 7;" : "+r"(x[k]) : "r"(a));
+                } else if (WHICH == 7) {  // IMAD.WIDE alone
+                    unsigned long long w;
+                    asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(w) : "r"(x[k]), "r"(a), "l"((unsigned long long)b << 32));
+                    x[k] = (uint32_t)(w >> 32);
+                } else {                  // LOP3 : IMAD 3 : 1
+                    if ((k & 3) == 3) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(a), "r"(b));
+                    else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[k]) : "r"(a), "r"(b));
                 }
             }
         }
@@ -723,6 +737,11 @@ cudaError_t launch_microbench(int which, int iters, uint32_t *d_sink, int *block
         case 1: microbench_kernel<1><<<nb, 256, 0, st>>>(iters, d_sink); break;
         case 2: microbench_kernel<2><<<nb, 256, 0, st>>>(iters, d_sink); break;
         case 3: microbench_kernel<3><<<nb, 256, 0, st>>>(iters, d_sink); break;
+        case 4: microbench_kernel<4><<<nb, 256, 0, st>>>(iters, d_sink); break;
+        case 5: microbench_kernel<5><<<nb, 256, 0, st>>>(iters, d_sink); break;
+        case 6: microbench_kernel<6><<<nb, 256, 0, st>>>(iters, d_sink); break;
+        case 7: microbench_kernel<7><<<nb, 256, 0, st>>>(iters, d_sink); break;
+        case 8: microbench_kernel<8><<<nb, 256, 0, st>>>(iters, d_sink); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
