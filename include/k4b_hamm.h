@@ -163,8 +163,18 @@ int k4b_diag_bootstrap_device(k4b_packed *g, int both_strands, uint32_t q_begin,
                               uint32_t *d_best, void *stream);
 int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t part, uint32_t nparts,
                           uint32_t *d_best, void *stream, int *launches);
+/* The bands run in SLABS (thresholds = block maxima of d_best are refreshed before each; the
+ * first slabs are small so that thresholds tighten early).  k4b_diag_slab_count gives the number
+ * of slabs for this image and nparts; k4b_diag_slabs_device runs slabs [slab_begin, slab_end) of
+ * one part, so that a multi-GPU driver can combine d_best across ranks (element-wise minimum)
+ * BETWEEN slabs and every rank thresholds against what all ranks have found so far.
+ * k4b_diag_bands_device == all slabs in one call. */
+int k4b_diag_slab_count(k4b_packed *g, int both_strands, uint32_t nparts, uint32_t *n_slabs);
+int k4b_diag_slabs_device(k4b_packed *g, int both_strands, uint32_t part, uint32_t nparts,
+                          uint32_t slab_begin, uint32_t slab_end, uint32_t *d_best, void *stream,
+                          int *launches);
 
-/* Counter widths of the most recent k4b_diag_bands_device run of this thread: planes of the full
+/* Counter widths of the most recent band run (k4b_diag_bands_device / _slabs_device) of this thread: planes of the full
  * and of the narrow kernel instance (0 = none), number of slabs, and how many slabs ran narrow
  * (chosen on the device from the slab's largest threshold).  Blocks until that run finished. */
 int k4b_last_diag_info(uint32_t *np_full, uint32_t *np_small, uint32_t *slabs, uint32_t *narrow_slabs);

@@ -325,15 +325,47 @@ extern "C" int k4b_packed_from_image(void *d_image, size_t image_bytes, uint32_t
 // ------------------------------------------------------------------------------------------
 // all-pairs on device-resident data
 // ------------------------------------------------------------------------------------------
-static thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
-static thread_local int g_ev_dev = -1;
+// Kernel timing: CUDA event pairs recorded on the launching stream around the engine launches.
+// A run may consist of several calls (band slabs with collectives in between): every call adds a
+// pair, k4b_last_kernel_ms() sums the pairs recorded since the run began.
+struct TimingPool {
+    std::vector<cudaEvent_t> ev;  // 2 per pair
+    size_t used = 0;              // pairs in use
+    int dev = -1;
+    int begin(int device, bool reset, cudaStream_t st) {
+        if (dev != device) {
+            for (cudaEvent_t e : ev) cudaEventDestroy(e);
+            ev.clear();
+            used = 0;
+            dev = device;
+        }
+        if (reset) used = 0;
+        if (ev.size() < 2 * (used + 1)) {
+            cudaEvent_t a, b;
+            CU(cudaEventCreate(&a));
+            CU(cudaEventCreate(&b));
+            ev.push_back(a);
+            ev.push_back(b);
+        }
+        ++used;
+        CU(cudaEventRecord(ev[2 * used - 2], st));
+        return 0;
+    }
+    cudaError_t end(cudaStream_t st) { return used ? cudaEventRecord(ev[2 * used - 1], st) : cudaSuccess; }
+    cudaEvent_t last() const { return used ? ev[2 * used - 1] : nullptr; }
+};
+static thread_local TimingPool g_tp;
 
 extern "C" float k4b_last_kernel_ms(void) {
-    if (!g_ev0) return -1.f;
-    float ms = -1.f;
-    if (cudaEventSynchronize(g_ev1) != cudaSuccess) return -1.f;
-    if (cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return -1.f;
-    return ms;
+    if (!g_tp.used) return -1.f;
+    float total = 0.f;
+    for (size_t i = 0; i < g_tp.used; ++i) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(g_tp.ev[2 * i + 1]) != cudaSuccess) return -1.f;
+        if (cudaEventElapsedTime(&ms, g_tp.ev[2 * i], g_tp.ev[2 * i + 1]) != cudaSuccess) return -1.f;
+        total += ms;
+    }
+    return total;
 }
 
 struct SweepRange {  // see AllPairsParams
@@ -379,15 +411,6 @@ static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_stra
         CU(cudaMalloc(&queries->d_rc_planes, (size_t)queries->stride * 12));
         CU(launch_revcomp_planes(queries->view(), queries->rc_view(), st));
     }
-    if (g_ev_dev != queries->device) {
-        if (g_ev0) {
-            cudaEventDestroy(g_ev0);
-            cudaEventDestroy(g_ev1);
-        }
-        CU(cudaEventCreate(&g_ev0));
-        CU(cudaEventCreate(&g_ev1));
-        g_ev_dev = queries->device;
-    }
 
     uint32_t *d_min32 = nullptr;
     CU(cudaMallocAsync(&d_min32, (size_t)nq * 4, st));
@@ -414,15 +437,16 @@ static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_stra
     want_chunks = std::max(1u, std::min(want_chunks, prm.tiles_total));
     prm.tiles_per_chunk = (prm.tiles_total + want_chunks - 1) / want_chunks;
 
-    cudaError_t e = cudaEventRecord(g_ev0, st);
-    if (e == cudaSuccess) {
+    RC(g_tp.begin(queries->device, true, st));
+    cudaError_t e = cudaSuccess;
+    {
         if (!generic)
             e = launch_allpairs(prm, three, crick, st, nullptr);
         else
             e = launch_allpairs_generic(prm, three, crick,
                                         crick ? queries->rc_view() : queries->view(), st, nullptr);
     }
-    if (e == cudaSuccess) e = cudaEventRecord(g_ev1, st);
+    if (e == cudaSuccess) e = g_tp.end(st);
     if (e == cudaSuccess)
         e = launch_finalize(d_min32, queries->view(), q_begin, nq, K, clamp, targeted_rules ? 4 : -1,
                             d_out_min, st);
@@ -470,15 +494,6 @@ static int diag_prepare(k4b_packed *g, bool crick, cudaStream_t st, int *nl) {
         CU(cudaMalloc(&g->d_rc_planes, (size_t)g->stride * 12));
         CU(launch_revcomp_planes(g->view(), g->rc_view(), st));
         ++*nl;
-    }
-    if (g_ev_dev != g->device) {
-        if (g_ev0) {
-            cudaEventDestroy(g_ev0);
-            cudaEventDestroy(g_ev1);
-        }
-        CU(cudaEventCreate(&g_ev0));
-        CU(cudaEventCreate(&g_ev1));
-        g_ev_dev = g->device;
     }
     return 0;
 }
@@ -530,8 +545,8 @@ static thread_local uint32_t g_info_slabs = 0, g_info_np_full = 0, g_info_np_sma
 
 extern "C" int k4b_last_diag_info(uint32_t *np_full, uint32_t *np_small, uint32_t *slabs,
                                   uint32_t *narrow_slabs) {
-    if (!g_ev1 || !g_h_tmax) return fail(K4B_ERR_PARAMS, "no band run recorded on this thread");
-    CU(cudaEventSynchronize(g_ev1));
+    if (!g_tp.used || !g_h_tmax) return fail(K4B_ERR_PARAMS, "no band run recorded on this thread");
+    CU(cudaEventSynchronize(g_tp.last()));
     CU(cudaDeviceSynchronize());
     uint32_t narrow = 0;
     for (uint32_t i = 0; i < g_info_slabs; ++i)
@@ -543,37 +558,83 @@ extern "C" int k4b_last_diag_info(uint32_t *np_full, uint32_t *np_small, uint32_
     return K4B_OK;
 }
 
-// Diagonal bands: part `part` of `nparts` of the pair matrix (interleaved CTA groups of 8192
-// diagonals), in slabs with the thresholds (block maxima of d_best) refreshed per slab.
-extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t part, uint32_t nparts,
-                                     uint32_t *d_best, void *stream, int *launches) {
+// Slab schedule of the band engine.  A part owns the CTA groups g = part + nparts * q of each
+// strand; slab j takes the q with (q mod R) in [bounds[j], bounds[j+1]).  The thresholds (block
+// maxima of the running minima) are refreshed before every slab, so the first slabs are SMALL
+// (1/R, 1/R, 2/R, 4/R ... of the work, then R/8 each): thresholds get tight after a few per cent
+// of the pairs instead of after the first 1/16 (profiles/r01_slab_schedule.log).
+namespace {
+struct SlabPlan {
+    uint32_t R = 1;
+    std::vector<uint32_t> bounds;  // n_slabs + 1 entries, 0 .. R
+    uint32_t n_slabs() const { return (uint32_t)bounds.size() - 1; }
+};
+SlabPlan make_slab_plan(uint64_t groups_per_part) {
+    SlabPlan p;
+    const char *sl = getenv("K4B_DIAG_SLABS");  // experiments: n equal slabs
+    if (sl && atoi(sl) > 0) {
+        p.R = (uint32_t)std::min(64, atoi(sl));
+        for (uint32_t i = 0; i <= p.R; ++i) p.bounds.push_back(i);
+        return p;
+    }
+    const char *pr = getenv("K4B_DIAG_PERIOD"), *cp = getenv("K4B_DIAG_CAP");
+    uint32_t rmax = pr ? (uint32_t)atoi(pr) : 64u;
+    while (p.R < rmax && (uint64_t)p.R * 8 <= groups_per_part) p.R *= 2;
+    const uint32_t cap = cp ? std::max(1, atoi(cp)) : std::max(1u, p.R / 8);
+    p.bounds.push_back(0);
+    for (uint32_t pos = 0; pos < p.R;) {
+        pos += std::max(1u, std::min(std::min(cap, pos), p.R - pos));
+        p.bounds.push_back(pos);
+    }
+    return p;
+}
+struct BandGeometry {
+    uint32_t M = 0;
+    uint64_t gw = 0, gc = 0;  // CTA groups of the Watson (s = 1..M) and Crick (s = -M..M) diagonals
+    SlabPlan plan;
+};
+BandGeometry band_geometry(const k4b_packed *g, bool crick, uint32_t nparts) {
+    BandGeometry bg;
+    bg.M = g->len - g->K;
+    bg.gw = ((uint64_t)bg.M + kDiagGroupDiagonals - 1) / kDiagGroupDiagonals;
+    bg.gc = crick ? (2ull * bg.M + 1 + kDiagGroupDiagonals - 1) / kDiagGroupDiagonals : 0;
+    bg.plan = make_slab_plan((bg.gw + bg.gc + nparts - 1) / nparts);
+    return bg;
+}
+}  // namespace
+
+extern "C" int k4b_diag_slab_count(k4b_packed *g, int both_strands, uint32_t nparts, uint32_t *n_slabs) {
+    if (!g || !n_slabs || !nparts) return fail(K4B_ERR_PARAMS, "NULL argument");
+    *n_slabs = g->len < g->K ? 0u : band_geometry(g, both_strands != 0, nparts).plan.n_slabs();
+    return K4B_OK;
+}
+
+// Diagonal bands: slabs [slab_begin, slab_end) of part `part` of `nparts` of the pair matrix
+// (interleaved CTA groups of 8192 diagonals), thresholds refreshed per slab.  Parts (and, with a
+// collective between calls, slab ranges) combine by element-wise minimum of d_best.
+extern "C" int k4b_diag_slabs_device(k4b_packed *g, int both_strands, uint32_t part, uint32_t nparts,
+                                     uint32_t slab_begin, uint32_t slab_end, uint32_t *d_best,
+                                     void *stream, int *launches) {
     if (launches) *launches = 0;
     if (!g || !d_best) return fail(K4B_ERR_PARAMS, "NULL argument");
     if (!nparts || part >= nparts) return fail(K4B_ERR_PARAMS, "part %u of %u", part, nparts);
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t K = g->K, len = g->len;
     if (len < K) return K4B_OK;
-    const uint32_t M = len - K;
     const bool three = g->has_non_acgt != 0, crick = both_strands != 0;
+    const BandGeometry bg = band_geometry(g, crick, nparts);
+    const uint32_t M = bg.M, n_slabs = bg.plan.n_slabs();
+    slab_end = std::min(slab_end, n_slabs);
+    if (slab_begin >= slab_end) return K4B_OK;
     int nl = 0;
     RC(diag_prepare(g, crick, st, &nl));
     const uint32_t bm_shift = 8;
     const uint32_t n_blocks = (M >> bm_shift) + 1;
-    uint32_t *d_bm = nullptr;  // [n_blocks] block maxima + [n_slabs] global maxima (one per slab)
+    uint32_t *d_bm = nullptr;  // [n_blocks] block maxima + [64] global maxima (one per slab)
     CU(cudaMallocAsync(&d_bm, ((size_t)n_blocks + 64) * 4, st));
     CU(cudaMemsetAsync(d_bm + n_blocks, 0, 64 * 4, st));
     const char *rs = getenv("K4B_DIAG_ROWS");
     const uint32_t rows_per_seg = rs ? (uint32_t)atoi(rs) : 4096u;
-    const uint64_t gw = ((uint64_t)M + kDiagGroupDiagonals - 1) / kDiagGroupDiagonals;            // s = 1..M
-    const uint64_t gc = crick ? (2ull * M + 1 + kDiagGroupDiagonals - 1) / kDiagGroupDiagonals : 0;  // s = -M..M
-    // slabs: more slabs = tighter thresholds, fewer = longer launches (less tail); keep at least
-    // ~40 waves of resident CTAs (148 SMs x 8) per launch
-    const uint64_t n_seg64 = ((uint64_t)M + 1 + rows_per_seg - 1) / rows_per_seg;
-    const uint64_t ctas_watson = gw * n_seg64 / 2 + 1;
-    const char *sl = getenv("K4B_DIAG_SLABS");
-    uint32_t n_slabs = sl ? (uint32_t)atoi(sl)
-                          : (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(2, ctas_watson / ((uint64_t)nparts * 1184 * 40)));
-    n_slabs = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min(n_slabs, 64u), (gw + gc) / (4ull * nparts) + 1));
     DiagParams dp;
     dp.a = g->view();
     dp.va = g->view();
@@ -589,23 +650,30 @@ extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t p
     dp.best = d_best;
     dp.blockmax = d_bm;
     dp.bm_shift = bm_shift;
-    dp.grp_step = nparts * n_slabs;
+    dp.part = part;
+    dp.nparts = nparts;
+    dp.q_period = bg.plan.R;
     // counter width: one plane fewer whenever every threshold of the slab fits (checked on the
     // device against the slab's global maximum, so nothing waits for the host)
     const int np_full = diag_planes_for_k(K);
     const int np_small = (np_full - 1 >= 5 && !getenv("K4B_DIAG_FULLNP")) ? np_full - 1 : 0;
-    cudaError_t e = cudaEventRecord(g_ev0, st);
-    for (uint32_t slab = 0; slab < n_slabs && e == cudaSuccess; ++slab) {
+    RC(g_tp.begin(g->device, slab_begin == 0, st));
+    cudaError_t e = cudaSuccess;
+    for (uint32_t slab = slab_begin; slab < slab_end && e == cudaSuccess; ++slab) {
         uint32_t *d_tmax = d_bm + n_blocks + slab;
         e = launch_blockmax(d_best, g->view(), M + 1, bm_shift, d_bm, n_blocks, d_tmax, st);
         dp.tmax_ptr = d_tmax;
         dp.sel_limit = np_small ? (1u << (np_small - 1)) : 0u;
         ++nl;
-        dp.grp_first = part + nparts * slab;
+        dp.q_lo = bg.plan.bounds[slab];
+        dp.q_span = bg.plan.bounds[slab + 1] - dp.q_lo;
         for (int strand = 0; strand < (crick ? 2 : 1) && e == cudaSuccess; ++strand) {
-            const uint64_t ngroups_all = strand ? gc : gw;
-            if (dp.grp_first >= ngroups_all) continue;
-            const uint32_t ng = (uint32_t)((ngroups_all - dp.grp_first + dp.grp_step - 1) / dp.grp_step);
+            const uint64_t ngroups_all = strand ? bg.gc : bg.gw;
+            if (part >= ngroups_all) continue;
+            const uint64_t Qs = (ngroups_all - part + nparts - 1) / nparts;  // this part's groups
+            const uint64_t rem = Qs % bg.plan.R;
+            const uint64_t ng = Qs / bg.plan.R * dp.q_span +
+                                std::min<uint64_t>(dp.q_span, rem > dp.q_lo ? rem - dp.q_lo : 0);
             dp.mode = strand ? kDiagCrick : kDiagWatson;
             dp.col_flip = strand;
             dp.b = strand ? g->rc_view() : g->view();
@@ -613,9 +681,9 @@ extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t p
             // the 1-D grid is limited to 2^31-1 CTAs: split very large launches by groups
             const uint32_t max_groups = std::max(1u, 0x7fffffffu / dp.n_seg);
             DiagParams q = dp;
-            for (uint32_t done = 0; done < ng && e == cudaSuccess; done += max_groups) {
-                q.grp_first = dp.grp_first + done * dp.grp_step;
-                const uint32_t now = std::min(max_groups, ng - done);
+            for (uint64_t done = 0; done < ng && e == cudaSuccess; done += max_groups) {
+                q.l_first = (uint32_t)done;
+                const uint32_t now = (uint32_t)std::min<uint64_t>(max_groups, ng - done);
                 if (np_small) {
                     q.sel = 1;
                     e = launch_diag(q, three, np_small, now, st, nullptr);
@@ -629,10 +697,11 @@ extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t p
             }
         }
     }
-    if (e == cudaSuccess) e = cudaEventRecord(g_ev1, st);
+    if (e == cudaSuccess) e = g_tp.end(st);
     if (e == cudaSuccess && !g_h_tmax) e = cudaMallocHost(&g_h_tmax, 64 * sizeof(uint32_t));
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(g_h_tmax, d_bm + n_blocks, 64 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        e = cudaMemcpyAsync(g_h_tmax + slab_begin, d_bm + n_blocks + slab_begin,
+                            (slab_end - slab_begin) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
     g_info_slabs = n_slabs;
     g_info_np_full = (uint32_t)np_full;
     g_info_np_small = (uint32_t)np_small;
@@ -641,6 +710,12 @@ extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t p
     if (e != cudaSuccess) return fail(cuda_code(e), "diagonal engine launch: %s", cudaGetErrorString(e));
     if (launches) *launches = nl;
     return K4B_OK;
+}
+
+// all slabs of one part in one call
+extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t part, uint32_t nparts,
+                                     uint32_t *d_best, void *stream, int *launches) {
+    return k4b_diag_slabs_device(g, both_strands, part, nparts, 0, 0xffffffffu, d_best, stream, launches);
 }
 
 // Targeted (probes vs assembly) on the band engine: rows = probe K-mers (forward, then their
@@ -682,11 +757,16 @@ extern "C" int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets,
     dp.sel = 0;
     dp.sel_limit = 0;
     dp.s_first = -(long long)dp.Mrow;
-    dp.grp_step = nparts;
+    dp.part = part;
+    dp.nparts = nparts;
+    dp.q_period = 1;  // no slabs: the threshold is fixed
+    dp.q_lo = 0;
+    dp.q_span = 1;
     int np = diag_planes_for_k(K);
     if (np - 1 >= 5 && dp.t_fixed <= (1u << (np - 2))) --np;  // the clamp is tiny: narrow counters
     const uint64_t groups = ((uint64_t)dp.Mrow + dp.Mcol + 1 + kDiagGroupDiagonals - 1) / kDiagGroupDiagonals;
-    cudaError_t e = cudaEventRecord(g_ev0, st);
+    RC(g_tp.begin(probes->device, true, st));
+    cudaError_t e = cudaSuccess;
     for (int strand = 0; strand < (crick ? 2 : 1) && e == cudaSuccess; ++strand) {
         if (part >= groups) break;
         dp.a = strand ? probes->rc_view() : probes->view();
@@ -694,12 +774,12 @@ extern "C" int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets,
         const uint32_t ng = (uint32_t)((groups - part + nparts - 1) / nparts);
         const uint32_t max_groups = std::max(1u, 0x7fffffffu / dp.n_seg);
         for (uint32_t done = 0; done < ng && e == cudaSuccess; done += max_groups) {
-            dp.grp_first = part + done * nparts;
+            dp.l_first = done;
             e = launch_diag(dp, three, np, std::min(max_groups, ng - done), st, nullptr);
             ++nl;
         }
     }
-    if (e == cudaSuccess) e = cudaEventRecord(g_ev1, st);
+    if (e == cudaSuccess) e = g_tp.end(st);
     if (e != cudaSuccess) return fail(cuda_code(e), "targeted band launch: %s", cudaGetErrorString(e));
     if (launches) *launches = nl;
     return K4B_OK;
@@ -916,7 +996,8 @@ int make_sweep(uint32_t len, uint32_t K, uint32_t sweep_start, uint32_t sweep_en
 
 // full-sweep exhaustive run on the diagonal engine: the pair matrix (not the queries) is
 // partitioned over the devices, each keeps a complete array of running minima, and the arrays
-// meet in ONE ncclAllReduce(min) - the single exchange step of the symmetric formulation
+// meet in ncclAllReduce(min) after the bootstrap and after every slab - the exchange step of
+// the symmetric formulation
 static int run_exhaustive_diag(const uint8_t *concat, uint32_t len, uint32_t K, int both,
                                uint16_t *out_min) {
     RC(ensure_init());
@@ -957,13 +1038,20 @@ static int run_exhaustive_diag(const uint8_t *concat, uint32_t len, uint32_t K, 
             return 0;
         };
         if ((rc = allreduce_min())) break;
-        for (int i = 0; i < n && !rc; ++i) {
-            cudaSetDevice(g_eng.devs[i]);
-            rc = k4b_diag_bands_device(imgs[i], both, (uint32_t)i, (uint32_t)n, bests[i], g_eng.streams[i], nullptr);
+        // bands slab by slab; with several devices the minima meet after EVERY slab, so that each
+        // device thresholds against what all of them have found so far
+        uint32_t n_slabs = 0;
+        if ((rc = k4b_diag_slab_count(imgs[0], both, (uint32_t)n, &n_slabs))) break;
+        for (uint32_t slab = 0; slab < n_slabs && !rc; slab = (n == 1 ? n_slabs : slab + 1)) {
+            for (int i = 0; i < n && !rc; ++i) {
+                cudaSetDevice(g_eng.devs[i]);
+                rc = k4b_diag_slabs_device(imgs[i], both, (uint32_t)i, (uint32_t)n, slab,
+                                           n == 1 ? n_slabs : slab + 1, bests[i], g_eng.streams[i], nullptr);
+            }
+            if (!rc) rc = allreduce_min();
         }
         if (rc) break;
         trace.mark("launch");
-        if ((rc = allreduce_min())) break;
         cudaError_t e = cudaSetDevice(g_eng.devs[0]);
         if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)len * 2);
         if (e == cudaSuccess) e = cudaMallocHost(&h_out, (size_t)len * 2);

@@ -152,7 +152,9 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
     }
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t grp_local = blockIdx.x / prm.n_seg, seg = blockIdx.x - grp_local * prm.n_seg;
-    const long long grp = (long long)prm.grp_first + (long long)grp_local * prm.grp_step;
+    const uint32_t l = prm.l_first + grp_local;
+    const long long q = (long long)(l / prm.q_span) * prm.q_period + prm.q_lo + l % prm.q_span;
+    const long long grp = (long long)prm.part + q * prm.nparts;
     const long long S0cta = prm.s_first + grp * kGroupDiags;
     const long long S1cta = S0cta + kGroupDiags - 1;
     const long long Mrow = prm.Mrow, Mcol = prm.Mcol;

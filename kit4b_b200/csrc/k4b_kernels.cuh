@@ -75,7 +75,9 @@ struct DiagParams {
     int wild;                // row symbols >= N are wildcards (targeted rules, needs 3 planes)
     uint32_t t_fixed;        // kDiagRect: fixed threshold (the clamp); else thresholds come from blockmax
     long long s_first;       // diagonal (column - row) of lane 0 of group 0
-    uint32_t grp_first, grp_step;  // CTA group g of this launch = grp_first + local * grp_step
+    // CTA groups of this launch: g = part + nparts * q for the q with (q mod q_period) in
+    // [q_lo, q_lo + q_span), enumerated from index l_first (parts of the pair matrix x slabs)
+    uint32_t part, nparts, q_period, q_lo, q_span, l_first;
     uint32_t n_seg, rows_per_seg;  // row segments per group
     uint32_t *best;          // running minima per position (atomicMin)
     const uint32_t *blockmax;  // max of best over 2^bm_shift positions (valid starts only)

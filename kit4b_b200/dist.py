@@ -74,6 +74,14 @@ class CudaEngine:
         return hamm.diag_bands_device(packed, both, part, nparts, best.data_ptr(),
                                       torch.cuda.current_stream(self.device).cuda_stream)
 
+    def slab_count(self, packed, both: bool, nparts: int) -> int:
+        return hamm.diag_slab_count(packed, both, nparts)
+
+    def slabs(self, packed, both: bool, part: int, nparts: int, slab_begin: int, slab_end: int,
+              best: torch.Tensor) -> int:
+        return hamm.diag_slabs_device(packed, both, part, nparts, slab_begin, slab_end, best.data_ptr(),
+                                      torch.cuda.current_stream(self.device).cuda_stream)
+
     def finalize(self, packed, best: torch.Tensor) -> torch.Tensor:
         out = torch.empty(best.numel(), dtype=torch.int16, device=self.device)
         hamm.best_finalize_device(packed, best.data_ptr(), out.data_ptr(),
@@ -115,12 +123,22 @@ def exhaustive_distributed_bands(concat: Optional[np.ndarray], K: int, both: boo
     engine.bootstrap(packed, both, b, e, best)
     if world > 1:
         dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
-    engine.bands(packed, both, rank, world, best)
-    if world > 1:
-        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
+    bands_slabwise(engine, packed, both, rank, world, best, group)
     if rank != 0:
         return None
     return engine.finalize(packed, best).cpu().numpy().view(np.uint16)
+
+
+def bands_slabwise(engine, packed, both: bool, rank: int, world: int, best: torch.Tensor, group=None) -> int:
+    """This rank's part of the pair matrix, slab by slab, with all_reduce(MIN) after every slab
+    (every rank runs the same number of slabs).  Returns the number of kernel launches."""
+    if world == 1:
+        return engine.bands(packed, both, 0, 1, best)
+    launches = 0
+    for slab in range(engine.slab_count(packed, both, world)):
+        launches += engine.slabs(packed, both, rank, world, slab, slab + 1, best)
+        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
+    return launches
 
 
 def exhaustive_distributed(concat: Optional[np.ndarray], K: int, both: bool, q_begin: int = 0,

@@ -67,6 +67,9 @@ SIGNATURES = {
                                                   ctypes.POINTER(ctypes.c_int)]),
     "k4b_best_finalize_device": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "k4b_last_diag_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint32)] * 4),
+    "k4b_diag_slab_count": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)]),
+    "k4b_diag_slabs_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                             ctypes.c_uint32, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
     "k4b_targeted_diag_device": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32,
                                                 ctypes.c_uint32, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
     "k4b_targeted_finalize_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, _vp]),
@@ -262,6 +265,20 @@ def diag_bands_device(g: Packed, both_strands: bool, part: int, nparts: int, d_b
     n = ctypes.c_int(0)
     _check(load_lib().k4b_diag_bands_device(g.handle, int(both_strands), part, nparts, _vp(d_best_ptr), _vp(stream),
                                             ctypes.byref(n)))
+    return n.value
+
+
+def diag_slab_count(g: Packed, both_strands: bool, nparts: int) -> int:
+    n = ctypes.c_uint32(0)
+    _check(load_lib().k4b_diag_slab_count(g.handle, int(both_strands), nparts, ctypes.byref(n)))
+    return n.value
+
+
+def diag_slabs_device(g: Packed, both_strands: bool, part: int, nparts: int, slab_begin: int, slab_end: int,
+                      d_best_ptr: int, stream: int = 0) -> int:
+    n = ctypes.c_int(0)
+    _check(load_lib().k4b_diag_slabs_device(g.handle, int(both_strands), part, nparts, slab_begin, slab_end,
+                                            _vp(d_best_ptr), _vp(stream), ctypes.byref(n)))
     return n.value
 
 

@@ -62,6 +62,20 @@ class OracleEngine:
             torch.minimum(best, torch.from_numpy(hd.astype(np.int32)), out=best)
         return 1
 
+    # slab-wise form: 3 slabs, slab j = every third sweep offset of this rank's share
+    def slab_count(self, packed, both, nparts):
+        return 3
+
+    def slabs(self, packed, both, part, nparts, slab_begin, slab_end, best):
+        from oracle import hamm_oracle as ho
+        n = len(packed)
+        mine = list(range(1 + part, n + 2, nparts))
+        for slab in range(slab_begin, slab_end):
+            for s in mine[slab::3]:
+                hd = ho.exhaustive_sliding_sweep(packed, self.K, both, s, s)
+                torch.minimum(best, torch.from_numpy(hd.astype(np.int32)), out=best)
+        return slab_end - slab_begin
+
     def finalize(self, packed, best):
         return best.to(torch.int16)
 
