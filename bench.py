@@ -330,8 +330,9 @@ def run_ours_bands(args):
     info = hamm.last_diag_info()                    # counter widths the last step actually ran with
     fr = info["narrow_slabs"] / max(1, info["slabs"])
     np_planes = info["np_small"] * fr + info["np_full"] * (1.0 - fr) if info["np_small"] else float(info["np_full"])
-    ops_per_rowstep = 12.5 + np_planes             # per-thread ALU-pipe instructions per 32-cell row step (SASS:
-                                                   # a row PAIR is 8 SHF + 8 LOP3 + (2*NP+8) LOP3 + 1 ISETP)
+    ops_per_rowstep = 9.0 + np_planes              # per-thread ALU-pipe instructions per 32-cell row step (SASS: a row
+                                                   # PAIR is 8 SHF + (2*NP+9) LOP3 + 1 ISETP on the ALU pipe; its 8 IMAD
+                                                   # run on the FMA pipe, its 4 LDS.128 on the LSU)
     cells = cmps_per_step / 2.0 / world            # every cell serves the two K-mers of a pair
     achieved = cells / 32.0 * ops_per_rowstep / (k_ms * 1e-3) / 1e9
     peak = hamm.microbench_intpipe(1, 4000)        # measured LOP3 thread-ops/s on this GPU
@@ -341,9 +342,11 @@ def run_ours_bands(args):
                           "launches of one step on this rank)" % (info["np_small"], info["np_full"], info["narrow_slabs"],
                                                                  info["slabs"]),
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / ms if ms > 0 else None,
-                "ops_model": "%.1f ALU-pipe thread-ops per 32-cell row step (per row pair: 8 SHF + 8 LOP3 mismatch "
-                             "words, 2*NP+8 LOP3 signed-delta ripple, 1 ISETP; row-base sign extension runs on the "
-                             "uniform pipe); cells = valid pairs, each serving 2 comparisons" % ops_per_rowstep,
+                "ops_model": "%.1f ALU-pipe thread-ops per 32-cell row step (per row PAIR: 8 SHF window cuts + 2*NP+9 "
+                             "LOP3 [pair-min signed-delta ripple] + 1 ISETP; the 8 broadcast XORs of a pair run as IMAD "
+                             "on the FMA pipe, row bits come from a shared-memory table); cells = valid pairs, each "
+                             "serving 2 comparisons; block prologues, warm-up rows and the flagged-cell slow path are "
+                             "NOT counted as useful work" % ops_per_rowstep,
                 "peak_source": "measured live: register-resident LOP3 microbenchmark (k4b_microbench_intpipe), "
                                "nominal 64 lanes/clk/SM x 148 SMs x 1.965 GHz = 18614",
                 "hbm_note": "planes (%.1f MB) are L2 resident; HBM is not the bound" % (hamm.packed_image_bytes(L) / 1e6)}

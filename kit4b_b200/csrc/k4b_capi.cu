@@ -520,7 +520,8 @@ extern "C" int k4b_diag_bootstrap_device(k4b_packed *g, int both_strands, uint32
     bp.q_end = q_end;
     const uint32_t tiles_all = (g->nw + kTileGroups - 1) / kTileGroups;
     const char *bt = getenv("K4B_BOOT_TILES");
-    const uint32_t boot_tiles = bt ? (uint32_t)atoi(bt) : 2u;  // 2 x 8192 candidate starts (profiles/r01_diag_tune_cfg2.log)
+    const uint32_t boot_tiles = bt ? (uint32_t)atoi(bt) : 1u;  // 8192 candidate starts; with the small first slabs
+                                                               // one tile is enough (profiles/r01_slab_schedule.log)
     bp.tiles_total = std::min(tiles_all, std::max(1u, boot_tiles));
     bp.out = d_best + q_begin;  // the kernel indexes out[] relative to q_begin
     bp.self_exclude = 1;
