@@ -96,6 +96,14 @@ int k4b_hamm_exhaustive_shard(const uint8_t *concat, uint32_t concat_len, uint32
 int k4b_hamm_targeted(const uint8_t *target_concat, uint64_t target_len,
                       const uint8_t *probe_concat, uint32_t probe_len, uint32_t K, int R,
                       int both_strands, uint32_t q_begin, uint32_t q_end, uint8_t *out_h);
+/* The NULL-probe form (K-mers of the indexed assembly against itself) with the reference's -z
+ * IntraInterBoth option (hammings.cpp:228; SfxArray.cpp:4421-4426, :4597-4601): 0 = both,
+ * 1 = intra only, 2 = inter only.  As in the reference it filters ONLY exact (0-mismatch)
+ * sense-strand hits: such a hit counts only if it lies in the same (1) / in another (2) entry
+ * than the probe K-mer; entries are the EOS-terminated runs of target_concat. */
+int k4b_hamm_targeted_z(const uint8_t *target_concat, uint64_t target_len, uint32_t K, int R,
+                        int both_strands, int intra_inter_both, uint32_t q_begin, uint32_t q_end,
+                        uint8_t *out_h);
 
 /* ---- device-resident API (inputs already in HBM; used by bench.py and by ranks that receive
  *      the packed target set over NCCL instead of packing it themselves) --------------------- */

@@ -137,11 +137,6 @@ static int run_restricted(const Options &o) {
            sfx.descr.c_str(), sfx.title.c_str(), sfx.version);
     const uint32_t K = (uint32_t)o.K;
     const bool sep_probes = !o.in_seq_file.empty();
-    if (!sep_probes && o.intrainterboth != 0) {
-        logmsg(0, "Intra/inter filtering (-z%d) of K-mers drawn from the indexed assembly is not part of this build",
-               o.intrainterboth);
-        return kErrParams;
-    }
     Genome g;  // probe set in the LoadGenome layout; for no -I it mirrors the suffix entries
     std::vector<uint8_t> flat;
     double secs = 0;
@@ -180,8 +175,10 @@ static int run_restricted(const Options &o) {
                (unsigned long long)g.num_subseqs, K);
         flat.assign(sfx.seq.size(), 0xff);
         const auto t0 = std::chrono::steady_clock::now();
-        rc = k4b_hamm_targeted(sfx.seq.data(), sfx.seq.size(), nullptr, 0, K, o.rhamm, o.crick ? 1 : 0, 0, 0,
-                               flat.data());
+        // -z (hammings.cpp:228) takes effect only here: with -I the reference passes entry 0 and
+        // the filter never fires (hammings.cpp:1691-1694)
+        rc = k4b_hamm_targeted_z(sfx.seq.data(), sfx.seq.size(), K, o.rhamm, o.crick ? 1 : 0, o.intrainterboth, 0, 0,
+                                 flat.data());
         secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
     if (rc) {

@@ -376,6 +376,14 @@ static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_stra
                          int self_exclude, uint32_t q_begin, uint32_t q_end, uint32_t clamp,
                          const SweepRange &sweep, uint16_t *d_out_min, void *stream, int *launches);
 
+// -z of the call in progress on this thread (k4b_hamm_targeted_z): mode 1 intra / 2 inter and
+// the flat start positions of the entries of the indexed assembly
+struct ZFilter {
+    int mode = 0;
+    std::vector<uint32_t> starts;
+};
+static thread_local ZFilter g_zf;
+
 extern "C" int k4b_allpairs_min_device(k4b_packed *queries, k4b_packed *targets, int both_strands,
                                        int self_exclude, uint32_t q_begin, uint32_t q_end,
                                        uint32_t clamp, uint16_t *d_out_min, void *stream,
@@ -426,6 +434,17 @@ static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_stra
     prm.out = d_min32;
     prm.self_exclude = self_exclude ? 1 : 0;
     prm.wildcard = targeted_rules ? 1 : 0;
+    prm.zfilt = 0;
+    prm.ent_starts = nullptr;
+    prm.n_ent = 0;
+    uint32_t *d_ent = nullptr;
+    if (g_zf.mode && targeted_rules && self_exclude && queries == targets && !g_zf.starts.empty()) {
+        CU(cudaMallocAsync(&d_ent, g_zf.starts.size() * 4, st));
+        CU(cudaMemcpyAsync(d_ent, g_zf.starts.data(), g_zf.starts.size() * 4, cudaMemcpyHostToDevice, st));
+        prm.zfilt = g_zf.mode;
+        prm.ent_starts = d_ent;
+        prm.n_ent = (uint32_t)g_zf.starts.size();
+    }
     prm.ranged = sweep.ranged ? 1 : 0;
     prm.w_lo = sweep.w_lo; prm.w_hi = sweep.w_hi;
     prm.c1_lo = sweep.c1_lo; prm.c1_hi = sweep.c1_hi;
@@ -451,6 +470,7 @@ static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_stra
         e = launch_finalize(d_min32, queries->view(), q_begin, nq, K, clamp, targeted_rules ? 4 : -1,
                             d_out_min, st);
     cudaFreeAsync(d_min32, st);
+    if (d_ent) cudaFreeAsync(d_ent, st);
     if (e != cudaSuccess) return fail(cuda_code(e), "allpairs launch: %s", cudaGetErrorString(e));
     if (launches) *launches = 3;  // fill + allpairs + finalize
     return K4B_OK;
@@ -527,6 +547,9 @@ extern "C" int k4b_diag_bootstrap_device(k4b_packed *g, int both_strands, uint32
     bp.self_exclude = 1;
     bp.wildcard = 0;
     bp.ranged = 0;
+    bp.zfilt = 0;
+    bp.ent_starts = nullptr;
+    bp.n_ent = 0;
     bp.w_lo = bp.w_hi = bp.c1_lo = bp.c1_hi = bp.c2_lo = bp.c2_hi = 0;
     const bool generic = W > (uint32_t)kMaxRegW;
     const uint32_t qpt = generic ? 1u : (uint32_t)queries_per_thread(W, three);
@@ -1205,6 +1228,26 @@ extern "C" int k4b_hamm_exhaustive(const uint8_t *concat, uint32_t concat_len, u
                        sweep, [&](uint32_t pos, uint16_t v) {
                            if (v <= K && v < out_min[pos]) out_min[pos] = v;
                        });
+}
+
+extern "C" int k4b_hamm_targeted_z(const uint8_t *target_concat, uint64_t target_len, uint32_t K, int R,
+                                   int both_strands, int intra_inter_both, uint32_t q_begin,
+                                   uint32_t q_end, uint8_t *out_h) {
+    if (intra_inter_both < 0 || intra_inter_both > 2)
+        return fail(K4B_ERR_PARAMS, "intra_inter_both=%d outside 0..2", intra_inter_both);
+    if (!target_concat) return fail(K4B_ERR_PARAMS, "NULL buffer");
+    RC(check_len(target_len));
+    g_zf.mode = intra_inter_both;
+    g_zf.starts.clear();
+    if (intra_inter_both) {  // every entry is followed by EOS (SfxArray.cpp:1746-1750)
+        g_zf.starts.push_back(0);
+        for (uint64_t p = 0; p + 1 < target_len; ++p)
+            if (target_concat[p] == 7) g_zf.starts.push_back((uint32_t)p + 1);
+    }
+    const int rc = k4b_hamm_targeted(target_concat, target_len, nullptr, 0, K, R, both_strands, q_begin, q_end, out_h);
+    g_zf.mode = 0;
+    g_zf.starts.clear();
+    return rc;
 }
 
 extern "C" int k4b_hamm_targeted(const uint8_t *target_concat, uint64_t target_len,

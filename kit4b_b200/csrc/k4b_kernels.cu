@@ -283,6 +283,21 @@ __device__ __forceinline__ void cut_candidate(const uint32_t (&cw)[P][W + 1], ui
     }
 }
 
+// -z: does the exact forward hit of the K-mer at qpos on the K-mer at cpos count?
+__device__ __noinline__ bool zfilter_pass(const AllPairsParams &prm, uint32_t qpos, uint32_t cpos) {
+    auto entry_of = [&](uint32_t pos) {
+        uint32_t lo = 0, hi = prm.n_ent;  // largest i with ent_starts[i] <= pos
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(prm.ent_starts + mid) <= pos) lo = mid;
+            else hi = mid;
+        }
+        return lo;
+    };
+    const bool same = entry_of(qpos) == entry_of(cpos);
+    return prm.zfilt == 1 ? same : !same;
+}
+
 template <int W, int P, int Q, bool CRICK, bool WILD, bool RANGED>
 __global__ void __launch_bounds__(kThreads, 2) allpairs_min_kernel(const AllPairsParams prm) {
     constexpr int S = CRICK ? 2 : 1;
@@ -360,7 +375,8 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_kernel(const AllPair
 #pragma unroll
                 for (int w = 0; w <= W; ++w) cw[p][w] = tile[st][p][g + w];
             const uint32_t gabs = gabs0 + g;
-            const bool self_here = prm.self_exclude && gabs >= qg_lo && gabs <= qg_hi;
+            // -z sends every group down the per-candidate path (positions are needed)
+            const bool self_here = (prm.self_exclude && gabs >= qg_lo && gabs <= qg_hi) || prm.zfilt;
             if (RANGED) {
                 // sub-range sweeps: skip groups no query of this CTA can pair with
                 const long long t0 = (long long)gabs << 5, t1 = t0 + 31;
@@ -401,6 +417,7 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_kernel(const AllPair
                         // the reference skips only EXACT self hits (SfxArray.cpp:4418-4419,
                         // :4585-4594); for identity comparison the self pair is always exact
                         if (self_here && cpos == qpos[j] && d == 0) d = kNoDist;
+                        if (!RANGED && d == 0 && prm.zfilt && !zfilter_pass(prm, qpos[j], cpos)) d = kNoDist;
                         if (RANGED) {
                             const long long dl = (long long)cpos - (long long)qpos[j];
                             const long long ad = dl < 0 ? -dl : dl;
@@ -515,6 +532,7 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_generic_kernel(const
             uint32_t d = acc[0][s];
             const uint32_t cpos = (g << 5) + s;
             if (self_here && cpos == qpos && d == 0) d = kNoDist;
+            if (d == 0 && prm.zfilt && !zfilter_pass(prm, qpos, cpos)) d = kNoDist;
             if (prm.ranged) {
                 const long long dl = (long long)cpos - (long long)qpos;
                 const long long ad = dl < 0 ? -dl : dl;

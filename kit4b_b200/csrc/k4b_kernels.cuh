@@ -54,6 +54,12 @@ struct AllPairsParams {
     // [c2_lo,c2_hi] (the two anti-diagonals one Crick sweep offset covers)
     int ranged;
     long long w_lo, w_hi, c1_lo, c1_hi, c2_lo, c2_hi;
+    // -z intra/inter filter (probes drawn from the indexed assembly; SfxArray.cpp:4421-4426,
+    // :4597-4601): an EXACT forward hit counts only if it lies in the same (1) / another (2)
+    // entry than the query.  ent_starts: ascending flat start positions of the n_ent entries.
+    int zfilt;
+    const uint32_t *ent_starts;
+    uint32_t n_ent;
 };
 
 // diagonal-band engine (k4b_diag.cu)

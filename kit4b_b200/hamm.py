@@ -45,6 +45,8 @@ SIGNATURES = {
                                                  ctypes.c_uint32, ctypes.c_uint32, _u16p]),
     "k4b_hamm_targeted": (ctypes.c_int, [_u8p, ctypes.c_uint64, _u8p, ctypes.c_uint32, ctypes.c_uint32,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _u8p]),
+    "k4b_hamm_targeted_z": (ctypes.c_int, [_u8p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _u8p]),
     "k4b_packed_image_bytes": (ctypes.c_size_t, [ctypes.c_uint32]),
     "k4b_pack_host": (ctypes.c_int, [_u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(_vp)]),
     "k4b_pack_device": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, _vp, ctypes.POINTER(_vp)]),
@@ -143,13 +145,15 @@ def exhaustive_shard(concat, K: int, both_strands: bool, q_begin: int, q_end: in
 
 
 def targeted(target_concat, probe_concat, K: int, R: int, both_strands: bool, q_begin: int = 0,
-             q_end: int = 0) -> np.ndarray:
-    """Probe K-mers vs assembly (-m0 -I).  Returns uint8[len(probe_concat)], 0xFF where no K-mer starts."""
+             q_end: int = 0, intra_inter_both: int = 0) -> np.ndarray:
+    """Probe K-mers vs assembly (-m0 -I).  Returns uint8[len(probe_concat)], 0xFF where no K-mer starts.
+    probe_concat None = the probes are the assembly's own K-mers; only then does intra_inter_both
+    (-z: 1 intra only, 2 inter only, applied to exact sense hits as in the reference) take effect."""
     t = _as_u8(target_concat)
     if probe_concat is None:  # probes are the target's own K-mers (no -I)
         out = np.full(len(t), 0xFF, dtype=np.uint8)
-        _check(load_lib().k4b_hamm_targeted(t.ctypes.data_as(_u8p), len(t), None, 0, K, R, int(both_strands),
-                                            q_begin, q_end, out.ctypes.data_as(_u8p)))
+        _check(load_lib().k4b_hamm_targeted_z(t.ctypes.data_as(_u8p), len(t), K, R, int(both_strands),
+                                              int(intra_inter_both), q_begin, q_end, out.ctypes.data_as(_u8p)))
         return out
     p = _as_u8(probe_concat)
     out = np.full(len(p), 0xFF, dtype=np.uint8)

@@ -67,6 +67,9 @@ def lib():
         L.k4o_targeted_brute.restype = None
         L.k4o_targeted_self_brute.argtypes = [u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, u8p]
         L.k4o_targeted_self_brute.restype = None
+        L.k4o_targeted_self_brute_z.argtypes = [u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, u8p]
+        L.k4o_targeted_self_brute_z.restype = None
         L.k4o_exhaustive_sliding_sweep.argtypes = [u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, u16p,
                                                    ctypes.c_uint32, ctypes.c_uint32]
         L.k4o_exhaustive_sliding_sweep.restype = None
@@ -181,10 +184,11 @@ def targeted_brute(target: np.ndarray, probes: np.ndarray, K: int, R: int, both:
     return out
 
 
-def targeted_self_brute(target: np.ndarray, K: int, R: int, both: bool) -> np.ndarray:
-    """no -I: the probes are the K-mers of the indexed assembly itself."""
+def targeted_self_brute(target: np.ndarray, K: int, R: int, both: bool, zmode: int = 0) -> np.ndarray:
+    """no -I: the probes are the K-mers of the indexed assembly itself; zmode = -z (0 both,
+    1 intra-entry only, 2 inter-entry only - applies to exact sense-strand hits only)."""
     out = np.full(len(target), 0xFF, dtype=np.uint8)
-    lib().k4o_targeted_self_brute(_u8(target), len(target), K, R, int(both), _u8(out))
+    lib().k4o_targeted_self_brute_z(_u8(target), len(target), K, R, int(both), int(zmode), _u8(out))
     return out
 
 

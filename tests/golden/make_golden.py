@@ -144,7 +144,7 @@ def main_targeted(manifest):
     manifest["__targeted__"] = dict(target_fasta="targ.fa", sfx="targ.sfx", probes=probes, runs=runs)
 
 
-def main_targeted_self(manifest):
+def main_targeted_self(manifest, only_new=False):
     """-m0 without -I: K-mers of the indexed assembly against the assembly itself."""
     rng = random.Random(61)
     a = rnd(rng, 2500)
@@ -154,19 +154,26 @@ def main_targeted_self(manifest):
     s3 = mutate(rng, a[1700:1900], 1) + rnd(rng, 60)
     tfa = os.path.join(HERE, "targs.fa")
     sfx = os.path.join(HERE, "targs.sfx")
-    open(tfa, "w").write(fasta([("sA", s1), ("sB", s2), ("sC", s3)]))
-    subprocess.run([REF.replace("_nosleep", ""), "index", "-i", tfa, "-o", sfx, "-r", "targs", "-T2"], check=True,
-                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    if not (only_new and os.path.exists(sfx)):
+        open(tfa, "w").write(fasta([("sA", s1), ("sB", s2), ("sC", s3)]))
+        subprocess.run([REF.replace("_nosleep", ""), "index", "-i", tfa, "-o", sfx, "-r", "targs", "-T2"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     runs = []
-    for K, R, both, fmt in [(32, 3, True, 0), (25, 2, False, 0), (20, 1, True, 1), (50, 5, True, 2)]:
+    # z = -z intra/inter filter of exact sense hits (1 intra only, 2 inter only; SfxArray.cpp:4421-4426)
+    for K, R, both, fmt, z in [(32, 3, True, 0, 0), (25, 2, False, 0, 0), (20, 1, True, 1, 0), (50, 5, True, 2, 0),
+                               (25, 2, True, 0, 1), (25, 2, True, 0, 2), (20, 1, False, 0, 1), (32, 3, False, 0, 2),
+                               (140, 9, True, 0, 2)]:
         ext = ("csv", "bed", "wig")[fmt]
-        out = "targself.K%dr%d%s.%s" % (K, R, "c" if both else "w", ext)
+        out = "targself.K%dr%d%s%s.%s" % (K, R, "c" if both else "w", ("z%d" % z) if z else "", ext)
         args = [REF.replace("_nosleep", ""), "hammings", "-m0", "-K%d" % K, "-r%d" % R, "-S%d" % fmt, "-T2",
                 "-i", "targs.sfx", "-o", out]
         if both:
             args.insert(3, "-c")
-        subprocess.run(args, check=True, cwd=HERE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        runs.append(dict(K=K, R=R, both=both, fmt=fmt, out=out))
+        if z:
+            args.insert(3, "-z%d" % z)
+        if not (only_new and os.path.exists(os.path.join(HERE, out))):
+            subprocess.run(args, check=True, cwd=HERE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        runs.append(dict(K=K, R=R, both=both, fmt=fmt, z=z, out=out))
     manifest["__targeted_self__"] = dict(target_fasta="targs.fa", sfx="targs.sfx", runs=runs)
 
 
@@ -195,6 +202,13 @@ def main_sweeps(manifest):
 def main():
     if not os.access(REF, os.X_OK):
         sys.exit("reference binary missing: run oracle/build_ref.sh first")
+    if len(sys.argv) > 1 and sys.argv[1] == "--targeted-self-only":
+        # add new -m0 (no -I) runs without regenerating the other fixtures
+        mpath = os.path.join(HERE, "manifest.json")
+        manifest = json.load(open(mpath))
+        main_targeted_self(manifest, only_new=True)
+        json.dump(manifest, open(mpath, "w"), indent=1, sort_keys=True)
+        return
     manifest = {}
     main_targeted(manifest)
     main_targeted_self(manifest)

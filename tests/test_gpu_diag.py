@@ -77,6 +77,48 @@ def test_diag_engine_equals_popc_engine_at_scale(lens, K, both, alpha):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("nparts", [1, 3])
+def test_slab_ranges_and_parts_combine_to_the_full_result(nparts):
+    """k4b_diag_slabs_device: slab by slab, part by part (separate minima arrays combined by an
+    element-wise minimum after every slab, as the multi-GPU drivers do) == one all-slab call."""
+    import torch
+    c = random_genome(950, [700000, 90000])
+    c[3000:5000] = c[400000:402000]
+    c = np.ascontiguousarray(c)
+    K, both, L = 32, True, len(c)
+    want = k4b.exhaustive(c, K, both)
+    g = hamm.Packed.from_host(c, K)
+    try:
+        n_slabs = hamm.diag_slab_count(g, both, nparts)
+        assert n_slabs >= 4  # large enough for a real schedule
+        bests = [torch.empty(L, dtype=torch.int32, device="cuda") for _ in range(nparts)]
+        for i, b in enumerate(bests):
+            hamm.best_init_device(b.data_ptr(), L, K)
+            lo, hi = L * i // nparts, L * (i + 1) // nparts
+            hamm.diag_bootstrap_device(g, both, lo, hi, b.data_ptr())
+        def combine():
+            m = bests[0]
+            for b in bests[1:]:
+                m = torch.minimum(m, b)
+            for b in bests:
+                b.copy_(m)
+        torch.cuda.synchronize()
+        combine()
+        launches = 0
+        for slab in range(n_slabs):
+            for i, b in enumerate(bests):
+                launches += hamm.diag_slabs_device(g, both, i, nparts, slab, slab + 1, b.data_ptr())
+            torch.cuda.synchronize()
+            combine()
+        assert launches > 0 and hamm.last_kernel_ms() > 0
+        out = torch.empty(L, dtype=torch.int16, device="cuda")
+        hamm.best_finalize_device(g, bests[0].data_ptr(), out.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy().view(np.uint16), want)
+    finally:
+        g.free()
+
+
 def test_diag_engine_config1_output_md5(tmp_path):
     """BASELINE configs[0] through the CLI with the diagonal engine forced."""
     import random

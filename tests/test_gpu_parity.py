@@ -256,12 +256,15 @@ def test_cli_targeted_without_probe_file_equals_reference(oracle, mr, tmp_path):
             "-o", r["out"]]
     if r["both"]:
         args.insert(2, "-c")
+    z = r.get("z", 0)
+    if z:
+        args.insert(2, "-z%d" % z)  # intra / inter filter of exact sense hits
     _run_cli(args, cwd=str(tmp_path))
     assert open(os.path.join(str(tmp_path), r["out"]), "rb").read() == open(os.path.join(GOLDEN, r["out"]), "rb").read()
     # and the array-level API against the oracle
     _, tseq = oracle.read_sfx(os.path.join(GOLDEN, m["sfx"]))
-    assert np.array_equal(k4b.targeted(tseq, None, r["K"], r["R"], r["both"]),
-                          oracle.targeted_self_brute(tseq, r["K"], r["R"], r["both"]))
+    assert np.array_equal(k4b.targeted(tseq, None, r["K"], r["R"], r["both"], intra_inter_both=z),
+                          oracle.targeted_self_brute(tseq, r["K"], r["R"], r["both"], z))
 
 
 def _sweep_runs():

@@ -99,7 +99,7 @@ def test_targeted_self_oracle_matches_reference_output(oracle, mr):
     """-m0 without -I (K-mers of the indexed assembly against itself)."""
     m, r = mr
     ents, tseq = oracle.read_sfx(os.path.join(GOLDEN, m["sfx"]))
-    h = oracle.restricted_per_loci(ents, oracle.targeted_self_brute(tseq, r["K"], r["R"], r["both"]))
+    h = oracle.restricted_per_loci(ents, oracle.targeted_self_brute(tseq, r["K"], r["R"], r["both"], r.get("z", 0)))
     rep = oracle.restricted_report(ents, r["K"], r["R"], h, r["fmt"], out_name=r["out"])
     assert rep == open(os.path.join(GOLDEN, r["out"]), "rb").read()
 
