@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <chrono>
 #include <mutex>
+#include <cmath>
 #include <vector>
 
 #include "../../include/k4b_hamm.h"
@@ -431,6 +432,7 @@ static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_stra
     prm.q_begin = q_begin;
     prm.q_end = q_end;
     prm.tiles_total = (targets->nw + kTileGroups - 1) / kTileGroups;
+    prm.groups_limit = 0;
     prm.out = d_min32;
     prm.self_exclude = self_exclude ? 1 : 0;
     prm.wildcard = targeted_rules ? 1 : 0;
@@ -543,6 +545,9 @@ extern "C" int k4b_diag_bootstrap_device(k4b_packed *g, int both_strands, uint32
     const uint32_t boot_tiles = bt ? (uint32_t)atoi(bt) : 1u;  // 8192 candidate starts; with the small first slabs
                                                                // one tile is enough (profiles/r01_slab_schedule.log)
     bp.tiles_total = std::min(tiles_all, std::max(1u, boot_tiles));
+    // K > 128 runs the (slower) generic POPC kernel, and long K-mers have relatively narrow distance
+    // distributions: a quarter tile (2048 candidate starts) bounds the minima almost as well
+    bp.groups_limit = (W > (uint32_t)kMaxRegW && !bt) ? 64u : 0u;
     bp.out = d_best + q_begin;  // the kernel indexes out[] relative to q_begin
     bp.self_exclude = 1;
     bp.wildcard = 0;
@@ -565,7 +570,8 @@ extern "C" int k4b_diag_bootstrap_device(k4b_packed *g, int both_strands, uint32
 
 // bookkeeping of the most recent band run of this thread (which counter width each slab used)
 static thread_local uint32_t *g_h_tmax = nullptr;  // pinned, 64 entries
-static thread_local uint32_t g_info_slabs = 0, g_info_np_full = 0, g_info_np_small = 0, g_info_limit = 0;
+static thread_local uint32_t g_info_slabs = 0, g_info_np_full = 0, g_info_np_small = 0, g_info_limit = 0,
+                             g_info_low_max = 0;
 
 extern "C" int k4b_last_diag_info(uint32_t *np_full, uint32_t *np_small, uint32_t *slabs,
                                   uint32_t *narrow_slabs) {
@@ -574,7 +580,7 @@ extern "C" int k4b_last_diag_info(uint32_t *np_full, uint32_t *np_small, uint32_
     CU(cudaDeviceSynchronize());
     uint32_t narrow = 0;
     for (uint32_t i = 0; i < g_info_slabs; ++i)
-        if (g_info_np_small && g_h_tmax[i] <= g_info_limit) ++narrow;
+        if (g_info_np_small && g_h_tmax[i] <= g_info_limit && g_h_tmax[64 + i] <= g_info_low_max) ++narrow;
     if (np_full) *np_full = g_info_np_full;
     if (np_small) *np_small = g_info_np_small;
     if (slabs) *slabs = g_info_slabs;
@@ -654,9 +660,9 @@ extern "C" int k4b_diag_slabs_device(k4b_packed *g, int both_strands, uint32_t p
     RC(diag_prepare(g, crick, st, &nl));
     const uint32_t bm_shift = 8;
     const uint32_t n_blocks = (M >> bm_shift) + 1;
-    uint32_t *d_bm = nullptr;  // [n_blocks] block maxima + [64] global maxima (one per slab)
-    CU(cudaMallocAsync(&d_bm, ((size_t)n_blocks + 64) * 4, st));
-    CU(cudaMemsetAsync(d_bm + n_blocks, 0, 64 * 4, st));
+    uint32_t *d_bm = nullptr;  // [n_blocks] block maxima + per slab: [64] global maxima, [64] low-block counts
+    CU(cudaMallocAsync(&d_bm, ((size_t)n_blocks + 128) * 4, st));
+    CU(cudaMemsetAsync(d_bm + n_blocks, 0, 128 * 4, st));
     const char *rs = getenv("K4B_DIAG_ROWS");
     const uint32_t rows_per_seg = rs ? (uint32_t)atoi(rs) : 4096u;
     DiagParams dp;
@@ -681,13 +687,19 @@ extern "C" int k4b_diag_slabs_device(k4b_packed *g, int both_strands, uint32_t p
     // device against the slab's global maximum, so nothing waits for the host)
     const int np_full = diag_planes_for_k(K);
     const int np_small = (np_full - 1 >= 5 && !getenv("K4B_DIAG_FULLNP")) ? np_full - 1 : 0;
+    // the narrow instance must lift thresholds below K+1-2^(np_small-1) (its counters cannot hold
+    // K otherwise), which multiplies the flags there: it runs only while fewer than 1/64 of the
+    // blocks sit below that floor (K=25: floor 10 but final minima 6-9 -> full width)
+    const uint32_t low_floor = (np_small && K + 1 > (1u << (np_small - 1))) ? K + 1 - (1u << (np_small - 1)) : 0u;
     RC(g_tp.begin(g->device, slab_begin == 0, st));
     cudaError_t e = cudaSuccess;
     for (uint32_t slab = slab_begin; slab < slab_end && e == cudaSuccess; ++slab) {
-        uint32_t *d_tmax = d_bm + n_blocks + slab;
-        e = launch_blockmax(d_best, g->view(), M + 1, bm_shift, d_bm, n_blocks, d_tmax, st);
+        uint32_t *d_tmax = d_bm + n_blocks + slab, *d_low = d_bm + n_blocks + 64 + slab;
+        e = launch_blockmax(d_best, g->view(), M + 1, bm_shift, d_bm, n_blocks, d_tmax, low_floor, d_low, st);
         dp.tmax_ptr = d_tmax;
         dp.sel_limit = np_small ? (1u << (np_small - 1)) : 0u;
+        dp.low_ptr = d_low;
+        dp.low_max = n_blocks / 64;
         ++nl;
         dp.q_lo = bg.plan.bounds[slab];
         dp.q_span = bg.plan.bounds[slab + 1] - dp.q_lo;
@@ -722,10 +734,14 @@ extern "C" int k4b_diag_slabs_device(k4b_packed *g, int both_strands, uint32_t p
         }
     }
     if (e == cudaSuccess) e = g_tp.end(st);
-    if (e == cudaSuccess && !g_h_tmax) e = cudaMallocHost(&g_h_tmax, 64 * sizeof(uint32_t));
+    if (e == cudaSuccess && !g_h_tmax) e = cudaMallocHost(&g_h_tmax, 128 * sizeof(uint32_t));
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(g_h_tmax + slab_begin, d_bm + n_blocks + slab_begin,
                             (slab_end - slab_begin) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(g_h_tmax + 64 + slab_begin, d_bm + n_blocks + 64 + slab_begin,
+                            (slab_end - slab_begin) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    g_info_low_max = n_blocks / 64;
     g_info_slabs = n_slabs;
     g_info_np_full = (uint32_t)np_full;
     g_info_np_small = (uint32_t)np_small;
@@ -740,6 +756,14 @@ extern "C" int k4b_diag_slabs_device(k4b_packed *g, int both_strands, uint32_t p
 extern "C" int k4b_diag_bands_device(k4b_packed *g, int both_strands, uint32_t part, uint32_t nparts,
                                      uint32_t *d_best, void *stream, int *launches) {
     return k4b_diag_slabs_device(g, both_strands, part, nparts, 0, 0xffffffffu, d_best, stream, launches);
+}
+
+// P(distance of two unrelated K-mers < t) for uniform random bases: the binomial(K, 3/4) tail
+static double random_pair_tail(uint32_t K, uint32_t t) {
+    double sum = 0;
+    for (uint32_t x = 0; x < t && x <= K; ++x)
+        sum += exp(lgamma(K + 1.0) - lgamma(x + 1.0) - lgamma(K - x + 1.0) + x * log(0.75) + (K - x) * log(0.25));
+    return sum;
 }
 
 // Targeted (probes vs assembly) on the band engine: rows = probe K-mers (forward, then their
@@ -778,6 +802,8 @@ extern "C" int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets,
     dp.blockmax = nullptr;
     dp.bm_shift = 0;
     dp.tmax_ptr = nullptr;
+    dp.low_ptr = nullptr;
+    dp.low_max = 0;
     dp.sel = 0;
     dp.sel_limit = 0;
     dp.s_first = -(long long)dp.Mrow;
@@ -787,7 +813,13 @@ extern "C" int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets,
     dp.q_lo = 0;
     dp.q_span = 1;
     int np = diag_planes_for_k(K);
-    if (np - 1 >= 5 && dp.t_fixed <= (1u << (np - 2))) --np;  // the clamp is tiny: narrow counters
+    // the clamp is tiny: one counter plane fewer, provided the floor the narrow counters impose
+    // on the threshold (K+1-2^(np-2)) does not flag too many cells of unrelated sequence
+    if (np - 1 >= 5 && dp.t_fixed <= (1u << (np - 2))) {
+        const uint32_t half = 1u << (np - 2);
+        const uint32_t floor_narrow = K + 1 > half ? K + 1 - half : 0u;
+        if (floor_narrow <= dp.t_fixed || random_pair_tail(K, floor_narrow) < 1e-7) --np;
+    }
     const uint64_t groups = ((uint64_t)dp.Mrow + dp.Mcol + 1 + kDiagGroupDiagonals - 1) / kDiagGroupDiagonals;
     RC(g_tp.begin(probes->device, true, st));
     cudaError_t e = cudaSuccess;

@@ -46,7 +46,8 @@ __device__ __forceinline__ uint32_t sext_bit(uint32_t x, uint32_t t) {
 __global__ void __launch_bounds__(256) blockmax_kernel(const uint32_t *__restrict__ best, ImageView a,
                                                        uint32_t n_pos, uint32_t shift,
                                                        uint32_t *__restrict__ blockmax, uint32_t n_blocks,
-                                                       uint32_t *__restrict__ tmax) {
+                                                       uint32_t *__restrict__ tmax, uint32_t low_floor,
+                                                       uint32_t *__restrict__ n_low) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_blocks) return;
     const uint32_t base = warp << shift, span = 1u << shift;
@@ -59,6 +60,8 @@ __global__ void __launch_bounds__(256) blockmax_kernel(const uint32_t *__restric
     if (lane == 0) {
         blockmax[warp] = m;
         if (tmax && m) atomicMax(tmax, m);
+        // blocks whose threshold the narrow-counter instance would have to lift (more flags)
+        if (n_low && m && m < low_floor) atomicAdd(n_low, 1u);
     }
 }
 
@@ -148,7 +151,8 @@ template <int NP, int P, bool WILD>
 __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagParams prm) {
     if (prm.sel) {  // device-side choice between the narrow- and the full-counter instance
         const uint32_t tg = __ldg(prm.tmax_ptr);
-        if ((prm.sel == 1) != (tg <= prm.sel_limit)) return;
+        const bool narrow = tg <= prm.sel_limit && __ldg(prm.low_ptr) <= prm.low_max;
+        if ((prm.sel == 1) != narrow) return;
     }
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t grp_local = blockIdx.x / prm.n_seg, seg = blockIdx.x - grp_local * prm.n_seg;
@@ -348,10 +352,12 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
 }
 
 cudaError_t launch_blockmax(const uint32_t *d_best, ImageView a, uint32_t n_pos, uint32_t shift,
-                            uint32_t *d_blockmax, uint32_t n_blocks, uint32_t *d_tmax, cudaStream_t st) {
+                            uint32_t *d_blockmax, uint32_t n_blocks, uint32_t *d_tmax, uint32_t low_floor,
+                            uint32_t *d_n_low, cudaStream_t st) {
     if (!n_blocks) return cudaSuccess;
     const uint32_t threads = n_blocks * 32;
-    blockmax_kernel<<<(threads + 255) / 256, 256, 0, st>>>(d_best, a, n_pos, shift, d_blockmax, n_blocks, d_tmax);
+    blockmax_kernel<<<(threads + 255) / 256, 256, 0, st>>>(d_best, a, n_pos, shift, d_blockmax, n_blocks, d_tmax,
+                                                           low_floor, d_n_low);
     return cudaGetLastError();
 }
 

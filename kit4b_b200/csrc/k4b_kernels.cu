@@ -472,7 +472,8 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_generic_kernel(const
 
     const uint32_t g_begin = blockIdx.x * prm.tiles_per_chunk * kTileGroups;
     uint32_t g_end = g_begin + prm.tiles_per_chunk * kTileGroups;
-    const uint32_t g_tot = prm.tiles_total * kTileGroups;
+    uint32_t g_tot = prm.tiles_total * kTileGroups;
+    if (prm.groups_limit && g_tot > prm.groups_limit) g_tot = prm.groups_limit;
     if (g_end > g_tot) g_end = g_tot;
     const uint32_t qg = qpos >> 5;
 
@@ -728,6 +729,11 @@ __global__ void __launch_bounds__(256) microbench_kernel(int iters, uint32_t *si
                     unsigned long long w;
                     asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(w) : "r"(x[k]), "r"(a), "l"((unsigned long long)b << 32));
                     x[k] = (uint32_t)(w >> 32);
+                } else if (WHICH == 9) {  // IMAD.HI alone
+                    asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(a), "r"(b));
+                } else if (WHICH == 10) {  // LOP3 : IMAD.HI 3 : 1
+                    if ((k & 3) == 3) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(a), "r"(b));
+                    else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[k]) : "r"(a), "r"(b));
                 } else {                  // LOP3 : IMAD 3 : 1
                     if ((k & 3) == 3) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(a), "r"(b));
                     else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[k]) : "r"(a), "r"(b));
@@ -760,6 +766,8 @@ cudaError_t launch_microbench(int which, int iters, uint32_t *d_sink, int *block
         case 6: microbench_kernel<6><<<nb, 256, 0, st>>>(iters, d_sink); break;
         case 7: microbench_kernel<7><<<nb, 256, 0, st>>>(iters, d_sink); break;
         case 8: microbench_kernel<8><<<nb, 256, 0, st>>>(iters, d_sink); break;
+        case 9: microbench_kernel<9><<<nb, 256, 0, st>>>(iters, d_sink); break;
+        case 10: microbench_kernel<10><<<nb, 256, 0, st>>>(iters, d_sink); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

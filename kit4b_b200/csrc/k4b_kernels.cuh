@@ -46,6 +46,7 @@ struct AllPairsParams {
     uint32_t q_begin, q_end; // flat query start positions [q_begin, q_end)
     uint32_t tiles_total;    // number of kTileGroups tiles covering the target set
     uint32_t tiles_per_chunk;
+    uint32_t groups_limit;   // generic (K > 128) kernel only: stop after this many 32-candidate groups (0 = all)
     uint32_t *out;           // [q_end-q_begin] running minima (pre-set to K+1)
     int self_exclude;        // skip forward pair with query pos == target pos
     int wildcard;            // targeted mode: query symbols >= N match any target ACGT base
@@ -92,12 +93,17 @@ struct DiagParams {
     // counter widths and each instance checks the global maximum threshold on the device
     const uint32_t *tmax_ptr;  // max over all blockmax entries (written by blockmax_kernel)
     uint32_t sel_limit;
-    int sel;                   // 0 run always, 1 run iff *tmax_ptr <= sel_limit, 2 iff > sel_limit
+    const uint32_t *low_ptr;   // number of blocks whose maximum lies below the narrow instance's floor
+    uint32_t low_max;          // (their thresholds would be lifted: more flags); narrow only if <= low_max
+    int sel;                   // 0 run always, 1 run iff narrow fits (*tmax_ptr <= sel_limit and few
+                               // low blocks), 2 iff not
 };
 constexpr int kDiagGroupDiagonals = 8 * 1024;  // diagonals per CTA group (8 warps x 1024)
-// d_tmax (nullable): receives the maximum over all blocks; must be zeroed by the caller
+// d_tmax (nullable): receives the maximum over all blocks; d_n_low (nullable): the number of
+// blocks with 0 < maximum < low_floor; both must be zeroed by the caller
 cudaError_t launch_blockmax(const uint32_t *d_best, ImageView a, uint32_t n_pos, uint32_t shift,
-                            uint32_t *d_blockmax, uint32_t n_blocks, uint32_t *d_tmax, cudaStream_t st);
+                            uint32_t *d_blockmax, uint32_t n_blocks, uint32_t *d_tmax, uint32_t low_floor,
+                            uint32_t *d_n_low, cudaStream_t st);
 // np = number of counter planes (5..14); thresholds must fit 2^(np-1)
 cudaError_t launch_diag(const DiagParams &p, bool three_planes, int np, uint32_t n_groups, cudaStream_t st,
                         unsigned long long *n_ctas);

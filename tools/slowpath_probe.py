@@ -12,6 +12,7 @@ from kit4b_b200 import hamm
 k4b.gpu_init(1)
 for wl in sys.argv[1:] or ["cfg2"]:
     concat, chroms, K, both = bench.synth_genome(wl)
+    K = int(os.environ.get("K4B_PROBE_K", K))  # same genome, other K
     L = len(concat)
     d_concat = torch.from_numpy(concat).cuda()
     g = hamm.Packed.from_device(d_concat.data_ptr(), L, K)
