@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <fstream>
 #include <iterator>
+#include <thread>
+#include <vector>
 
 #include "k4b_host.h"
 
@@ -37,6 +39,19 @@ class Out {
         if (buf_.size() >= (1 << 20) - 4096) flush();
     }
     void put(const std::string &s) { put(s.data(), s.size()); }
+    void put_big(const std::string &s) {  // large block: straight to the fd
+        flush();
+        size_t off = 0;
+        while (off < s.size()) {
+            const ssize_t w = ::write(fd_, s.data() + off, s.size() - off);
+            if (w < 0) {
+                if (errno == EINTR || errno == EAGAIN) continue;
+                ok_ = false;
+                break;
+            }
+            off += (size_t)w;
+        }
+    }
     bool flush() {
         size_t off = 0;
         while (off < buf_.size()) {
@@ -90,6 +105,27 @@ struct PrefixFilter {
 
 }  // namespace
 
+// decimal digits of v at p, returns the end
+static inline char *put_u32(char *p, uint32_t v) {
+    char tmp[10];
+    int n = 0;
+    do {
+        tmp[n++] = (char)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+// One run of consecutive lines of the exhaustive CSV: chromosome ci, flat positions
+// seq_idx .. seq_idx+count-1, loci first_loci ..
+struct CsvRun {
+    size_t ci;
+    uint64_t seq_idx;
+    uint32_t first_loci;
+    uint64_t count;
+};
+
 int write_exhaustive_csv(const std::string &path, const Genome &g, uint32_t K, const uint16_t *hd,
                          uint32_t sweep_start, uint32_t sweep_end, std::string &err) {
     Out out;
@@ -98,26 +134,70 @@ int write_exhaustive_csv(const std::string &path, const Genome &g, uint32_t K, c
     char line[256];
     int n = snprintf(line, sizeof(line), "%u,%d,%d\n", g.genome_len, (int)(sweep_start + 1), (int)sweep_end);
     out.put(line, (size_t)n);
-    const uint32_t flat = g.genome_len - 2;
+    const uint64_t flat = g.genome_len - 2;
+    // The reference walks the flat array with (SeqIdx, CurLoci, chromosome) state
+    // (hammings.cpp:2899-2929): when CurLoci reaches the chromosome's NumSubSeqs it moves to the
+    // next chromosome and skips K positions (its K-1 tail positions + the separator) - which
+    // over-skips after a chromosome shorter than K, then reads mis-aligned values, and emits one
+    // line for a chromosome without any K-mer.  The same walk is first done run by run (cheap),
+    // then the runs are formatted by several threads and written in order: same bytes.
+    std::vector<CsvRun> runs;
     if (!g.chroms.empty()) {
         size_t ci = 0;
+        uint64_t seq_idx = 0;
         uint32_t cur_loci = 0;
-        // SeqIdx walks the flat array; a chromosome switch skips K positions (its K-1 tail
-        // positions + the separator) - which over-skips after a chromosome shorter than K and
-        // then reads mis-aligned (and possibly past-the-end) values exactly as the reference does
-        for (uint64_t seq_idx = 0; seq_idx < flat; ++seq_idx, ++cur_loci) {
+        while (seq_idx < flat) {
             if (cur_loci >= g.chroms[ci].num_subseqs) {
                 if (ci + 1 == g.chroms.size()) break;
                 ++ci;
                 cur_loci = 0;
                 seq_idx += K;
             }
-            const uint32_t v = seq_idx < flat ? hd[seq_idx] : K + 1;
-            if (v <= K) {
-                n = snprintf(line, sizeof(line), "\"%s\",%d,%d\n", g.chroms[ci].name.c_str(), (int)cur_loci, (int)v);
-                out.put(line, (size_t)n);
-            }
+            // this iteration plus the following ones that stay inside the chromosome
+            const uint64_t ns = g.chroms[ci].num_subseqs;
+            const uint64_t run = ns > (uint64_t)cur_loci + 1 ? ns - cur_loci : 1;
+            const uint64_t valid = seq_idx < flat ? std::min(run, flat - seq_idx) : 0;  // past the end: K+1, no line
+            if (valid) runs.push_back(CsvRun{ci, seq_idx, cur_loci, valid});
+            seq_idx += run;
+            cur_loci += (uint32_t)run;
         }
+    }
+    // tasks of at most kTaskLines lines, formatted kWave at a time
+    constexpr uint64_t kTaskLines = 1u << 20;
+    std::vector<CsvRun> tasks;
+    for (const CsvRun &r : runs)
+        for (uint64_t o = 0; o < r.count; o += kTaskLines)
+            tasks.push_back(CsvRun{r.ci, r.seq_idx + o, (uint32_t)(r.first_loci + o), std::min(kTaskLines, r.count - o)});
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t wave = std::max<size_t>(1, std::min<size_t>(hw ? hw : 4, 16));
+    std::vector<std::string> bufs(wave);
+    auto format = [&](const CsvRun &t, std::string &buf) {
+        const std::string &name = g.chroms[t.ci].name;
+        const size_t per_line = name.size() + 3 + 10 + 1 + 10 + 1;
+        buf.resize((size_t)t.count * per_line);
+        char *p = &buf[0];
+        for (uint64_t i = 0; i < t.count; ++i) {
+            const uint32_t v = hd[t.seq_idx + i];
+            if (v > K) continue;
+            *p++ = '"';
+            memcpy(p, name.data(), name.size());
+            p += name.size();
+            *p++ = '"';
+            *p++ = ',';
+            p = put_u32(p, t.first_loci + (uint32_t)i);
+            *p++ = ',';
+            p = put_u32(p, v);
+            *p++ = '\n';
+        }
+        buf.resize((size_t)(p - &buf[0]));
+    };
+    for (size_t t0 = 0; t0 < tasks.size(); t0 += wave) {
+        const size_t nt = std::min(wave, tasks.size() - t0);
+        std::vector<std::thread> th;
+        for (size_t j = 1; j < nt; ++j) th.emplace_back([&, j]() { format(tasks[t0 + j], bufs[j]); });
+        format(tasks[t0], bufs[0]);
+        for (std::thread &x : th) x.join();
+        for (size_t j = 0; j < nt; ++j) out.put_big(bufs[j]);
     }
     return out.close_sync(err);
 }
