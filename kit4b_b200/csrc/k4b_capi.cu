@@ -123,6 +123,15 @@ extern "C" int k4b_gpu_init(int n_gpus, const int *device_ids) {
     for (int i = 0; i < n_gpus; ++i) {
         CU(cudaSetDevice(g_eng.devs[i]));
         CU(cudaStreamCreateWithFlags(&g_eng.streams[i], cudaStreamNonBlocking));
+        {   // keep stream-ordered allocations cached in the pool: the default (release threshold 0)
+            // hands multi-GB scratch (seed index) back to the driver at the next synchronisation,
+            // which stalled the host for seconds (profiles/r01_seed_engine.log)
+            cudaMemPool_t pool = nullptr;
+            if (cudaDeviceGetDefaultMemPool(&pool, g_eng.devs[i]) == cudaSuccess && pool) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+        }
     }
     if (n_gpus > 1) {
         RC(load_nccl(g_eng.nccl));
@@ -481,16 +490,19 @@ static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_stra
 // ------------------------------------------------------------------------------------------
 // diagonal-band engine on device-resident data
 // ------------------------------------------------------------------------------------------
-static int g_engine = -1;  // 0 auto, 1 POPC all-pairs, 2 diagonal bands; -1 = read K4B_ENGINE
+// 0 auto, 1 POPC all-pairs, 2 diagonal bands, 3 seed-and-verify where it applies (targeted mode
+// with pure-ACGT probes) else as auto; -1 = read K4B_ENGINE
+static int g_engine = -1;
 static int engine_setting() {
     if (g_engine < 0) {
         const char *e = getenv("K4B_ENGINE");
-        g_engine = !e ? 0 : (!strcmp(e, "popc") ? 1 : (!strcmp(e, "diag") ? 2 : 0));
+        g_engine = !e ? 0 : (!strcmp(e, "popc") ? 1 : (!strcmp(e, "diag") ? 2 : (!strcmp(e, "seed") ? 3 : 0)));
     }
     return g_engine;
 }
 extern "C" int k4b_set_engine(int engine) {
-    if (engine < 0 || engine > 2) return fail(K4B_ERR_PARAMS, "engine must be 0 (auto), 1 (popc) or 2 (diag)");
+    if (engine < 0 || engine > 3)
+        return fail(K4B_ERR_PARAMS, "engine must be 0 (auto), 1 (popc), 2 (diag) or 3 (seed)");
     g_engine = engine;
     return K4B_OK;
 }
@@ -841,6 +853,51 @@ extern "C" int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets,
     return K4B_OK;
 }
 
+// Targeted (probes vs assembly) by seed-and-verify (k4b_seed.cu): exact for every distance below
+// clamp, the "not found" value, as long as clamp <= K / core_len (pigeonhole over the disjoint
+// cores); probes must be pure ACGT.  Handles the probe K-mers starting in [q_begin, q_end);
+// ranges combine by element-wise minimum of d_best.
+extern "C" int k4b_targeted_seed_device(k4b_packed *probes, k4b_packed *targets, int both_strands,
+                                        uint32_t clamp, uint32_t core_len, uint32_t q_begin,
+                                        uint32_t q_end, uint32_t *d_best, void *stream, int *launches) {
+    if (launches) *launches = 0;
+    if (!probes || !targets || !d_best) return fail(K4B_ERR_PARAMS, "NULL argument");
+    if (probes->K != targets->K) return fail(K4B_ERR_PARAMS, "probe/target K differ");
+    if (probes->device != targets->device) return fail(K4B_ERR_PARAMS, "images live on different devices");
+    if (probes->has_non_acgt) return fail(K4B_ERR_UNSUPPORTED, "seed engine needs pure-ACGT probes");
+    const uint32_t K = probes->K;
+    if (!core_len || core_len > K || !clamp || clamp > K / core_len)
+        return fail(K4B_ERR_PARAMS, "core_len=%u clamp=%u: the pigeonhole bound needs clamp <= K/core_len", core_len, clamp);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (q_end > probes->len) q_end = probes->len;
+    if (probes->len < K || targets->len < K || q_begin >= q_end) return K4B_OK;
+    const bool crick = both_strands != 0;
+    int nl = 0;
+    RC(diag_prepare(probes, crick, st, &nl));  // reverse-complemented probe planes
+    const uint32_t nb = 1u << seed_bucket_bits(core_len);
+    const size_t temp_bytes = seed_scan_temp_bytes(nb);
+    uint32_t *d_idx = nullptr;  // sig (targets->len x 8 B) | pos (targets->len) | cnt | off | cursor (nb+1 each)
+    void *d_temp = nullptr;
+    const size_t words = 3 * ((size_t)nb + 1) + 3 * (size_t)targets->len;
+    CU(cudaMallocAsync(&d_idx, words * 4, st));
+    CU(cudaMallocAsync(&d_temp, temp_bytes ? temp_bytes : 4, st));
+    uint2 *d_sig = (uint2 *)d_idx;
+    uint32_t *d_pos = d_idx + 2 * (size_t)targets->len;
+    uint32_t *d_cnt = d_pos + targets->len, *d_off = d_cnt + nb + 1, *d_cur = d_off + nb + 1;
+    CU(cudaMemsetAsync(d_cnt, 0, ((size_t)nb + 1) * 4, st));
+    RC(g_tp.begin(probes->device, true, st));
+    cudaError_t e = launch_seed_index(targets->view(), core_len, d_cnt, d_off, d_cur, d_pos, d_sig, d_temp, temp_bytes, st);
+    if (e == cudaSuccess)
+        e = launch_seed_query(probes->view(), crick ? probes->rc_view() : probes->view(), targets->view(), K, core_len,
+                              d_off, d_pos, d_sig, q_begin, q_end, clamp, crick, targets->has_non_acgt != 0, d_best, st);
+    if (e == cudaSuccess) e = g_tp.end(st);
+    cudaFreeAsync(d_temp, st);
+    cudaFreeAsync(d_idx, st);
+    if (e != cudaSuccess) return fail(cuda_code(e), "seed engine launch: %s", cudaGetErrorString(e));
+    if (launches) *launches = nl + 4;
+    return K4B_OK;
+}
+
 // minima -> uint16 with the targeted rules applied (cap at clamp, > 4 wildcards -> 0)
 extern "C" int k4b_targeted_finalize_device(k4b_packed *probes, const uint32_t *d_best, uint32_t clamp,
                                             uint16_t *d_out_min, void *stream) {
@@ -1144,22 +1201,35 @@ static int run_exhaustive_diag(const uint8_t *concat, uint32_t len, uint32_t K, 
 
 // probes-vs-assembly on the band engine over all devices (diagonals partitioned, one
 // ncclAllReduce(min) at the end)
-static int run_targeted_diag(const uint8_t *t_concat, uint32_t t_len, const uint8_t *q_concat, uint32_t q_len,
-                             uint32_t K, int both, uint32_t clamp, uint8_t *out_h) {
+// Whole-probe-set targeted run on the seed-and-verify engine (pure-ACGT probes, cores of at
+// least 6 bases) or on the band engine; *used = 0 when neither applies (caller falls back to the
+// POPC engine).  Devices split the probes (seed) or the diagonals (bands); minima meet in one
+// ncclAllReduce(min).
+static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8_t *q_concat, uint32_t q_len,
+                            uint32_t K, int both, uint32_t clamp, uint32_t core_len, bool allow_seed,
+                            bool allow_diag, uint8_t *out_h, int *used) {
+    *used = 0;
     RC(ensure_init());
     const int n = (int)g_eng.devs.size();
     PhaseTrace trace;
     std::vector<k4b_packed *> qs, ts;
     std::vector<uint32_t *> bests(n, nullptr);
     uint16_t *d_out = nullptr, *h_out = nullptr;
+    bool use_seed = false;
     int rc = 0;
     do {
         CU(cudaSetDevice(g_eng.devs[0]));
         k4b_packed *q0 = nullptr, *t0 = nullptr;
         if ((rc = k4b_pack_host(q_concat, q_len, K, &q0))) break;
         qs.push_back(q0);
+        // a core of c bases occurs in ~len/4^c places: below 6 bases verifying every occurrence costs
+        // as much as the bit-sliced bands
+        const bool seed = allow_seed && !q0->has_non_acgt && core_len >= 6 && clamp <= K / core_len;
+        if (!seed && !allow_diag) break;  // *used stays 0: the caller runs the POPC engine
+        *used = 1;
         if ((rc = k4b_pack_host(t_concat, t_len, K, &t0))) break;
         ts.push_back(t0);
+        use_seed = seed;
         if (n > 1) {
             qs.clear();
             ts.clear();
@@ -1172,6 +1242,15 @@ static int run_targeted_diag(const uint8_t *t_concat, uint32_t t_len, const uint
             }
         }
         trace.mark("H2D + pack (+bcast)");
+        {   // result buffers first: synchronous allocations behind queued work stall the host
+            cudaError_t e = cudaSetDevice(g_eng.devs[0]);
+            if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)q_len * 2);
+            if (e == cudaSuccess) e = cudaMallocHost(&h_out, (size_t)q_len * 2);
+            if (e != cudaSuccess) {
+                rc = fail(cuda_code(e), "result buffers: %s", cudaGetErrorString(e));
+                break;
+            }
+        }
         for (int i = 0; i < n && !rc; ++i) {
             cudaError_t e = cudaSetDevice(g_eng.devs[i]);
             if (e == cudaSuccess) e = cudaMalloc(&bests[i], (size_t)q_len * 4);
@@ -1180,9 +1259,22 @@ static int run_targeted_diag(const uint8_t *t_concat, uint32_t t_len, const uint
                 break;
             }
             rc = k4b_best_init_device(bests[i], q_len, K, g_eng.streams[i]);
-            if (!rc) rc = k4b_targeted_diag_device(qs[i], ts[i], both, clamp, (uint32_t)i, (uint32_t)n, bests[i], g_eng.streams[i], nullptr);
+            if (rc) break;
+            if (use_seed)
+                rc = k4b_targeted_seed_device(qs[i], ts[i], both, clamp, core_len, (uint32_t)((uint64_t)q_len * i / n),
+                                              (uint32_t)((uint64_t)q_len * (i + 1) / n), bests[i], g_eng.streams[i], nullptr);
+            else
+                rc = k4b_targeted_diag_device(qs[i], ts[i], both, clamp, (uint32_t)i, (uint32_t)n, bests[i], g_eng.streams[i], nullptr);
         }
         if (rc) break;
+        trace.mark("alloc + enqueue");
+        if (trace.on) {  // attribute the engine time (tracing only: adds a synchronisation)
+            for (int i = 0; i < n; ++i) {
+                cudaSetDevice(g_eng.devs[i]);
+                cudaStreamSynchronize(g_eng.streams[i]);
+            }
+            trace.mark("engine kernels");
+        }
         if (n > 1) {
             int nr = g_eng.nccl.GroupStart();
             for (int i = 0; i < n && !nr; ++i)
@@ -1194,21 +1286,16 @@ static int run_targeted_diag(const uint8_t *t_concat, uint32_t t_len, const uint
             }
         }
         cudaError_t e = cudaSetDevice(g_eng.devs[0]);
-        if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)q_len * 2);
-        if (e == cudaSuccess) e = cudaMallocHost(&h_out, (size_t)q_len * 2);
-        if (e != cudaSuccess) {
-            rc = fail(cuda_code(e), "result buffers: %s", cudaGetErrorString(e));
-            break;
-        }
         if ((rc = k4b_targeted_finalize_device(qs[0], bests[0], clamp, d_out, g_eng.streams[0]))) break;
-        e = cudaMemcpyAsync(h_out, d_out, (size_t)q_len * 2, cudaMemcpyDeviceToHost, g_eng.streams[0]);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(h_out, d_out, (size_t)q_len * 2, cudaMemcpyDeviceToHost, g_eng.streams[0]);
         for (int i = 0; i < n; ++i) {
             cudaSetDevice(g_eng.devs[i]);
             const cudaError_t e2 = cudaStreamSynchronize(g_eng.streams[i]);
             if (e2 != cudaSuccess && e == cudaSuccess) e = e2;
         }
         if (e != cudaSuccess) {
-            rc = fail(cuda_code(e), "targeted band engine: %s", cudaGetErrorString(e));
+            rc = fail(cuda_code(e), "targeted %s engine: %s", use_seed ? "seed" : "band", cudaGetErrorString(e));
             break;
         }
         trace.mark("kernels + D2H");
@@ -1312,9 +1399,13 @@ extern "C" int k4b_hamm_targeted(const uint8_t *target_concat, uint64_t target_l
         const int eng = engine_setting();
         const bool whole = q_begin == 0 && q_end == probe_len;
         const bool big = (uint64_t)probe_len * target_len >= (1ull << 32);
-        if (whole && eng != 1 && (eng == 2 || big))
-            return run_targeted_diag(target_concat, (uint32_t)target_len, probe_concat, probe_len, K,
-                                     both_strands, notfound, out_h);
+        if (whole && eng != 1) {
+            int used = 0;
+            const int rc = run_targeted_big(target_concat, (uint32_t)target_len, probe_concat, probe_len, K, both_strands,
+                                            notfound, core, eng == 0 || eng == 3, eng == 2 || (eng != 1 && big), out_h,
+                                            &used);
+            if (used || rc) return rc;
+        }
     }
     return run_sharded(probe_concat, probe_len, target_concat, (uint32_t)target_len, K,
                        both_strands, 0, q_begin, q_end, notfound, 1, SweepRange(),

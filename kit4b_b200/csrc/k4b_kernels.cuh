@@ -126,6 +126,17 @@ cudaError_t launch_allpairs_generic(const AllPairsParams &p, bool three_planes, 
 // rc.base: logical word 0 of a 3-array allocation with q's stride and pads
 cudaError_t launch_revcomp_planes(ImageView q, ImageView rc, cudaStream_t st);
 int queries_per_thread(uint32_t W, bool three_planes);
+
+// seed-and-verify engine for the targeted mode (k4b_seed.cu)
+uint32_t seed_bucket_bits(uint32_t core_len);
+size_t seed_scan_temp_bytes(uint32_t n_buckets);
+cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t *d_cnt, uint32_t *d_off,
+                              uint32_t *d_cursor, uint32_t *d_pos, uint2 *d_sig, void *d_temp, size_t temp_bytes,
+                              cudaStream_t st);
+cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t K, uint32_t core_len,
+                              const uint32_t *d_off, const uint32_t *d_pos, const uint2 *d_sig, uint32_t q_begin,
+                              uint32_t q_end, uint32_t clamp, bool crick, bool three, uint32_t *d_best,
+                              cudaStream_t st);
 cudaError_t launch_microbench(int which, int iters, uint32_t *d_sink, int *blocks, int *threads,
                               int *ops_per_thread_iter, cudaStream_t st);
 

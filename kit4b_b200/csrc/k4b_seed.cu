@@ -1,0 +1,219 @@
+// k4b_seed.cu - seed-and-verify engine for the targeted mode (-m0 -I) on sm_100a.
+//
+// The reference answers a probe K-mer with min(true minimum, "not found") where "not found" =
+// K / CoreLen, CoreLen = K / (R+1) (libkit4b/SfxArray.cpp:4462-4463), and finds the hits by the
+// pigeonhole principle: a hit with fewer than K/CoreLen mismatches leaves at least one of the
+// K/CoreLen disjoint cores of the probe intact, so it is enough to look up every core exactly
+// (suffix-array runs, :4480-4527) and to verify the full K bases of each occurrence (:4567-4581).
+// Same idea here, without the suffix array and without the reference's depth cut-offs:
+//   * index: every target position whose CoreLen window is pure ACGT is bucketed by the code (or a
+//     hash, for long cores) of that window - count, exclusive scan, fill (three streaming passes
+//     over the packed planes, HBM-bound);
+//     every entry carries the 16 bases before and the 16 bases after the core as a signature;
+//   * query: one warp per (probe K-mer, strand, core): the lanes walk the bucket of the core
+//     (12 coalesced bytes per occurrence); the mismatches between the signature and the probe's
+//     own flanks are a lower bound of the distance, so almost every unrelated occurrence is
+//     dismissed without touching the target planes; the survivors are verified over the full K
+//     bases (target K-mer cut out of the planes, XOR / OR / POPC); the running minimum of the
+//     probe is lowered with one atomicMin.
+// Exact for every distance below the "not found" value, which is all the output can show;
+// buckets that hold unrelated cores (hash collisions) only cost extra verifications.
+// Probes must be pure ACGT (wildcard probes need the reference's substitution rule, :4266-4296;
+// they stay on the brute-force engines); target N / InDel count as mismatches, windows across an
+// entry boundary are rejected through the valid-start plane.
+#include "k4b_kernels.cuh"
+
+#include <algorithm>
+
+#include <cub/device/device_scan.cuh>
+
+namespace k4b {
+
+constexpr uint32_t kSeedMaxBits = 22;  // at most 4 M buckets
+
+// bits [pos, pos+32) of a plane; pos may be slightly negative (front pad) or run past the end
+// (back pad): both pads are part of every image
+__device__ __forceinline__ uint32_t plane_bits(const uint32_t *pl, long long pos) {
+    const long long wi = pos >> 5;  // floor
+    const uint32_t sh = (uint32_t)(pos & 31);
+    return __funnelshift_r(__ldg(pl + wi), __ldg(pl + wi + 1), sh);
+}
+
+// bucket of the core starting at pos; ok = the window is pure ACGT (plane 2 clear; EOS and the
+// pads have it set).  core_len <= 11 with bits == 2*core_len: the code itself, else a hash.
+__device__ __forceinline__ uint32_t core_bucket(const ImageView &img, long long pos, uint32_t core_len,
+                                                uint32_t bits, bool &ok) {
+    uint32_t h = 0x9e3779b9u, bad = 0, key = 0;
+    for (uint32_t o = 0; o < core_len; o += 32) {
+        const uint32_t n = core_len - o < 32 ? core_len - o : 32;
+        const uint32_t m = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
+        const uint32_t w0 = plane_bits(img.plane(0), pos + o) & m;
+        const uint32_t w1 = plane_bits(img.plane(1), pos + o) & m;
+        bad |= plane_bits(img.plane(2), pos + o) & m;
+        key = w0 | (w1 << (core_len & 31));  // used only when core_len <= 11
+        h = (h ^ w0) * 0x85ebca6bu;
+        h ^= h >> 13;
+        h = (h ^ w1) * 0xc2b2ae35u;
+        h ^= h >> 16;
+    }
+    ok = bad == 0;
+    return (2 * core_len == bits) ? key : (h & ((1u << bits) - 1u));
+}
+
+__global__ void __launch_bounds__(256) seed_count_kernel(ImageView t, uint32_t n_pos, uint32_t core_len,
+                                                         uint32_t bits, uint32_t *__restrict__ cnt) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pos) return;
+    bool ok;
+    const uint32_t b = core_bucket(t, p, core_len, bits, ok);
+    if (ok) atomicAdd(cnt + b, 1u);
+}
+
+// 16 bases starting at pos as (plane-0 bits | plane-1 bits << 16); planes 0/1 only: a non-ACGT
+// symbol then looks like a base, which can only LOWER the mismatch count taken from it
+__device__ __forceinline__ uint32_t flank16(const ImageView &img, long long pos) {
+    const uint32_t w0 = plane_bits(img.plane(0), pos) & 0xffffu;
+    const uint32_t w1 = plane_bits(img.plane(1), pos) & 0xffffu;
+    return w0 | (w1 << 16);
+}
+
+__global__ void __launch_bounds__(256) seed_fill_kernel(ImageView t, uint32_t n_pos, uint32_t core_len,
+                                                        uint32_t bits, uint32_t *__restrict__ cursor,
+                                                        uint32_t *__restrict__ pos, uint2 *__restrict__ sig) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pos) return;
+    bool ok;
+    const uint32_t b = core_bucket(t, p, core_len, bits, ok);
+    if (!ok) return;
+    const uint32_t slot = atomicAdd(cursor + b, 1u);
+    pos[slot] = p;
+    // x = the 16 bases before the core (the front pad makes p < 16 readable), y = the 16 after it
+    sig[slot] = make_uint2(flank16(t, (long long)p - 16), flank16(t, (long long)p + core_len));
+}
+
+// mismatches between the K-mer of `a` at pa and the K-mer of `b` at pb (b may hold non-ACGT
+// symbols, a is pure ACGT inside the window); stops counting once `limit` is reached
+__device__ __forceinline__ uint32_t kmer_mismatches(const ImageView &a, long long pa, const ImageView &b,
+                                                    long long pb, uint32_t K, bool three, uint32_t limit) {
+    uint32_t d = 0;
+    for (uint32_t o = 0; o < K && d < limit; o += 32) {
+        uint32_t m = plane_bits(a.plane(0), pa + o) ^ plane_bits(b.plane(0), pb + o);
+        m |= plane_bits(a.plane(1), pa + o) ^ plane_bits(b.plane(1), pb + o);
+        if (three) m |= plane_bits(b.plane(2), pb + o);
+        if (K - o < 32) m &= (1u << (K - o)) - 1u;
+        d += __popc(m);
+    }
+    return d;
+}
+
+// one warp per (probe position, strand, core)
+__global__ void __launch_bounds__(256) seed_query_kernel(ImageView q, ImageView rcq, ImageView t, uint32_t K,
+                                                         uint32_t core_len, uint32_t n_cores, uint32_t bits,
+                                                         const uint32_t *__restrict__ off,
+                                                         const uint32_t *__restrict__ pos,
+                                                         const uint2 *__restrict__ sig, uint32_t q_begin,
+                                                         uint32_t q_end, uint32_t clamp, int strands, int three,
+                                                         uint32_t *__restrict__ best) {
+    const unsigned long long warp_id = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t per_probe = (uint32_t)strands * n_cores;
+    const unsigned long long pi = warp_id / per_probe;
+    if (pi >= (unsigned long long)(q_end - q_begin)) return;
+    const uint32_t p = q_begin + (uint32_t)pi;
+    if (!((q.valid()[p >> 5] >> (p & 31)) & 1u)) return;  // no K-mer of one entry starts here
+    const uint32_t sub = (uint32_t)(warp_id - pi * per_probe);
+    const uint32_t strand = sub / n_cores, c = sub - strand * n_cores;
+    // the reverse complement of the K-mer at p is the K-mer at len-K-p of the reverse-complemented planes
+    const ImageView &img = strand ? rcq : q;
+    const long long pp = strand ? (long long)q.len - K - p : p;
+    uint32_t cur = __ldg(best + p);  // running minimum so far (other cores / strands / launches)
+    if (cur > clamp) cur = clamp;    // only distances below the "not found" value matter
+    if (cur == 0) return;
+    bool ok;
+    const uint32_t b = core_bucket(img, pp + (long long)c * core_len, core_len, bits, ok);
+    if (!ok) return;  // cannot happen for pure-ACGT probes; kept for safety
+    const uint32_t lo = __ldg(off + b), hi = __ldg(off + b + 1);
+    const long long Mt = (long long)t.len - K;
+    const long long shift = (long long)c * core_len;
+    // the probe's own flanks of this core, cut to what lies inside the K-mer: nl bases before the
+    // core, nr bases after it
+    const uint32_t nl = shift < 16 ? (uint32_t)shift : 16u;
+    const uint32_t after = K - (uint32_t)shift - core_len;
+    const uint32_t nr = after < 16 ? after : 16u;
+    const uint32_t ql = flank16(img, pp + shift - 16), qr = flank16(img, pp + shift + core_len);
+    const uint32_t ml = nl ? (0xffffu << (16 - nl)) & 0xffffu : 0u;  // the LAST nl of the 16 bases before the core
+    const uint32_t mr = nr == 16 ? 0xffffu : ((1u << nr) - 1u);      // the FIRST nr of the 16 bases after it
+    uint32_t mine = cur;
+    for (uint32_t i = lo + lane; i < hi && mine; i += 32) {
+        const uint2 sg = __ldg(sig + i);
+        const uint32_t xl = sg.x ^ ql, xr = sg.y ^ qr;
+        const uint32_t lb = __popc((xl | (xl >> 16)) & ml) + __popc((xr | (xr >> 16)) & mr);
+        if (lb >= mine) continue;  // already as far as the best hit so far: no need to look at the target
+        const long long ts = (long long)__ldg(pos + i) - shift;
+        if (ts < 0 || ts > Mt) continue;
+        const uint32_t d = kmer_mismatches(img, pp, t, ts, K, three != 0, mine);
+        // windows across an entry boundary are no K-mers: checked only for the rare improvement
+        if (d < mine && ((t.valid()[ts >> 5] >> (ts & 31)) & 1u)) mine = d;
+    }
+    mine = __reduce_min_sync(0xffffffffu, mine);
+    if (lane == 0 && mine < cur) atomicMin(best + p, mine);
+}
+
+uint32_t seed_bucket_bits(uint32_t core_len) {
+    return 2 * core_len < kSeedMaxBits ? 2 * core_len : kSeedMaxBits;
+}
+
+size_t seed_scan_temp_bytes(uint32_t n_buckets) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n_buckets + 1);
+    return bytes;
+}
+
+// d_cnt: n_buckets+1 counters (zeroed by the caller), turned into bucket offsets d_off
+// (n_buckets+1 entries, d_off[n_buckets] = number of indexed cores); d_cursor: n_buckets+1
+// scratch; d_pos, d_sig: t.len entries
+cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t *d_cnt, uint32_t *d_off,
+                              uint32_t *d_cursor, uint32_t *d_pos, uint2 *d_sig, void *d_temp, size_t temp_bytes,
+                              cudaStream_t st) {
+    if (t.len < core_len) return cudaSuccess;
+    const uint32_t bits = seed_bucket_bits(core_len), nb = 1u << bits;
+    const uint32_t n_pos = t.len - core_len + 1;
+    const uint32_t grid = (n_pos + 255) / 256;
+    seed_count_kernel<<<grid, 256, 0, st>>>(t, n_pos, core_len, bits, d_cnt);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_cnt, d_off, (int)nb + 1, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(d_cursor, d_off, ((size_t)nb + 1) * 4, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return e;
+    seed_fill_kernel<<<grid, 256, 0, st>>>(t, n_pos, core_len, bits, d_cursor, d_pos, d_sig);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t K, uint32_t core_len,
+                              const uint32_t *d_off, const uint32_t *d_pos, const uint2 *d_sig, uint32_t q_begin,
+                              uint32_t q_end, uint32_t clamp, bool crick, bool three, uint32_t *d_best,
+                              cudaStream_t st) {
+    if (q_begin >= q_end || t.len < K || q.len < K) return cudaSuccess;
+    const uint32_t n_cores = K / core_len;
+    const uint32_t strands = crick ? 2u : 1u;
+    const unsigned long long warps = (unsigned long long)(q_end - q_begin) * strands * n_cores;
+    // 1-D grids hold 2^31-1 CTAs of 8 warps: split the probe range if needed
+    const unsigned long long max_warps = 0x7fffffffull * 8ull;
+    const uint32_t per_probe = strands * n_cores;
+    const uint32_t max_probes = (uint32_t)std::min<unsigned long long>(0xffffffffull, max_warps / per_probe);
+    (void)warps;
+    for (uint32_t b = q_begin; b < q_end;) {
+        const uint32_t e = (q_end - b > max_probes) ? b + max_probes : q_end;
+        const unsigned long long w = (unsigned long long)(e - b) * per_probe;
+        const unsigned grid = (unsigned)((w + 7) / 8);
+        seed_query_kernel<<<grid, 256, 0, st>>>(q, rcq, t, K, core_len, n_cores, seed_bucket_bits(core_len), d_off,
+                                                d_pos, d_sig, b, e, clamp, (int)strands, three ? 1 : 0, d_best);
+        const cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+        b = e;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace k4b

@@ -74,6 +74,8 @@ SIGNATURES = {
                                              ctypes.c_uint32, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
     "k4b_targeted_diag_device": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32,
                                                 ctypes.c_uint32, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
+    "k4b_targeted_seed_device": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                                ctypes.c_uint32, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
     "k4b_targeted_finalize_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, _vp]),
     "k4b_diag_bootstrap_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
     "k4b_diag_bands_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp,
@@ -235,7 +237,7 @@ def allpairs_min_device(queries: Packed, targets: Packed, both_strands: bool, se
     return n.value
 
 
-ENGINE_AUTO, ENGINE_POPC, ENGINE_DIAG = 0, 1, 2
+ENGINE_AUTO, ENGINE_POPC, ENGINE_DIAG, ENGINE_SEED = 0, 1, 2, 3
 
 
 def set_engine(engine: int) -> None:
@@ -291,6 +293,14 @@ def targeted_diag_device(probes: Packed, targets: Packed, both_strands: bool, cl
     n = ctypes.c_int(0)
     _check(load_lib().k4b_targeted_diag_device(probes.handle, targets.handle, int(both_strands), clamp, part, nparts,
                                                _vp(d_best_ptr), _vp(stream), ctypes.byref(n)))
+    return n.value
+
+
+def targeted_seed_device(probes: Packed, targets: Packed, both_strands: bool, clamp: int, core_len: int, q_begin: int,
+                         q_end: int, d_best_ptr: int, stream: int = 0) -> int:
+    n = ctypes.c_int(0)
+    _check(load_lib().k4b_targeted_seed_device(probes.handle, targets.handle, int(both_strands), clamp, core_len,
+                                               q_begin, q_end, _vp(d_best_ptr), _vp(stream), ctypes.byref(n)))
     return n.value
 
 

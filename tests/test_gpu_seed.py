@@ -1,0 +1,127 @@
+"""GPU parity tests of the seed-and-verify engine for the targeted mode (k4b_seed.cu): reference
+golden files, the oracle on seeded inputs (short and hashed cores, K > 128, targets with N,
+entry boundaries) and the band engine at a size the CPU oracle cannot reach."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_manifest, random_genome
+
+import kit4b_b200 as k4b
+from kit4b_b200 import hamm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _engine():
+    k4b.gpu_init(1)
+    k4b.set_engine(hamm.ENGINE_SEED)
+    yield
+    k4b.set_engine(hamm.ENGINE_AUTO)
+    k4b.gpu_shutdown()
+
+
+def _targeted_runs():
+    m = golden_manifest()["__targeted__"]
+    return [(m, r) for r in m["runs"]]
+
+
+@pytest.mark.parametrize("mr", _targeted_runs(), ids=lambda mr: mr[1]["out"])
+def test_seed_engine_targeted_equals_reference_files(oracle, mr):
+    """-m0 -I: reference outputs (probes with N fall back to the brute-force engines)."""
+    m, r = mr
+    _, tseq = oracle.read_sfx(os.path.join(GOLDEN, m["sfx"]))
+    concat, chroms, _ = oracle.concat_entries(oracle.read_bioseq(os.path.join(GOLDEN, m["probes"][r["probes"]]["bioseq"])))
+    got = k4b.targeted(tseq, concat, r["K"], r["R"], r["both"])
+    rep = oracle.restricted_report(chroms, r["K"], r["R"], oracle.restricted_per_loci(chroms, got), r["fmt"], out_name=r["out"])
+    assert rep == open(os.path.join(GOLDEN, r["out"]), "rb").read()
+
+
+def _planted(seed, tlens, alpha_t=4):
+    """targets + pure-ACGT probes made of mutated copies (forward and reverse complement), a
+    piece that spans an entry boundary, and unrelated sequence"""
+    rng = np.random.default_rng(seed)
+    cpl = np.array([3, 2, 1, 0, 4, 5, 6, 7], np.uint8)
+    target = random_genome(seed + 1, tlens, alpha_t).copy()
+    acgt = np.flatnonzero(target < 4)
+    parts = []
+    for start, nmut, rc in [(300, 0, False), (900, 2, False), (1500, 5, True), (2100, 9, False), (2700, 1, True)]:
+        seg = target[start:start + 400].copy()
+        seg = seg[seg < 4]
+        idx = rng.choice(len(seg), size=min(nmut * 3, len(seg)), replace=False)
+        seg[idx] = (seg[idx] + 1 + rng.integers(0, 3, size=len(idx))) % 4
+        parts += [cpl[seg[::-1]] if rc else seg, np.array([7], np.uint8)]
+    b = tlens[0]  # first entry boundary (an EOS sits at index tlens[0])
+    span = target[b - 150:b + 150]
+    parts += [span[span < 4], np.array([7], np.uint8), rng.integers(0, 4, size=500, dtype=np.uint8)]
+    assert len(acgt)
+    return np.ascontiguousarray(target), np.ascontiguousarray(np.concatenate(parts), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("K,R,both", [(32, 3, True), (25, 2, False), (48, 5, True), (64, 1, True), (100, 4, True),
+                                      (140, 9, True), (300, 2, False), (20, 1, True), (24, 3, True), (500, 10, True)])
+def test_seed_engine_matches_oracle(oracle, K, R, both):
+    """cores of 6..250 bases: direct codes (<= 11), hashed buckets, multi-word cores"""
+    target, probes = _planted(4000 + K, [6000, 3000, 2500])
+    assert np.array_equal(k4b.targeted(target, probes, K, R, both), oracle.targeted_brute(target, probes, K, R, both))
+
+
+def test_seed_engine_targets_with_non_acgt(oracle):
+    target, probes = _planted(4100, [5000, 4000], alpha_t=5)  # N in the targets, probes stay ACGT
+    target[1000:1010] = 4
+    target[2200] = 6
+    for K, R, both in [(32, 3, True), (40, 2, True), (70, 4, False)]:
+        assert np.array_equal(k4b.targeted(target, probes, K, R, both), oracle.targeted_brute(target, probes, K, R, both)), (K, R)
+
+
+def test_seed_engine_device_api_ranges_combine(oracle):
+    """k4b_targeted_seed_device on probe sub-ranges into one minima array == the host entry point"""
+    import torch
+    target, probes = _planted(4200, [7000, 2000])
+    K, R, both = 32, 3, True
+    core = K // (R + 1)
+    clamp = K // core
+    t = hamm.Packed.from_host(target, K)
+    q = hamm.Packed.from_host(probes, K)
+    try:
+        L = len(probes)
+        best = torch.empty(L, dtype=torch.int32, device="cuda")
+        hamm.best_init_device(best.data_ptr(), L, K)
+        for b, e in [(0, 700), (700, 701), (701, L)]:
+            assert hamm.targeted_seed_device(q, t, both, clamp, core, b, e, best.data_ptr()) > 0
+        out = torch.empty(L, dtype=torch.int16, device="cuda")
+        hamm.targeted_finalize_device(q, best.data_ptr(), clamp, out.data_ptr())
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().view(np.uint16)
+        want = oracle.targeted_brute(target, probes, K, R, both)
+        valid = want != 0xFF
+        assert np.array_equal(got[valid].astype(np.uint8), want[valid])
+        with pytest.raises(Exception):  # the pigeonhole bound needs clamp <= K / core_len
+            hamm.targeted_seed_device(q, t, both, clamp + 1, core, 0, L, best.data_ptr())
+    finally:
+        t.free()
+        q.free()
+
+
+def test_seed_engine_equals_band_engine_at_scale():
+    rng = np.random.default_rng(87)
+    target = random_genome(88, [3000000, 1000000])
+    parts = []
+    for start, nmut in [(1000, 0), (200000, 3), (900000, 10), (3100000, 25), (2500000, 40)]:
+        seg = target[start:start + 3000].copy()
+        idx = rng.choice(3000, size=nmut * 10, replace=False)
+        seg[idx] = (seg[idx] + 1 + rng.integers(0, 3, size=len(idx))) % 4
+        parts += [seg, np.array([7], np.uint8)]
+    parts.append(rng.integers(0, 4, size=30000, dtype=np.uint8))
+    probes = np.ascontiguousarray(np.concatenate(parts), dtype=np.uint8)
+    for K, R in [(32, 3), (50, 5), (96, 2)]:
+        got = k4b.targeted(target, probes, K, R, True)
+        k4b.set_engine(hamm.ENGINE_DIAG)
+        try:
+            want = k4b.targeted(target, probes, K, R, True)
+        finally:
+            k4b.set_engine(hamm.ENGINE_SEED)
+        assert np.array_equal(got, want), (K, R)
+        assert (got[:2900] == 0).all()
