@@ -195,8 +195,9 @@ int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets, int both_s
 /* Targeted by seed-and-verify (the reference's pigeonhole search, SfxArray.cpp:4462-4581, without
  * its depth cut-offs): every core of core_len bases of a probe K-mer is looked up exactly in a
  * bucket index of the target's cores and each occurrence is verified over the full K bases.
- * Exact for distances < clamp, which needs clamp <= K/core_len; probes must be pure ACGT (else
- * K4B_ERR_UNSUPPORTED).  Probe K-mers starting in [q_begin, q_end); d_best as above. */
+ * Exact for distances < clamp, which needs clamp <= K/core_len.  Probe K-mers that hold N / InDel
+ * (wildcards) are skipped - k4b_hamm_targeted answers those with k4b_allpairs_min_device.  Probe
+ * K-mers starting in [q_begin, q_end); d_best as above. */
 int k4b_targeted_seed_device(k4b_packed *probes, k4b_packed *targets, int both_strands, uint32_t clamp,
                              uint32_t core_len, uint32_t q_begin, uint32_t q_end, uint32_t *d_best,
                              void *stream, int *launches);

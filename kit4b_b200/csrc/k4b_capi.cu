@@ -855,8 +855,9 @@ extern "C" int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets,
 
 // Targeted (probes vs assembly) by seed-and-verify (k4b_seed.cu): exact for every distance below
 // clamp, the "not found" value, as long as clamp <= K / core_len (pigeonhole over the disjoint
-// cores); probes must be pure ACGT.  Handles the probe K-mers starting in [q_begin, q_end);
-// ranges combine by element-wise minimum of d_best.
+// cores).  Probe K-mers holding N / InDel are skipped (d_best keeps its value): wildcard probes need
+// the reference's substitution rule and belong to the brute-force engines.  Handles the probe
+// K-mers starting in [q_begin, q_end); ranges combine by element-wise minimum of d_best.
 extern "C" int k4b_targeted_seed_device(k4b_packed *probes, k4b_packed *targets, int both_strands,
                                         uint32_t clamp, uint32_t core_len, uint32_t q_begin,
                                         uint32_t q_end, uint32_t *d_best, void *stream, int *launches) {
@@ -864,7 +865,6 @@ extern "C" int k4b_targeted_seed_device(k4b_packed *probes, k4b_packed *targets,
     if (!probes || !targets || !d_best) return fail(K4B_ERR_PARAMS, "NULL argument");
     if (probes->K != targets->K) return fail(K4B_ERR_PARAMS, "probe/target K differ");
     if (probes->device != targets->device) return fail(K4B_ERR_PARAMS, "images live on different devices");
-    if (probes->has_non_acgt) return fail(K4B_ERR_UNSUPPORTED, "seed engine needs pure-ACGT probes");
     const uint32_t K = probes->K;
     if (!core_len || core_len > K || !clamp || clamp > K / core_len)
         return fail(K4B_ERR_PARAMS, "core_len=%u clamp=%u: the pigeonhole bound needs clamp <= K/core_len", core_len, clamp);
@@ -889,7 +889,8 @@ extern "C" int k4b_targeted_seed_device(k4b_packed *probes, k4b_packed *targets,
     cudaError_t e = launch_seed_index(targets->view(), core_len, d_cnt, d_off, d_cur, d_pos, d_sig, d_temp, temp_bytes, st);
     if (e == cudaSuccess)
         e = launch_seed_query(probes->view(), crick ? probes->rc_view() : probes->view(), targets->view(), K, core_len,
-                              d_off, d_pos, d_sig, q_begin, q_end, clamp, crick, targets->has_non_acgt != 0, d_best, st);
+                              d_off, d_pos, d_sig, q_begin, q_end, clamp, crick, targets->has_non_acgt != 0,
+                              probes->has_non_acgt != 0, d_best, st);
     if (e == cudaSuccess) e = g_tp.end(st);
     cudaFreeAsync(d_temp, st);
     cudaFreeAsync(d_idx, st);
@@ -1224,7 +1225,24 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
         qs.push_back(q0);
         // a core of c bases occurs in ~len/4^c places: below 6 bases verifying every occurrence costs
         // as much as the bit-sliced bands
-        const bool seed = allow_seed && !q0->has_non_acgt && core_len >= 6 && clamp <= K / core_len;
+        bool seed = allow_seed && core_len >= 6 && clamp <= K / core_len;
+        // probe K-mers that hold N / InDel (wildcards, SfxArray.cpp:4266-4296) cannot be seeded: their
+        // positions are collected as intervals and answered by the POPC engine afterwards
+        std::vector<std::pair<uint32_t, uint32_t>> impure;
+        if (seed && q0->has_non_acgt) {
+            uint64_t total = 0;
+            uint32_t in_win = 0, run_b = 0;
+            bool open = false;
+            for (uint32_t p = 0; p < K - 1 && p < q_len; ++p) in_win += (q_concat[p] >= 4 && q_concat[p] < 7);
+            for (uint32_t p = 0; p + K <= q_len; ++p) {
+                in_win += (q_concat[p + K - 1] >= 4 && q_concat[p + K - 1] < 7);
+                if (in_win && !open) { open = true; run_b = p; }
+                if (!in_win && open) { open = false; impure.emplace_back(run_b, p); total += p - run_b; }
+                in_win -= (q_concat[p] >= 4 && q_concat[p] < 7);
+            }
+            if (open) { impure.emplace_back(run_b, q_len - K + 1); total += q_len - K + 1 - run_b; }
+            if (impure.size() > 4096 || total * 4 > q_len) seed = false;  // mostly wildcards: not worth it
+        }
         if (!seed && !allow_diag) break;  // *used stays 0: the caller runs the POPC engine
         *used = 1;
         if ((rc = k4b_pack_host(t_concat, t_len, K, &t0))) break;
@@ -1287,6 +1305,11 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
         }
         cudaError_t e = cudaSetDevice(g_eng.devs[0]);
         if ((rc = k4b_targeted_finalize_device(qs[0], bests[0], clamp, d_out, g_eng.streams[0]))) break;
+        if (use_seed)  // the wildcard probe K-mers the seed engine skipped
+            for (size_t k = 0; k < impure.size() && !rc; ++k)
+                rc = k4b_allpairs_min_device(qs[0], ts[0], both, 0, impure[k].first, impure[k].second, clamp,
+                                             d_out + impure[k].first, g_eng.streams[0], nullptr);
+        if (rc) break;
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(h_out, d_out, (size_t)q_len * 2, cudaMemcpyDeviceToHost, g_eng.streams[0]);
         for (int i = 0; i < n; ++i) {

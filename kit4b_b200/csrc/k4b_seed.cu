@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) seed_query_kernel(ImageView q, ImageView 
                                                          const uint32_t *__restrict__ pos,
                                                          const uint2 *__restrict__ sig, uint32_t q_begin,
                                                          uint32_t q_end, uint32_t clamp, int strands, int three,
-                                                         uint32_t *__restrict__ best) {
+                                                         int q_impure, uint32_t *__restrict__ best) {
     const unsigned long long warp_id = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t per_probe = (uint32_t)strands * n_cores;
@@ -121,6 +121,15 @@ __global__ void __launch_bounds__(256) seed_query_kernel(ImageView q, ImageView 
     if (pi >= (unsigned long long)(q_end - q_begin)) return;
     const uint32_t p = q_begin + (uint32_t)pi;
     if (!((q.valid()[p >> 5] >> (p & 31)) & 1u)) return;  // no K-mer of one entry starts here
+    if (q_impure) {  // probe K-mers holding N / InDel are left to the brute-force engines
+        uint32_t bad = 0;
+        for (uint32_t o = 0; o < K; o += 32) {
+            uint32_t w = plane_bits(q.plane(2), (long long)p + o);
+            if (K - o < 32) w &= (1u << (K - o)) - 1u;
+            bad |= w;
+        }
+        if (bad) return;
+    }
     const uint32_t sub = (uint32_t)(warp_id - pi * per_probe);
     const uint32_t strand = sub / n_cores, c = sub - strand * n_cores;
     // the reverse complement of the K-mer at p is the K-mer at len-K-p of the reverse-complemented planes
@@ -192,8 +201,8 @@ cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t *d_cnt, u
 
 cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t K, uint32_t core_len,
                               const uint32_t *d_off, const uint32_t *d_pos, const uint2 *d_sig, uint32_t q_begin,
-                              uint32_t q_end, uint32_t clamp, bool crick, bool three, uint32_t *d_best,
-                              cudaStream_t st) {
+                              uint32_t q_end, uint32_t clamp, bool crick, bool three, bool q_impure,
+                              uint32_t *d_best, cudaStream_t st) {
     if (q_begin >= q_end || t.len < K || q.len < K) return cudaSuccess;
     const uint32_t n_cores = K / core_len;
     const uint32_t strands = crick ? 2u : 1u;
@@ -208,7 +217,7 @@ cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t 
         const unsigned long long w = (unsigned long long)(e - b) * per_probe;
         const unsigned grid = (unsigned)((w + 7) / 8);
         seed_query_kernel<<<grid, 256, 0, st>>>(q, rcq, t, K, core_len, n_cores, seed_bucket_bits(core_len), d_off,
-                                                d_pos, d_sig, b, e, clamp, (int)strands, three ? 1 : 0, d_best);
+                                                d_pos, d_sig, b, e, clamp, (int)strands, three ? 1 : 0, q_impure ? 1 : 0, d_best);
         const cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) return err;
         b = e;

@@ -76,6 +76,20 @@ def test_seed_engine_targets_with_non_acgt(oracle):
         assert np.array_equal(k4b.targeted(target, probes, K, R, both), oracle.targeted_brute(target, probes, K, R, both)), (K, R)
 
 
+def test_seed_engine_probe_sets_with_wildcards(oracle):
+    """probe K-mers holding N / InDel are skipped by the seed kernel and answered by the POPC
+    engine on their position intervals (wildcard rule, > 4 wildcards -> 0)"""
+    target, probes = _planted(4300, [6000, 3000])
+    probes = probes.copy()
+    for p in (50, 130, 131, 700, 701, 702, 703, 704, 1200, len(probes) - 5):
+        if probes[p] != 7:
+            probes[p] = 4
+    probes[900] = 6
+    probes = np.ascontiguousarray(probes)
+    for K, R, both in [(32, 3, True), (25, 2, False), (64, 5, True)]:
+        assert np.array_equal(k4b.targeted(target, probes, K, R, both), oracle.targeted_brute(target, probes, K, R, both)), (K, R)
+
+
 def test_seed_engine_device_api_ranges_combine(oracle):
     """k4b_targeted_seed_device on probe sub-ranges into one minima array == the host entry point"""
     import torch
