@@ -69,6 +69,26 @@ def synth_genome(name):
     return np.ascontiguousarray(np.concatenate(parts)), chroms, K, both
 
 
+def synth_targeted(scale=1.0):
+    """BASELINE configs[3]: assembly of 20 x 25 Mbp (seed 41, every entry followed by
+    EOS as in the .sfx sequence area), probes = 1 Mbp copied from the assembly with 3 % substitutions
+    + 1 Mbp fresh random (seed 42); K=32, R=3, both strands."""
+    rng = np.random.default_rng(41)
+    nchr, clen = 20, int(25_000_000 * scale)
+    parts = []
+    for _ in range(nchr):
+        parts += [rng.integers(0, 4, size=clen, dtype=np.uint8), np.array([7], dtype=np.uint8)]
+    target = np.ascontiguousarray(np.concatenate(parts))
+    rng = np.random.default_rng(42)
+    pl = int(1_000_000 * scale)
+    src = int(3.3 * clen) + 12345
+    copy = target[src:src + pl].copy()
+    idx = rng.choice(pl, size=int(0.03 * pl), replace=False)
+    copy[idx] = (copy[idx] + 1 + rng.integers(0, 3, size=len(idx))) % 4
+    probes = np.ascontiguousarray(np.concatenate([copy, [7], rng.integers(0, 4, size=pl, dtype=np.uint8)]), dtype=np.uint8)
+    return target, probes, 32, 3, True, nchr * (clen - 32 + 1), 2 * (pl - 32 + 1)
+
+
 def valid_count(chroms, K, b=None, e=None):
     """number of valid K-mer starts (inside one chromosome) in flat range [b,e)"""
     tot = 0
@@ -411,6 +431,138 @@ def run_ours_bands(args):
     k4b.gpu_shutdown()
 
 
+def run_ours_targeted(args):
+    """--workload cfg4: targeted mode (-m0 -I) on the seed-and-verify engine.  One step = the WHOLE
+    job (bucket index of the assembly + every probe K-mer, both strands); N GPUs split the probes
+    (each builds the index from the broadcast planes; minima meet in one all_reduce MIN)."""
+    torch, dist, k4b, world, rank, local, dev = _setup(args)
+    from kit4b_b200 import hamm
+    from kit4b_b200.dist import CudaEngine, shard_bounds
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    target, probes, K, R, both, Nt, Nq = synth_targeted(args.scale)
+    core = K // (R + 1)
+    clamp = K // core
+    engine = CudaEngine(dev)
+    imgs = []
+    for concat in (target, probes):  # rank 0 packs, ONE broadcast of each packed set
+        if rank == 0:
+            image, packed, non_acgt = engine.pack(concat, K)
+            flag = torch.tensor([int(non_acgt)], dtype=torch.int64, device=dev)
+        else:
+            image = engine.empty_image(len(concat))
+            flag = torch.zeros(1, dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.broadcast(flag, src=0)
+            dist.broadcast(image, src=0)
+        if rank != 0:
+            packed = engine.adopt(image, len(concat), K, bool(flag.item()))
+        imgs.append((image, packed))
+    t_img, q_img = imgs[0][1], imgs[1][1]
+    torch.cuda.synchronize()
+    L = len(probes)
+    best = torch.empty(L, dtype=torch.int32, device=dev)
+    out = torch.empty(L, dtype=torch.int16, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    qb, qe = shard_bounds(0, L, world)[rank]
+
+    def step():
+        hamm.best_init_device(best.data_ptr(), L, K, stream.cuda_stream)
+        n = 1 + hamm.targeted_seed_device(q_img, t_img, both, clamp, core, qb, qe, best.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.all_reduce(best, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            hamm.targeted_finalize_device(q_img, best.data_ptr(), clamp, out.data_ptr(), stream.cuda_stream)
+            n += 1
+        return n
+
+    for i in range(args.warmup):
+        flush.fill_(i & 0xFF)
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches, k_ms = 0, []
+    ev0.record(stream)
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        launches += step() + 1
+        k_ms.append(hamm.last_kernel_ms())
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    cmps = float(Nq) * float(Nt) * 2.0
+    value = cmps * args.steps / (ms_max * 1e-3) / 1e9
+    checksum = int(out.to(torch.int64).sum().item()) if rank == 0 else 0
+
+    info = hamm.last_seed_info()
+    kms = float(np.mean(k_ms))
+    # algorithmic bytes of one step on this rank: query = 12 B per streamed bucket entry; index =
+    # planes read twice (2 x 3/8 B per base) + 12 B written per indexed core
+    alg_bytes = 12.0 * info["occurrences"] + 0.75 * len(target) + 12.0 * info["indexed_cores"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6552.3))
+    roofline = {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": alg_bytes / (kms * 1e-3) / 1e9 / peak, "traffic": _traffic("cfg4_seed"),
+                "kernel": "seed_query_kernel (+ seed_count/seed_fill index build) of one step on this rank",
+                "kernel_ms": kms, "kernel_share_of_step": kms * args.steps / ms if ms > 0 else None,
+                "bytes_model": "12 B per bucket entry streamed by the query kernel (%d entries) + index build: planes read "
+                               "twice, 12 B written per indexed core (%d cores)" % (info["occurrences"], info["indexed_cores"]),
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (driver-written copy bandwidth)" if peaks else
+                               "fallback 6552.3 GB/s (MEASURED_PEAKS.json absent)"}
+
+    e2e_steps = args.steps if args.e2e_steps is None else args.e2e_steps
+    e2e_val, e2e_ok = None, None
+    if e2e_steps and world == 1:
+        k4b.targeted(target, probes, K, R, both)  # warm-up of the host path
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            h = k4b.targeted(target, probes, K, R, both)
+        dt = time.perf_counter() - t0
+        e2e_val = cmps * e2e_steps / dt / 1e9
+        e2e_ok = int(h[h != 0xFF].astype(np.int64).sum()) == int(out.cpu().numpy().view(np.uint16)[h != 0xFF].astype(np.int64).sum())
+    if rank == 0:
+        line = {
+            "metric": "kmer_comparisons_per_sec", "value": value, "unit": "Gcmp/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / max(1, args.steps),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[3]: hammings -m0 -K32 -r3 -c -I probes: %d probe K-mers (1 Mbp mutated "
+                                   "copy + 1 Mbp random, x%.2f) vs a %d-base synthetic assembly (20 entries)" % (Nq, args.scale, len(target)),
+                       "K": K, "R": R, "both_strands": both, "probe_kmers": int(Nq), "target_kmers": int(Nt),
+                       "step": "the whole targeted job: index of the assembly + every probe K-mer (%.3g logical comparisons)" % cmps,
+                       "engine": "seed-and-verify (pigeonhole cores of %d bases, bucket index with flank signatures)" % core,
+                       "parallelism": "probe shards x%d + all_reduce(MIN)" % world,
+                       "l2": "256 MB flush write between timed steps", "result_checksum": checksum},
+            "roofline": roofline, "cpu_baseline": None,
+            "cpu_baseline_note": "the reference needs its suffix-array index for this mode; timed beside this engine by "
+                                 "tools/cfg4_reference.py (profiles/r01_cfg4_reference*.log)",
+            "e2e": {"value": e2e_val, "unit": "Gcmp/s", "h2d_bytes_per_step": int(len(target) + len(probes)),
+                    "d2h_bytes_per_step": int(2 * L), "steps": e2e_steps if world == 1 else 0,
+                    "result_checksum_equals_resident_run": e2e_ok, "api": "k4b_hamm_targeted (host buffers)"},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    k4b.gpu_shutdown()
+
+
 def run_ours_popc(args):
     """--engine popc: the XOR/fold/POPC all-pairs kernel alone.  A full pass takes minutes, so a
     step is one query batch per GPU against all targets (per-query work is uniform); weak scaling."""
@@ -560,7 +712,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg4"])
+    ap.add_argument("--scale", type=float, default=1.0, help="--workload cfg4: size factor of assembly and probes")
     ap.add_argument("--engine", default="bands", choices=["bands", "popc"],
                     help="bands: diagonal-band engine, step = whole job (default); popc: all-pairs POPC kernel, step = query batch")
     ap.add_argument("--batch", type=int, default=131072, help="--engine popc: query K-mers per GPU per step")
@@ -570,7 +723,13 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.workload == "cfg4":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "cfg4: the reference needs its suffix-array index; "
+                              "see tools/cfg4_reference.py"}))
+            return
+        run_ours_targeted(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.engine == "popc":
         run_ours_popc(args)

@@ -201,6 +201,9 @@ int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets, int both_s
 int k4b_targeted_seed_device(k4b_packed *probes, k4b_packed *targets, int both_strands, uint32_t clamp,
                              uint32_t core_len, uint32_t q_begin, uint32_t q_end, uint32_t *d_best,
                              void *stream, int *launches);
+/* Work of the most recent k4b_targeted_seed_device call of this thread: bucket entries streamed by
+ * the query kernel (12 bytes each) and cores held by the index.  Blocks until that call finished. */
+int k4b_last_seed_info(uint64_t *occurrences, uint64_t *indexed_cores);
 int k4b_targeted_finalize_device(k4b_packed *probes, const uint32_t *d_best, uint32_t clamp,
                                  uint16_t *d_out_min, void *stream);
 

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <future>
 
 #include "../../../include/k4b_hamm.h"
 #include "k4b_host.h"
@@ -62,6 +63,17 @@ static int touch_output(const std::string &path) {
 }
 
 // ---- exhaustive (-m1) ------------------------------------------------------------------------
+// The CUDA context of a B200 takes seconds to create: k4b_gpu_init runs on a helper thread while
+// the input files are read, and is joined right before the first engine call.
+static std::future<int> g_gpu_init;
+static std::string g_gpu_init_err;  // k4b_last_error() is per thread: copied by the helper thread
+static int gpu_ready() {
+    if (!g_gpu_init.valid()) return 0;
+    const int rc = g_gpu_init.get();
+    if (rc) logmsg(0, "Unable to initialise the GPU engine (%d): %s", rc, g_gpu_init_err.c_str());
+    return rc;
+}
+
 static int run_exhaustive(const Options &o) {
     std::vector<SeqEntry> entries;
     std::string title, err;
@@ -92,8 +104,10 @@ static int run_exhaustive(const Options &o) {
 
     const uint32_t flat = g.genome_len - 2;
     std::vector<uint16_t> hd(flat, (uint16_t)(K + 1));
+    if ((rc = gpu_ready())) return rc;
     logmsg(2, "Starting Hamming edit distance processing on %d GPU(s)", k4b_gpu_count());
     const auto t0 = std::chrono::steady_clock::now();
+    if ((rc = gpu_ready())) return rc;
     rc = k4b_hamm_exhaustive(g.concat.data(), flat, K, o.crick ? 1 : 0, ss, se, hd.data());
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc) {
@@ -155,6 +169,7 @@ static int run_restricted(const Options &o) {
         const uint32_t plen = (uint32_t)g.concat.size();
         flat.assign(plen, 0xff);
         const auto t0 = std::chrono::steady_clock::now();
+        if ((rc = gpu_ready())) return rc;
         rc = k4b_hamm_targeted(sfx.seq.data(), sfx.seq.size(), g.concat.data(), plen, K, o.rhamm, o.crick ? 1 : 0, 0,
                                plen, flat.data());
         secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -177,6 +192,7 @@ static int run_restricted(const Options &o) {
         const auto t0 = std::chrono::steady_clock::now();
         // -z (hammings.cpp:228) takes effect only here: with -I the reference passes entry 0 and
         // the filter never fires (hammings.cpp:1691-1694)
+        if ((rc = gpu_ready())) return rc;
         rc = k4b_hamm_targeted_z(sfx.seq.data(), sfx.seq.size(), K, o.rhamm, o.crick ? 1 : 0, o.intrainterboth, 0, 0,
                                  flat.data());
         secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -390,13 +406,15 @@ int main(int argc, char **argv) {
                   "depends on -T)");
         rc = kErrParams;
     } else {
-        rc = k4b_gpu_init(run.gpus, nullptr);
-        if (rc) {
-            logmsg(0, "Unable to initialise the GPU engine (%d): %s", rc, k4b_last_error());
-        } else {
-            rc = run.mode != 0 ? run_exhaustive(run) : run_restricted(run);
-            k4b_gpu_shutdown();
-        }
+        const int gpus = run.gpus;
+        g_gpu_init = std::async(std::launch::async, [gpus]() {
+            const int irc = k4b_gpu_init(gpus, nullptr);
+            if (irc) g_gpu_init_err = k4b_last_error();
+            return irc;
+        });
+        rc = run.mode != 0 ? run_exhaustive(run) : run_restricted(run);
+        if (g_gpu_init.valid()) g_gpu_init.get();  // an input error returned before the engine was needed
+        k4b_gpu_shutdown();
     }
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const int code = rc >= 0 ? 0 : 1;

@@ -853,6 +853,18 @@ extern "C" int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets,
     return K4B_OK;
 }
 
+// statistics of the most recent seed-engine call of this thread (pinned, copied on its stream)
+static thread_local unsigned long long *g_h_seed = nullptr;
+extern "C" int k4b_last_seed_info(uint64_t *occurrences, uint64_t *indexed_cores) {
+    if (!g_h_seed || !g_tp.used) return fail(K4B_ERR_PARAMS, "no seed-engine call recorded on this thread");
+    CU(cudaDeviceSynchronize());
+    uint64_t occ = 0;
+    for (int i = 0; i < kSeedOccSlots; ++i) occ += g_h_seed[i];
+    if (occurrences) *occurrences = occ;
+    if (indexed_cores) *indexed_cores = g_h_seed[kSeedOccSlots] & 0xffffffffull;
+    return K4B_OK;
+}
+
 // Targeted (probes vs assembly) by seed-and-verify (k4b_seed.cu): exact for every distance below
 // clamp, the "not found" value, as long as clamp <= K / core_len (pigeonhole over the disjoint
 // cores).  Probe K-mers holding N / InDel are skipped (d_best keeps its value): wildcard probes need
@@ -876,13 +888,15 @@ extern "C" int k4b_targeted_seed_device(k4b_packed *probes, k4b_packed *targets,
     RC(diag_prepare(probes, crick, st, &nl));  // reverse-complemented probe planes
     const uint32_t nb = 1u << seed_bucket_bits(core_len);
     const size_t temp_bytes = seed_scan_temp_bytes(nb);
-    uint32_t *d_idx = nullptr;  // sig (targets->len x 8 B) | pos (targets->len) | cnt | off | cursor (nb+1 each)
+    uint32_t *d_idx = nullptr;  // occ slots | sig (targets->len x 8 B) | pos (targets->len) | cnt | off | cursor (nb+1 each)
     void *d_temp = nullptr;
-    const size_t words = 3 * ((size_t)nb + 1) + 3 * (size_t)targets->len;
+    const size_t words = 2 * (size_t)kSeedOccSlots + 3 * ((size_t)nb + 1) + 3 * (size_t)targets->len;
     CU(cudaMallocAsync(&d_idx, words * 4, st));
     CU(cudaMallocAsync(&d_temp, temp_bytes ? temp_bytes : 4, st));
-    uint2 *d_sig = (uint2 *)d_idx;
-    uint32_t *d_pos = d_idx + 2 * (size_t)targets->len;
+    unsigned long long *d_occ = (unsigned long long *)d_idx;
+    CU(cudaMemsetAsync(d_occ, 0, kSeedOccSlots * 8, st));
+    uint2 *d_sig = (uint2 *)(d_idx + 2 * (size_t)kSeedOccSlots);
+    uint32_t *d_pos = d_idx + 2 * (size_t)kSeedOccSlots + 2 * (size_t)targets->len;
     uint32_t *d_cnt = d_pos + targets->len, *d_off = d_cnt + nb + 1, *d_cur = d_off + nb + 1;
     CU(cudaMemsetAsync(d_cnt, 0, ((size_t)nb + 1) * 4, st));
     RC(g_tp.begin(probes->device, true, st));
@@ -890,8 +904,12 @@ extern "C" int k4b_targeted_seed_device(k4b_packed *probes, k4b_packed *targets,
     if (e == cudaSuccess)
         e = launch_seed_query(probes->view(), crick ? probes->rc_view() : probes->view(), targets->view(), K, core_len,
                               d_off, d_pos, d_sig, q_begin, q_end, clamp, crick, targets->has_non_acgt != 0,
-                              probes->has_non_acgt != 0, d_best, st);
+                              probes->has_non_acgt != 0, d_best, d_occ, st);
     if (e == cudaSuccess) e = g_tp.end(st);
+    if (e == cudaSuccess && !g_h_seed) e = cudaMallocHost(&g_h_seed, (kSeedOccSlots + 1) * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(g_h_seed, d_occ, kSeedOccSlots * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)  // number of indexed cores = the last bucket offset
+        e = cudaMemcpyAsync(g_h_seed + kSeedOccSlots, d_off + nb, 4, cudaMemcpyDeviceToHost, st);
     cudaFreeAsync(d_temp, st);
     cudaFreeAsync(d_idx, st);
     if (e != cudaSuccess) return fail(cuda_code(e), "seed engine launch: %s", cudaGetErrorString(e));

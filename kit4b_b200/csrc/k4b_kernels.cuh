@@ -136,7 +136,8 @@ cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t *d_cnt, u
 cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t K, uint32_t core_len,
                               const uint32_t *d_off, const uint32_t *d_pos, const uint2 *d_sig, uint32_t q_begin,
                               uint32_t q_end, uint32_t clamp, bool crick, bool three, bool q_impure,
-                              uint32_t *d_best, cudaStream_t st);
+                              uint32_t *d_best, unsigned long long *d_occ, cudaStream_t st);
+constexpr int kSeedOccSlots = 1024;  // d_occ (nullable): bucket entries streamed, summed over these slots
 cudaError_t launch_microbench(int which, int iters, uint32_t *d_sink, int *blocks, int *threads,
                               int *ops_per_thread_iter, cudaStream_t st);
 

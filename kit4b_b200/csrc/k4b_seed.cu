@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(256) seed_query_kernel(ImageView q, ImageView 
                                                          const uint32_t *__restrict__ pos,
                                                          const uint2 *__restrict__ sig, uint32_t q_begin,
                                                          uint32_t q_end, uint32_t clamp, int strands, int three,
-                                                         int q_impure, uint32_t *__restrict__ best) {
+                                                         int q_impure, uint32_t *__restrict__ best,
+                                                         unsigned long long *__restrict__ occ) {
     const unsigned long long warp_id = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t per_probe = (uint32_t)strands * n_cores;
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(256) seed_query_kernel(ImageView q, ImageView 
     const uint32_t b = core_bucket(img, pp + (long long)c * core_len, core_len, bits, ok);
     if (!ok) return;  // cannot happen for pure-ACGT probes; kept for safety
     const uint32_t lo = __ldg(off + b), hi = __ldg(off + b + 1);
+    if (occ && lane == 0) atomicAdd(occ + (blockIdx.x & (kSeedOccSlots - 1)), (unsigned long long)(hi - lo));
     const long long Mt = (long long)t.len - K;
     const long long shift = (long long)c * core_len;
     // the probe's own flanks of this core, cut to what lies inside the K-mer: nl bases before the
@@ -202,7 +204,7 @@ cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t *d_cnt, u
 cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t K, uint32_t core_len,
                               const uint32_t *d_off, const uint32_t *d_pos, const uint2 *d_sig, uint32_t q_begin,
                               uint32_t q_end, uint32_t clamp, bool crick, bool three, bool q_impure,
-                              uint32_t *d_best, cudaStream_t st) {
+                              uint32_t *d_best, unsigned long long *d_occ, cudaStream_t st) {
     if (q_begin >= q_end || t.len < K || q.len < K) return cudaSuccess;
     const uint32_t n_cores = K / core_len;
     const uint32_t strands = crick ? 2u : 1u;
@@ -217,7 +219,8 @@ cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t 
         const unsigned long long w = (unsigned long long)(e - b) * per_probe;
         const unsigned grid = (unsigned)((w + 7) / 8);
         seed_query_kernel<<<grid, 256, 0, st>>>(q, rcq, t, K, core_len, n_cores, seed_bucket_bits(core_len), d_off,
-                                                d_pos, d_sig, b, e, clamp, (int)strands, three ? 1 : 0, q_impure ? 1 : 0, d_best);
+                                                d_pos, d_sig, b, e, clamp, (int)strands, three ? 1 : 0, q_impure ? 1 : 0, d_best,
+                                                d_occ);
         const cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) return err;
         b = e;

@@ -76,6 +76,7 @@ SIGNATURES = {
                                                 ctypes.c_uint32, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
     "k4b_targeted_seed_device": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                                 ctypes.c_uint32, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
+    "k4b_last_seed_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64)] * 2),
     "k4b_targeted_finalize_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, _vp]),
     "k4b_diag_bootstrap_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
     "k4b_diag_bands_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp,
@@ -302,6 +303,12 @@ def targeted_seed_device(probes: Packed, targets: Packed, both_strands: bool, cl
     _check(load_lib().k4b_targeted_seed_device(probes.handle, targets.handle, int(both_strands), clamp, core_len,
                                                q_begin, q_end, _vp(d_best_ptr), _vp(stream), ctypes.byref(n)))
     return n.value
+
+
+def last_seed_info() -> dict:
+    a, b = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    _check(load_lib().k4b_last_seed_info(ctypes.byref(a), ctypes.byref(b)))
+    return {"occurrences": a.value, "indexed_cores": b.value}
 
 
 def targeted_finalize_device(probes: Packed, d_best_ptr: int, clamp: int, d_out_ptr: int, stream: int = 0) -> None:
