@@ -237,6 +237,19 @@ def test_in_process_multi_gpu_shards(oracle):
         probes = np.ascontiguousarray(np.concatenate([target[100:900], [7], target[5000:5600]]), dtype=np.uint8)
         probes[50] = (probes[50] + 1) % 4
         assert np.array_equal(k4b.targeted(target, probes, 32, 3, True), oracle.targeted_brute(target, probes, 32, 3, True))
+        # targeted on every engine: probes split over the devices (seed), diagonals split (bands);
+        # wildcard probes ride along on the POPC engine
+        probes_n = probes.copy()
+        probes_n[[200, 201, 1000]] = 4
+        want = oracle.targeted_brute(target, probes, 32, 3, True)
+        want_n = oracle.targeted_brute(target, probes_n, 32, 3, True)
+        for eng in (hamm.ENGINE_SEED, hamm.ENGINE_DIAG, hamm.ENGINE_POPC):
+            k4b.set_engine(eng)
+            try:
+                assert np.array_equal(k4b.targeted(target, probes, 32, 3, True), want), eng
+                assert np.array_equal(k4b.targeted(target, probes_n, 32, 3, True), want_n), eng
+            finally:
+                k4b.set_engine(hamm.ENGINE_AUTO)
     finally:
         k4b.gpu_shutdown()
         k4b.gpu_init(1)
