@@ -868,7 +868,8 @@ extern "C" int k4b_last_seed_info(uint64_t *occurrences, uint64_t *indexed_cores
 // Targeted (probes vs assembly) by seed-and-verify (k4b_seed.cu): exact for every distance below
 // clamp, the "not found" value, as long as clamp <= K / core_len (pigeonhole over the disjoint
 // cores).  Probe K-mers holding N / InDel are skipped (d_best keeps its value): wildcard probes need
-// the reference's substitution rule and belong to the brute-force engines.  Handles the probe
+// the reference's substitution rule and belong to the brute-force engines.  probes == targets (the
+// same handle) selects the rules of probes drawn from the assembly itself.  Handles the probe
 // K-mers starting in [q_begin, q_end); ranges combine by element-wise minimum of d_best.
 extern "C" int k4b_targeted_seed_device(k4b_packed *probes, k4b_packed *targets, int both_strands,
                                         uint32_t clamp, uint32_t core_len, uint32_t q_begin,
@@ -899,12 +900,23 @@ extern "C" int k4b_targeted_seed_device(k4b_packed *probes, k4b_packed *targets,
     uint32_t *d_pos = d_idx + 2 * (size_t)kSeedOccSlots + 2 * (size_t)targets->len;
     uint32_t *d_cnt = d_pos + targets->len, *d_off = d_cnt + nb + 1, *d_cur = d_off + nb + 1;
     CU(cudaMemsetAsync(d_cnt, 0, ((size_t)nb + 1) * 4, st));
+    // probes == targets: the K-mers of the assembly against the assembly itself (exact sense self hit
+    // skipped; -z of the k4b_hamm_targeted_z call in progress on this thread)
+    SeedSelfRules self{probes == targets ? 1 : 0, 0, nullptr, 0};
+    uint32_t *d_ent = nullptr;
+    if (self.on && g_zf.mode && !g_zf.starts.empty()) {
+        CU(cudaMallocAsync(&d_ent, g_zf.starts.size() * 4, st));
+        CU(cudaMemcpyAsync(d_ent, g_zf.starts.data(), g_zf.starts.size() * 4, cudaMemcpyHostToDevice, st));
+        self.zfilt = g_zf.mode;
+        self.ent_starts = d_ent;
+        self.n_ent = (uint32_t)g_zf.starts.size();
+    }
     RC(g_tp.begin(probes->device, true, st));
     cudaError_t e = launch_seed_index(targets->view(), core_len, d_cnt, d_off, d_cur, d_pos, d_sig, d_temp, temp_bytes, st);
     if (e == cudaSuccess)
         e = launch_seed_query(probes->view(), crick ? probes->rc_view() : probes->view(), targets->view(), K, core_len,
                               d_off, d_pos, d_sig, q_begin, q_end, clamp, crick, targets->has_non_acgt != 0,
-                              probes->has_non_acgt != 0, d_best, d_occ, st);
+                              probes->has_non_acgt != 0, self, d_best, d_occ, st);
     if (e == cudaSuccess) e = g_tp.end(st);
     if (e == cudaSuccess && !g_h_seed) e = cudaMallocHost(&g_h_seed, (kSeedOccSlots + 1) * 8);
     if (e == cudaSuccess) e = cudaMemcpyAsync(g_h_seed, d_occ, kSeedOccSlots * 8, cudaMemcpyDeviceToHost, st);
@@ -912,6 +924,7 @@ extern "C" int k4b_targeted_seed_device(k4b_packed *probes, k4b_packed *targets,
         e = cudaMemcpyAsync(g_h_seed + kSeedOccSlots, d_off + nb, 4, cudaMemcpyDeviceToHost, st);
     cudaFreeAsync(d_temp, st);
     cudaFreeAsync(d_idx, st);
+    if (d_ent) cudaFreeAsync(d_ent, st);
     if (e != cudaSuccess) return fail(cuda_code(e), "seed engine launch: %s", cudaGetErrorString(e));
     if (launches) *launches = nl + 4;
     return K4B_OK;
@@ -1239,6 +1252,11 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
     do {
         CU(cudaSetDevice(g_eng.devs[0]));
         k4b_packed *q0 = nullptr, *t0 = nullptr;
+        const bool same = q_concat == nullptr;  // probes = the K-mers of the assembly itself (no -I)
+        if (same) {
+            q_concat = t_concat;
+            q_len = t_len;
+        }
         if ((rc = k4b_pack_host(q_concat, q_len, K, &q0))) break;
         qs.push_back(q0);
         // a core of c bases occurs in ~len/4^c places: below 6 bases verifying every occurrence costs
@@ -1261,16 +1279,22 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
             if (open) { impure.emplace_back(run_b, q_len - K + 1); total += q_len - K + 1 - run_b; }
             if (impure.size() > 4096 || total * 4 > q_len) seed = false;  // mostly wildcards: not worth it
         }
+        if (same && !seed) break;          // the band engine has no self-hit rules
         if (!seed && !allow_diag) break;  // *used stays 0: the caller runs the POPC engine
         *used = 1;
-        if ((rc = k4b_pack_host(t_concat, t_len, K, &t0))) break;
+        if (same) {
+            t0 = q0;
+        } else if ((rc = k4b_pack_host(t_concat, t_len, K, &t0))) {
+            break;
+        }
         ts.push_back(t0);
         use_seed = seed;
         if (n > 1) {
             qs.clear();
             ts.clear();
             rc = broadcast_packed(q0, qs);
-            if (!rc) rc = broadcast_packed(t0, ts);
+            if (!rc && same) ts = qs;
+            if (!rc && !same) rc = broadcast_packed(t0, ts);
             if (rc) {
                 if (qs.empty()) qs.push_back(q0);
                 if (ts.empty()) ts.push_back(t0);
@@ -1325,7 +1349,7 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
         if ((rc = k4b_targeted_finalize_device(qs[0], bests[0], clamp, d_out, g_eng.streams[0]))) break;
         if (use_seed)  // the wildcard probe K-mers the seed engine skipped
             for (size_t k = 0; k < impure.size() && !rc; ++k)
-                rc = k4b_allpairs_min_device(qs[0], ts[0], both, 0, impure[k].first, impure[k].second, clamp,
+                rc = k4b_allpairs_min_device(qs[0], ts[0], both, same ? 1 : 0, impure[k].first, impure[k].second, clamp,
                                              d_out + impure[k].first, g_eng.streams[0], nullptr);
         if (rc) break;
         if (e == cudaSuccess)
@@ -1347,7 +1371,7 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
         cudaSetDevice(g_eng.devs[i]);
         if (bests[i]) cudaFree(bests[i]);
         if ((size_t)i < qs.size() && qs[i]) k4b_packed_free(qs[i]);
-        if ((size_t)i < ts.size() && ts[i]) k4b_packed_free(ts[i]);
+        if ((size_t)i < ts.size() && ts[i] && !((size_t)i < qs.size() && ts[i] == qs[i])) k4b_packed_free(ts[i]);
     }
     cudaSetDevice(g_eng.devs[0]);
     if (d_out) cudaFree(d_out);
@@ -1430,6 +1454,13 @@ extern "C" int k4b_hamm_targeted(const uint8_t *target_concat, uint64_t target_l
         // is additionally capped at 20 (:4208-4209)
         const uint32_t tl = (uint32_t)target_len;
         if (q_end == 0 || q_end > tl) q_end = tl;
+        const int eng = engine_setting();
+        if (q_begin == 0 && q_end == tl && (eng == 0 || eng == 3) && tl >= 4096) {
+            int used = 0;
+            const int rc = run_targeted_big(target_concat, tl, nullptr, 0, K, both_strands, std::min(notfound, 20u), core,
+                                            true, false, out_h, &used);
+            if (used || rc) return rc;
+        }
         return run_sharded(target_concat, tl, nullptr, 0, K, both_strands, 1, q_begin, q_end,
                            std::min(notfound, 20u), 1, SweepRange(), [&](uint32_t pos, uint16_t v) {
                                if (v <= K) out_h[pos] = (uint8_t)v;

@@ -128,6 +128,12 @@ cudaError_t launch_revcomp_planes(ImageView q, ImageView rc, cudaStream_t st);
 int queries_per_thread(uint32_t W, bool three_planes);
 
 // seed-and-verify engine for the targeted mode (k4b_seed.cu)
+struct SeedSelfRules {          // probes drawn from the indexed assembly itself (no -I)
+    int on;                     // skip the exact sense-strand hit at the probe's own position
+    int zfilt;                  // -z: 1 intra only, 2 inter only (exact sense hits only)
+    const uint32_t *ent_starts; // ascending flat start positions of the entries
+    uint32_t n_ent;
+};
 uint32_t seed_bucket_bits(uint32_t core_len);
 size_t seed_scan_temp_bytes(uint32_t n_buckets);
 cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t *d_cnt, uint32_t *d_off,
@@ -136,7 +142,7 @@ cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t *d_cnt, u
 cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t K, uint32_t core_len,
                               const uint32_t *d_off, const uint32_t *d_pos, const uint2 *d_sig, uint32_t q_begin,
                               uint32_t q_end, uint32_t clamp, bool crick, bool three, bool q_impure,
-                              uint32_t *d_best, unsigned long long *d_occ, cudaStream_t st);
+                              SeedSelfRules self, uint32_t *d_best, unsigned long long *d_occ, cudaStream_t st);
 constexpr int kSeedOccSlots = 1024;  // d_occ (nullable): bucket entries streamed, summed over these slots
 cudaError_t launch_microbench(int which, int iters, uint32_t *d_sink, int *blocks, int *threads,
                               int *ops_per_thread_iter, cudaStream_t st);

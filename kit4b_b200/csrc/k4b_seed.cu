@@ -106,6 +106,16 @@ __device__ __forceinline__ uint32_t kmer_mismatches(const ImageView &a, long lon
     return d;
 }
 
+__device__ __forceinline__ uint32_t seed_entry_of(const SeedSelfRules &r, uint32_t pos) {
+    uint32_t lo = 0, hi = r.n_ent;  // largest i with ent_starts[i] <= pos
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(r.ent_starts + mid) <= pos) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
 // one warp per (probe position, strand, core)
 __global__ void __launch_bounds__(256) seed_query_kernel(ImageView q, ImageView rcq, ImageView t, uint32_t K,
                                                          uint32_t core_len, uint32_t n_cores, uint32_t bits,
@@ -113,7 +123,8 @@ __global__ void __launch_bounds__(256) seed_query_kernel(ImageView q, ImageView 
                                                          const uint32_t *__restrict__ pos,
                                                          const uint2 *__restrict__ sig, uint32_t q_begin,
                                                          uint32_t q_end, uint32_t clamp, int strands, int three,
-                                                         int q_impure, uint32_t *__restrict__ best,
+                                                         int q_impure, SeedSelfRules self,
+                                                         uint32_t *__restrict__ best,
                                                          unsigned long long *__restrict__ occ) {
     const unsigned long long warp_id = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -164,7 +175,19 @@ __global__ void __launch_bounds__(256) seed_query_kernel(ImageView q, ImageView 
         if (ts < 0 || ts > Mt) continue;
         const uint32_t d = kmer_mismatches(img, pp, t, ts, K, three != 0, mine);
         // windows across an entry boundary are no K-mers: checked only for the rare improvement
-        if (d < mine && ((t.valid()[ts >> 5] >> (ts & 31)) & 1u)) mine = d;
+        if (d < mine && ((t.valid()[ts >> 5] >> (ts & 31)) & 1u)) {
+            // probes drawn from the assembly itself: an exact sense-strand hit at the probe's own
+            // position is no hit (SfxArray.cpp:4418-4419, :4585-4594), and -z lets an exact sense
+            // hit count only inside (1) / outside (2) the probe's own entry (:4421-4426, :4597-4601)
+            if (self.on && strand == 0 && d == 0) {
+                if (ts == (long long)p) continue;
+                if (self.zfilt) {
+                    const bool same = seed_entry_of(self, p) == seed_entry_of(self, (uint32_t)ts);
+                    if (self.zfilt == 1 ? !same : same) continue;
+                }
+            }
+            mine = d;
+        }
     }
     mine = __reduce_min_sync(0xffffffffu, mine);
     if (lane == 0 && mine < cur) atomicMin(best + p, mine);
@@ -204,7 +227,7 @@ cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t *d_cnt, u
 cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t K, uint32_t core_len,
                               const uint32_t *d_off, const uint32_t *d_pos, const uint2 *d_sig, uint32_t q_begin,
                               uint32_t q_end, uint32_t clamp, bool crick, bool three, bool q_impure,
-                              uint32_t *d_best, unsigned long long *d_occ, cudaStream_t st) {
+                              SeedSelfRules self, uint32_t *d_best, unsigned long long *d_occ, cudaStream_t st) {
     if (q_begin >= q_end || t.len < K || q.len < K) return cudaSuccess;
     const uint32_t n_cores = K / core_len;
     const uint32_t strands = crick ? 2u : 1u;
@@ -219,8 +242,8 @@ cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t 
         const unsigned long long w = (unsigned long long)(e - b) * per_probe;
         const unsigned grid = (unsigned)((w + 7) / 8);
         seed_query_kernel<<<grid, 256, 0, st>>>(q, rcq, t, K, core_len, n_cores, seed_bucket_bits(core_len), d_off,
-                                                d_pos, d_sig, b, e, clamp, (int)strands, three ? 1 : 0, q_impure ? 1 : 0, d_best,
-                                                d_occ);
+                                                d_pos, d_sig, b, e, clamp, (int)strands, three ? 1 : 0, q_impure ? 1 : 0, self,
+                                                d_best, d_occ);
         const cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) return err;
         b = e;

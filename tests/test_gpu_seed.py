@@ -90,6 +90,49 @@ def test_seed_engine_probe_sets_with_wildcards(oracle):
         assert np.array_equal(k4b.targeted(target, probes, K, R, both), oracle.targeted_brute(target, probes, K, R, both)), (K, R)
 
 
+@pytest.mark.parametrize("K,R,both,z", [(32, 3, True, 0), (25, 2, False, 0), (32, 3, True, 1), (32, 3, True, 2),
+                                         (25, 2, True, 1), (140, 9, True, 2), (20, 1, False, 2)])
+def test_seed_engine_self_mode_matches_oracle(oracle, K, R, both, z):
+    """-m0 without -I: probes are the assembly's own K-mers - exact sense self hit skipped, -z
+    filter of exact sense hits, cap at 20, wildcard K-mers through the POPC engine"""
+    rng = np.random.default_rng(4400 + K)
+    cpl = np.array([3, 2, 1, 0, 4, 5, 6, 7], np.uint8)
+    a = rng.integers(0, 4, size=3000, dtype=np.uint8)
+    e1 = np.concatenate([a[:1500], a[200:500], a[1500:], rng.integers(0, 4, size=300, dtype=np.uint8)])  # intra duplicate
+    e2 = np.concatenate([rng.integers(0, 4, size=400, dtype=np.uint8), a[1000:1400], cpl[a[2000:2300][::-1]],
+                         rng.integers(0, 4, size=200, dtype=np.uint8)])                                    # inter + antisense
+    e2[50:53] = 4                                                                                          # wildcards
+    e3 = a[2500:2900].copy()
+    e3[[10, 200]] = (e3[[10, 200]] + 1) % 4
+    target = np.ascontiguousarray(np.concatenate([e1, [7], e2, [7], e3, [7]]), dtype=np.uint8)
+    want = oracle.targeted_self_brute(target, K, R, both, z)
+    assert np.array_equal(k4b.targeted(target, None, K, R, both, intra_inter_both=z), want)
+    k4b.set_engine(hamm.ENGINE_POPC)
+    try:
+        assert np.array_equal(k4b.targeted(target, None, K, R, both, intra_inter_both=z), want)
+    finally:
+        k4b.set_engine(hamm.ENGINE_SEED)
+
+
+def test_seed_engine_self_mode_at_scale_equals_popc_engine():
+    rng = np.random.default_rng(97)
+    t = random_genome(98, [300000, 120000]).copy()
+    t[5000:8000] = t[200000:203000]
+    t[310000:311000] = np.array([3, 2, 1, 0, 4, 5, 6, 7], np.uint8)[t[40000:41000][::-1]]
+    t[100000:100005] = 4
+    t = np.ascontiguousarray(t)
+    for z in (0, 2):
+        got = k4b.targeted(t, None, 32, 3, True, intra_inter_both=z)
+        k4b.set_engine(hamm.ENGINE_POPC)
+        try:
+            want = k4b.targeted(t, None, 32, 3, True, intra_inter_both=z)
+        finally:
+            k4b.set_engine(hamm.ENGINE_SEED)
+        assert np.array_equal(got, want), z
+        # the planted copy lies in the same entry: an exact hit, unless -z2 (inter only) filters it
+        assert (got[5000:7900] == 0).all() == (z == 0)
+
+
 def test_seed_engine_device_api_ranges_combine(oracle):
     """k4b_targeted_seed_device on probe sub-ranges into one minima array == the host entry point"""
     import torch
