@@ -6,14 +6,16 @@ reference's `genbioseq`, then
     this repo:  k4b_hammings  hammings -m0 -K32 -r3 -c          -i asm.sfx -I probes.seq -o ours.csv
 timed end to end (process start to exit) and compared byte for byte.  Test/measurement
 infrastructure: needs oracle/_ref (built from /root/reference by oracle/build_ref.sh).
-usage: python tools/cfg4_reference.py [scale]      (scale 1.0 = 50 Mbp assembly, 200 kbp probes)"""
+usage: python tools/cfg4_reference.py [scale] [--self]   (scale 1.0 = 50 Mbp assembly, 200 kbp probes;
+       --self drops -I: the K-mers of the assembly against the assembly itself)"""
 import json, os, subprocess, sys, tempfile, time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref", "ngskit4b_ref")
 CLI = os.path.join(ROOT, "kit4b_b200", "bin", "k4b_hammings")
-scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+scale = float(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1] != "--self" else 1.0
+SELF = "--self" in sys.argv  # -m0 without -I: the K-mers of the assembly against the assembly itself
 K, R = 32, 3
 L = "ACGT"
 
@@ -53,7 +55,8 @@ def main():
         res["reference_index_s"] = round(t, 1)
         t, p = run([REF, "genbioseq", "-i", "probes.fa", "-o", "probes.seq", "-r", "probes"], d)
         assert p.returncode == 0, p.stdout[-2000:]
-        args = ["hammings", "-m0", "-K%d" % K, "-r%d" % R, "-c", "-i", "asm.sfx", "-I", "probes.seq"]
+        args = ["hammings", "-m0", "-K%d" % K, "-r%d" % R, "-c", "-i", "asm.sfx"] + ([] if SELF else ["-I", "probes.seq"])
+        res["mode"] = "-m0 without -I (assembly vs itself)" if SELF else "-m0 -I probes"
         t, p = run([REF] + args + ["-T%d" % min(cores, 64), "-o", "ref.csv"], d)
         assert p.returncode == 0, p.stdout[-2000:]
         res["reference_hammings_s"] = round(t, 2)
@@ -67,7 +70,7 @@ def main():
         ours, ref = open(os.path.join(d, "ours.csv"), "rb").read(), open(os.path.join(d, "ref.csv"), "rb").read()
         res["output_bytes"] = len(ref)
         res["outputs_identical"] = ours == ref
-        nq = 2 * (pl - K + 1)
+        nq = nchr * (clen - K + 1) if SELF else 2 * (pl - K + 1)
         nt = nchr * (clen - K + 1)
         res["logical_Gcmp"] = round(nq * nt * 2 / 1e9, 1)
         res["speedup_wall"] = round(res["reference_hammings_s"] / res["ours_hammings_s"], 1)
