@@ -23,8 +23,11 @@
 // entry boundary are rejected through the valid-start plane.
 #include "k4b_kernels.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 namespace k4b {
@@ -116,81 +119,200 @@ __device__ __forceinline__ uint32_t seed_entry_of(const SeedSelfRules &r, uint32
     return lo;
 }
 
-// one warp per (probe position, strand, core)
-__global__ void __launch_bounds__(256) seed_query_kernel(ImageView q, ImageView rcq, ImageView t, uint32_t K,
-                                                         uint32_t core_len, uint32_t n_cores, uint32_t bits,
-                                                         const uint32_t *__restrict__ off,
+// ---- what both query kernels share -------------------------------------------------------
+struct SeedCtx {  // launch-wide constants
+    ImageView q, rcq, t;
+    uint32_t K, core_len, n_cores, bits, clamp;
+    int strands, three, q_impure;
+    SeedSelfRules self;
+};
+struct SeedItem {  // one (probe K-mer, strand, core)
+    uint32_t p, strand, c;  // probe position, 0 sense / 1 antisense, core number
+    long long pp;           // position of the (reverse-complemented) K-mer in its image
+    uint32_t ql, qr, ml, mr;  // the probe's own flanks of the core and the masks of what lies inside the K-mer
+    uint32_t cur;           // running minimum when the item was set up (<= clamp)
+};
+
+// decodes item `sub` of probe p; false = nothing to do (no K-mer, wildcard K-mer, already at 0)
+__device__ __forceinline__ bool seed_item_setup(const SeedCtx &cx, uint32_t p, uint32_t sub,
+                                                const uint32_t *__restrict__ best, SeedItem &it) {
+    if (!((cx.q.valid()[p >> 5] >> (p & 31)) & 1u)) return false;  // no K-mer of one entry starts here
+    if (cx.q_impure) {  // probe K-mers holding N / InDel are left to the brute-force engines
+        uint32_t bad = 0;
+        for (uint32_t o = 0; o < cx.K; o += 32) {
+            uint32_t w = plane_bits(cx.q.plane(2), (long long)p + o);
+            if (cx.K - o < 32) w &= (1u << (cx.K - o)) - 1u;
+            bad |= w;
+        }
+        if (bad) return false;
+    }
+    it.p = p;
+    it.strand = sub / cx.n_cores;
+    it.c = sub - it.strand * cx.n_cores;
+    // the reverse complement of the K-mer at p is the K-mer at len-K-p of the reverse-complemented planes
+    it.pp = it.strand ? (long long)cx.q.len - cx.K - p : p;
+    it.cur = __ldg(best + p);            // running minimum so far (other cores / strands / launches)
+    if (it.cur > cx.clamp) it.cur = cx.clamp;  // only distances below the "not found" value matter
+    if (it.cur == 0) return false;
+    const ImageView &img = it.strand ? cx.rcq : cx.q;
+    const uint32_t shift = it.c * cx.core_len;
+    // the probe's own flanks of this core, cut to what lies inside the K-mer: nl bases before the
+    // core, nr bases after it
+    const uint32_t nl = shift < 16 ? shift : 16u;
+    const uint32_t after = cx.K - shift - cx.core_len;
+    const uint32_t nr = after < 16 ? after : 16u;
+    it.ql = flank16(img, it.pp + shift - 16);
+    it.qr = flank16(img, it.pp + shift + cx.core_len);
+    it.ml = nl ? (0xffffu << (16 - nl)) & 0xffffu : 0u;  // the LAST nl of the 16 bases before the core
+    it.mr = nr == 16 ? 0xffffu : ((1u << nr) - 1u);      // the FIRST nr of the 16 bases after it
+    return true;
+}
+
+// one index entry (signature sg, core position tpos) against one item; lowers `mine`
+__device__ __forceinline__ void seed_test_entry(const SeedCtx &cx, const SeedItem &it, uint2 sg, uint32_t tpos,
+                                                uint32_t &mine) {
+    const uint32_t xl = sg.x ^ it.ql, xr = sg.y ^ it.qr;
+    const uint32_t lb = __popc((xl | (xl >> 16)) & it.ml) + __popc((xr | (xr >> 16)) & it.mr);
+    if (lb >= mine) return;  // already as far as the best hit so far: no need to look at the target
+    const long long ts = (long long)tpos - (long long)it.c * cx.core_len;
+    if (ts < 0 || ts > (long long)cx.t.len - cx.K) return;
+    const ImageView &img = it.strand ? cx.rcq : cx.q;
+    const uint32_t d = kmer_mismatches(img, it.pp, cx.t, ts, cx.K, cx.three != 0, mine);
+    // windows across an entry boundary are no K-mers: checked only for the rare improvement
+    if (d < mine && ((cx.t.valid()[ts >> 5] >> (ts & 31)) & 1u)) {
+        // probes drawn from the assembly itself: an exact sense-strand hit at the probe's own
+        // position is no hit (SfxArray.cpp:4418-4419, :4585-4594), and -z lets an exact sense
+        // hit count only inside (1) / outside (2) the probe's own entry (:4421-4426, :4597-4601)
+        if (cx.self.on && it.strand == 0 && d == 0) {
+            if (ts == (long long)it.p) return;
+            if (cx.self.zfilt) {
+                const bool same = seed_entry_of(cx.self, it.p) == seed_entry_of(cx.self, (uint32_t)ts);
+                if (cx.self.zfilt == 1 ? !same : same) return;
+            }
+        }
+        mine = d;
+    }
+}
+
+// ---- query, warp per item: one warp per (probe position, strand, core) streams the bucket ----
+__global__ void __launch_bounds__(256) seed_query_kernel(SeedCtx cx, const uint32_t *__restrict__ off,
                                                          const uint32_t *__restrict__ pos,
                                                          const uint2 *__restrict__ sig, uint32_t q_begin,
-                                                         uint32_t q_end, uint32_t clamp, int strands, int three,
-                                                         int q_impure, SeedSelfRules self,
-                                                         uint32_t *__restrict__ best,
+                                                         uint32_t q_end, uint32_t *__restrict__ best,
                                                          unsigned long long *__restrict__ occ) {
     const unsigned long long warp_id = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t per_probe = (uint32_t)strands * n_cores;
+    const uint32_t per_probe = (uint32_t)cx.strands * cx.n_cores;
     const unsigned long long pi = warp_id / per_probe;
     if (pi >= (unsigned long long)(q_end - q_begin)) return;
-    const uint32_t p = q_begin + (uint32_t)pi;
-    if (!((q.valid()[p >> 5] >> (p & 31)) & 1u)) return;  // no K-mer of one entry starts here
-    if (q_impure) {  // probe K-mers holding N / InDel are left to the brute-force engines
-        uint32_t bad = 0;
-        for (uint32_t o = 0; o < K; o += 32) {
-            uint32_t w = plane_bits(q.plane(2), (long long)p + o);
-            if (K - o < 32) w &= (1u << (K - o)) - 1u;
-            bad |= w;
-        }
-        if (bad) return;
-    }
-    const uint32_t sub = (uint32_t)(warp_id - pi * per_probe);
-    const uint32_t strand = sub / n_cores, c = sub - strand * n_cores;
-    // the reverse complement of the K-mer at p is the K-mer at len-K-p of the reverse-complemented planes
-    const ImageView &img = strand ? rcq : q;
-    const long long pp = strand ? (long long)q.len - K - p : p;
-    uint32_t cur = __ldg(best + p);  // running minimum so far (other cores / strands / launches)
-    if (cur > clamp) cur = clamp;    // only distances below the "not found" value matter
-    if (cur == 0) return;
+    SeedItem it;
+    if (!seed_item_setup(cx, q_begin + (uint32_t)pi, (uint32_t)(warp_id - pi * per_probe), best, it)) return;
     bool ok;
-    const uint32_t b = core_bucket(img, pp + (long long)c * core_len, core_len, bits, ok);
+    const uint32_t b = core_bucket(it.strand ? cx.rcq : cx.q, it.pp + (long long)it.c * cx.core_len, cx.core_len,
+                                   cx.bits, ok);
     if (!ok) return;  // cannot happen for pure-ACGT probes; kept for safety
     const uint32_t lo = __ldg(off + b), hi = __ldg(off + b + 1);
     if (occ && lane == 0) atomicAdd(occ + (blockIdx.x & (kSeedOccSlots - 1)), (unsigned long long)(hi - lo));
-    const long long Mt = (long long)t.len - K;
-    const long long shift = (long long)c * core_len;
-    // the probe's own flanks of this core, cut to what lies inside the K-mer: nl bases before the
-    // core, nr bases after it
-    const uint32_t nl = shift < 16 ? (uint32_t)shift : 16u;
-    const uint32_t after = K - (uint32_t)shift - core_len;
-    const uint32_t nr = after < 16 ? after : 16u;
-    const uint32_t ql = flank16(img, pp + shift - 16), qr = flank16(img, pp + shift + core_len);
-    const uint32_t ml = nl ? (0xffffu << (16 - nl)) & 0xffffu : 0u;  // the LAST nl of the 16 bases before the core
-    const uint32_t mr = nr == 16 ? 0xffffu : ((1u << nr) - 1u);      // the FIRST nr of the 16 bases after it
-    uint32_t mine = cur;
-    for (uint32_t i = lo + lane; i < hi && mine; i += 32) {
-        const uint2 sg = __ldg(sig + i);
-        const uint32_t xl = sg.x ^ ql, xr = sg.y ^ qr;
-        const uint32_t lb = __popc((xl | (xl >> 16)) & ml) + __popc((xr | (xr >> 16)) & mr);
-        if (lb >= mine) continue;  // already as far as the best hit so far: no need to look at the target
-        const long long ts = (long long)__ldg(pos + i) - shift;
-        if (ts < 0 || ts > Mt) continue;
-        const uint32_t d = kmer_mismatches(img, pp, t, ts, K, three != 0, mine);
-        // windows across an entry boundary are no K-mers: checked only for the rare improvement
-        if (d < mine && ((t.valid()[ts >> 5] >> (ts & 31)) & 1u)) {
-            // probes drawn from the assembly itself: an exact sense-strand hit at the probe's own
-            // position is no hit (SfxArray.cpp:4418-4419, :4585-4594), and -z lets an exact sense
-            // hit count only inside (1) / outside (2) the probe's own entry (:4421-4426, :4597-4601)
-            if (self.on && strand == 0 && d == 0) {
-                if (ts == (long long)p) continue;
-                if (self.zfilt) {
-                    const bool same = seed_entry_of(self, p) == seed_entry_of(self, (uint32_t)ts);
-                    if (self.zfilt == 1 ? !same : same) continue;
-                }
+    uint32_t mine = it.cur;
+    for (uint32_t i = lo + lane; i < hi && mine; i += 32) seed_test_entry(cx, it, __ldg(sig + i), __ldg(pos + i), mine);
+    mine = __reduce_min_sync(0xffffffffu, mine);
+    if (lane == 0 && mine < it.cur) atomicMin(best + it.p, mine);
+}
+
+// ---- query, bucket-major join --------------------------------------------------------------
+// With a few thousand entries per bucket and hundreds of items per bucket, streaming the bucket
+// once per item is HBM-bound (12 B per entry test).  Here the items of a probe chunk are sorted by
+// bucket; a CTA takes 64 consecutive sorted items, stages the bucket of each run of equal-bucket
+// items tile by tile in shared memory and lets its 8 warps test their items against the tile:
+// one global read of an entry serves up to 64 entry tests.
+constexpr int kJoinItems = 64;    // sorted items per CTA
+constexpr int kJoinTile = 1024;   // index entries staged per tile (12 KB)
+
+// bucket of every item of the probe chunk [q0, q0+n_probes); inactive items sort to the end
+__global__ void __launch_bounds__(256) seed_item_keys_kernel(SeedCtx cx, uint32_t q0, uint32_t n_probes,
+                                                             const uint32_t *__restrict__ best,
+                                                             uint32_t *__restrict__ keys, uint32_t *__restrict__ ids) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t per_probe = (uint32_t)cx.strands * cx.n_cores;
+    if (i >= n_probes * per_probe) return;
+    const uint32_t pl = i / per_probe;
+    SeedItem it;
+    uint32_t key = 1u << cx.bits;  // inactive: sorts behind every bucket
+    if (seed_item_setup(cx, q0 + pl, i - pl * per_probe, best, it)) {
+        bool ok;
+        const uint32_t b = core_bucket(it.strand ? cx.rcq : cx.q, it.pp + (long long)it.c * cx.core_len, cx.core_len,
+                                       cx.bits, ok);
+        if (ok) key = b;
+    }
+    keys[i] = key;
+    ids[i] = i;
+}
+
+__global__ void __launch_bounds__(256) seed_join_kernel(SeedCtx cx, const uint32_t *__restrict__ off,
+                                                        const uint32_t *__restrict__ pos,
+                                                        const uint2 *__restrict__ sig, uint32_t q0, uint32_t n_items,
+                                                        const uint32_t *__restrict__ keys,
+                                                        const uint32_t *__restrict__ ids, uint32_t *__restrict__ best,
+                                                        unsigned long long *__restrict__ occ) {
+    __shared__ uint32_t tile_pos[kJoinTile];
+    __shared__ uint2 tile_sig[kJoinTile];
+    __shared__ SeedItem items[kJoinItems];
+    __shared__ uint32_t s_key[kJoinItems], s_mine[kJoinItems];
+    __shared__ uint32_t run_end[kJoinItems];  // run_end[j] = end of the run of equal keys that starts at j
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t base = blockIdx.x * kJoinItems;
+    const uint32_t per_probe = (uint32_t)cx.strands * cx.n_cores;
+    const uint32_t kNone = 1u << cx.bits;
+    if (tid < kJoinItems) {
+        uint32_t key = kNone;
+        s_mine[tid] = 0;
+        if (base + tid < n_items) {
+            key = __ldg(keys + base + tid);
+            if (key < kNone) {
+                const uint32_t id = __ldg(ids + base + tid);
+                const uint32_t pl = id / per_probe;
+                // the item was active when the keys were made; its minimum may have dropped since
+                if (!seed_item_setup(cx, q0 + pl, id - pl * per_probe, best, items[tid])) key = kNone;
+                else s_mine[tid] = items[tid].cur;
             }
-            mine = d;
+        }
+        s_key[tid] = key;
+    }
+    __syncthreads();
+    if (tid < kJoinItems) {  // run boundaries (sorted keys; an item deactivated above splits its run)
+        uint32_t e = tid + 1;
+        while (e < kJoinItems && s_key[e] == s_key[tid]) ++e;
+        run_end[tid] = e;
+    }
+    __syncthreads();
+    for (uint32_t r = 0; r < kJoinItems; r = run_end[r]) {
+        const uint32_t key = s_key[r];
+        if (key >= kNone) continue;
+        const uint32_t r_end = run_end[r];
+        const uint32_t lo = __ldg(off + key), hi = __ldg(off + key + 1);
+        if (occ && tid == 0)
+            atomicAdd(occ + (blockIdx.x & (kSeedOccSlots - 1)), (unsigned long long)(hi - lo) * (r_end - r));
+        for (uint32_t t0 = lo; t0 < hi; t0 += kJoinTile) {
+            const uint32_t n = hi - t0 < (uint32_t)kJoinTile ? hi - t0 : (uint32_t)kJoinTile;
+            __syncthreads();  // the previous tile has been consumed
+            for (uint32_t e = tid; e < n; e += 256) {
+                tile_pos[e] = __ldg(pos + t0 + e);
+                tile_sig[e] = __ldg(sig + t0 + e);
+            }
+            __syncthreads();
+            for (uint32_t j = r + warp; j < r_end; j += 8) {
+                uint32_t mine = s_mine[j];
+                if (mine == 0) continue;
+                const SeedItem it = items[j];
+                for (uint32_t e = lane; e < n && mine; e += 32) seed_test_entry(cx, it, tile_sig[e], tile_pos[e], mine);
+                mine = __reduce_min_sync(0xffffffffu, mine);
+                if (lane == 0) s_mine[j] = mine;
+            }
         }
     }
-    mine = __reduce_min_sync(0xffffffffu, mine);
-    if (lane == 0 && mine < cur) atomicMin(best + p, mine);
+    __syncthreads();
+    if (tid < kJoinItems && s_key[tid] < kNone && s_mine[tid] < items[tid].cur)
+        atomicMin(best + items[tid].p, s_mine[tid]);
 }
 
 uint32_t seed_bucket_bits(uint32_t core_len) {
@@ -229,26 +351,72 @@ cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t 
                               uint32_t q_end, uint32_t clamp, bool crick, bool three, bool q_impure,
                               SeedSelfRules self, uint32_t *d_best, unsigned long long *d_occ, cudaStream_t st) {
     if (q_begin >= q_end || t.len < K || q.len < K) return cudaSuccess;
-    const uint32_t n_cores = K / core_len;
-    const uint32_t strands = crick ? 2u : 1u;
-    const unsigned long long warps = (unsigned long long)(q_end - q_begin) * strands * n_cores;
-    // 1-D grids hold 2^31-1 CTAs of 8 warps: split the probe range if needed
-    const unsigned long long max_warps = 0x7fffffffull * 8ull;
-    const uint32_t per_probe = strands * n_cores;
-    const uint32_t max_probes = (uint32_t)std::min<unsigned long long>(0xffffffffull, max_warps / per_probe);
-    (void)warps;
-    for (uint32_t b = q_begin; b < q_end;) {
-        const uint32_t e = (q_end - b > max_probes) ? b + max_probes : q_end;
-        const unsigned long long w = (unsigned long long)(e - b) * per_probe;
-        const unsigned grid = (unsigned)((w + 7) / 8);
-        seed_query_kernel<<<grid, 256, 0, st>>>(q, rcq, t, K, core_len, n_cores, seed_bucket_bits(core_len), d_off,
-                                                d_pos, d_sig, b, e, clamp, (int)strands, three ? 1 : 0, q_impure ? 1 : 0, self,
-                                                d_best, d_occ);
-        const cudaError_t err = cudaGetLastError();
-        if (err != cudaSuccess) return err;
+    SeedCtx cx;
+    cx.q = q;
+    cx.rcq = rcq;
+    cx.t = t;
+    cx.K = K;
+    cx.core_len = core_len;
+    cx.n_cores = K / core_len;
+    cx.bits = seed_bucket_bits(core_len);
+    cx.clamp = clamp;
+    cx.strands = crick ? 2 : 1;
+    cx.three = three ? 1 : 0;
+    cx.q_impure = q_impure ? 1 : 0;
+    cx.self = self;
+    const uint32_t per_probe = (uint32_t)cx.strands * cx.n_cores;
+    // bucket-major join when buckets are long enough to be worth staging (short cores on long
+    // targets); otherwise one warp per item streams its (short) bucket
+    const char *env = getenv("K4B_SEED_JOIN");
+    const bool join = env ? atoi(env) != 0 : (t.len >> cx.bits) >= 256;
+    if (!join) {
+        // 1-D grids hold 2^31-1 CTAs of 8 warps: split the probe range if needed
+        const unsigned long long max_warps = 0x7fffffffull * 8ull;
+        const uint32_t max_probes = (uint32_t)std::min<unsigned long long>(0xffffffffull, max_warps / per_probe);
+        for (uint32_t b = q_begin; b < q_end;) {
+            const uint32_t e = (q_end - b > max_probes) ? b + max_probes : q_end;
+            const unsigned long long w = (unsigned long long)(e - b) * per_probe;
+            seed_query_kernel<<<(unsigned)((w + 7) / 8), 256, 0, st>>>(cx, d_off, d_pos, d_sig, b, e, d_best, d_occ);
+            const cudaError_t err = cudaGetLastError();
+            if (err != cudaSuccess) return err;
+            b = e;
+        }
+        return cudaSuccess;
+    }
+    // probe chunks of at most 2^25 items: keys -> radix sort by bucket -> join
+    const uint32_t chunk_probes = std::max(1u, (1u << 25) / per_probe);
+    const uint32_t max_items = std::min<unsigned long long>((unsigned long long)chunk_probes,
+                                                            (unsigned long long)(q_end - q_begin)) * per_probe;
+    size_t sort_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, (int)max_items, 0, (int)cx.bits + 1, st);
+    uint32_t *d_buf = nullptr;
+    void *d_sort = nullptr;
+    cudaError_t err = cudaMallocAsync(&d_buf, (size_t)max_items * 16, st);
+    if (err == cudaSuccess) err = cudaMallocAsync(&d_sort, sort_bytes ? sort_bytes : 4, st);
+    if (err != cudaSuccess) {
+        if (d_buf) cudaFreeAsync(d_buf, st);
+        return err;
+    }
+    uint32_t *k_in = d_buf, *k_out = d_buf + max_items, *i_in = k_out + max_items, *i_out = i_in + max_items;
+    for (uint32_t b = q_begin; b < q_end && err == cudaSuccess;) {
+        const uint32_t e = (q_end - b > chunk_probes) ? b + chunk_probes : q_end;
+        const uint32_t n_items = (e - b) * per_probe;
+        seed_item_keys_kernel<<<(n_items + 255) / 256, 256, 0, st>>>(cx, b, e - b, d_best, k_in, i_in);
+        err = cudaGetLastError();
+        if (err == cudaSuccess)
+            err = cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, k_in, k_out, i_in, i_out, (int)n_items, 0,
+                                                  (int)cx.bits + 1, st);
+        if (err == cudaSuccess) {
+            seed_join_kernel<<<(n_items + kJoinItems - 1) / kJoinItems, 256, 0, st>>>(cx, d_off, d_pos, d_sig, b, n_items,
+                                                                                    k_out, i_out, d_best, d_occ);
+            err = cudaGetLastError();
+        }
         b = e;
     }
-    return cudaSuccess;
+    cudaFreeAsync(d_sort, st);
+    cudaFreeAsync(d_buf, st);
+    return err;
 }
 
 }  // namespace k4b
