@@ -517,14 +517,33 @@ def run_ours_targeted(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6552.3))
-    roofline = {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg_bytes / (kms * 1e-3) / 1e9 / peak, "traffic": _traffic("cfg4_seed"),
-                "kernel": "seed_query_kernel (+ seed_count/seed_fill index build) of one step on this rank",
-                "kernel_ms": kms, "kernel_share_of_step": kms * args.steps / ms if ms > 0 else None,
-                "bytes_model": "12 B per bucket entry streamed by the query kernel (%d entries) + index build: planes read "
-                               "twice, 12 B written per indexed core (%d cores)" % (info["occurrences"], info["indexed_cores"]),
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (driver-written copy bandwidth)" if peaks else
-                               "fallback 6552.3 GB/s (MEASURED_PEAKS.json absent)"}
+    bits = min(2 * core, 22)
+    join = os.environ.get("K4B_SEED_JOIN", str(int((len(target) >> bits) >= 256))) != "0"
+    if join:
+        # bucket-major join: entries are staged once per 64 items in shared memory, so HBM is no longer the
+        # bound; every entry test is 3 LOP3 + 1 POPC, and POPC (XU pipe, 16 lanes/clk/SM) is the scarcer pipe
+        ppeak = hamm.microbench_intpipe(0, 4000)
+        ach = info["occurrences"] / (kms * 1e-3) / 1e9
+        roofline = {"bound": "int_pipe(xu: popc)", "achieved": ach, "peak": ppeak, "unit": "Gop/s", "frac": ach / ppeak,
+                    "traffic": _traffic("cfg4_seed_join"),
+                    "kernel": "seed_join_kernel (+ item keys, radix sort, index build) of one step on this rank",
+                    "kernel_ms": kms, "kernel_share_of_step": kms * args.steps / ms if ms > 0 else None,
+                    "ops_model": "1 POPC per entry test (%d tests: every item against every entry of its core's bucket); "
+                                 "index build, item keys and the radix sort of the items are counted as overhead"
+                                 % info["occurrences"],
+                    "hbm_equivalent_GBps": alg_bytes / (kms * 1e-3) / 1e9,
+                    "hbm_note": "the warp-per-item kernel streams 12 B per test from HBM (0.75 of the %.0f GB/s peak, "
+                                "profiles/r01_bench_n1_cfg4_seed.json); the join reads each entry once per 64 items" % peak,
+                    "peak_source": "measured live: register-resident POPC microbenchmark (k4b_microbench_intpipe)"}
+    else:
+        roofline = {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": alg_bytes / (kms * 1e-3) / 1e9 / peak, "traffic": _traffic("cfg4_seed"),
+                    "kernel": "seed_query_kernel (+ seed_count/seed_fill index build) of one step on this rank",
+                    "kernel_ms": kms, "kernel_share_of_step": kms * args.steps / ms if ms > 0 else None,
+                    "bytes_model": "12 B per bucket entry streamed by the query kernel (%d entries) + index build: planes read "
+                                   "twice, 12 B written per indexed core (%d cores)" % (info["occurrences"], info["indexed_cores"]),
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (driver-written copy bandwidth)" if peaks else
+                                   "fallback 6552.3 GB/s (MEASURED_PEAKS.json absent)"}
 
     e2e_steps = args.steps if args.e2e_steps is None else args.e2e_steps
     e2e_val, e2e_ok = None, None
@@ -545,7 +564,8 @@ def run_ours_targeted(args):
                                    "copy + 1 Mbp random, x%.2f) vs a %d-base synthetic assembly (20 entries)" % (Nq, args.scale, len(target)),
                        "K": K, "R": R, "both_strands": both, "probe_kmers": int(Nq), "target_kmers": int(Nt),
                        "step": "the whole targeted job: index of the assembly + every probe K-mer (%.3g logical comparisons)" % cmps,
-                       "engine": "seed-and-verify (pigeonhole cores of %d bases, bucket index with flank signatures)" % core,
+                       "engine": "seed-and-verify (pigeonhole cores of %d bases, bucket index with flank signatures, %s)"
+                                 % (core, "bucket-major join" if join else "warp per item"),
                        "parallelism": "probe shards x%d + all_reduce(MIN)" % world,
                        "l2": "256 MB flush write between timed steps", "result_checksum": checksum},
             "roofline": roofline, "cpu_baseline": None,

@@ -72,12 +72,13 @@ __global__ void __launch_bounds__(256) seed_count_kernel(ImageView t, uint32_t n
     if (ok) atomicAdd(cnt + b, 1u);
 }
 
-// 16 bases starting at pos as (plane-0 bits | plane-1 bits << 16); planes 0/1 only: a non-ACGT
-// symbol then looks like a base, which can only LOWER the mismatch count taken from it
-__device__ __forceinline__ uint32_t flank16(const ImageView &img, long long pos) {
-    const uint32_t w0 = plane_bits(img.plane(0), pos) & 0xffffu;
-    const uint32_t w1 = plane_bits(img.plane(1), pos) & 0xffffu;
-    return w0 | (w1 << 16);
+// Flank signature of a core: the 16 bases before it (bits 0..15) and the 16 bases after it (bits
+// 16..31), x = their plane-0 bits, y = their plane-1 bits.  Planes 0/1 only: a non-ACGT symbol then
+// looks like a base, which can only LOWER the mismatch count taken from the signature.
+__device__ __forceinline__ uint2 flank_sig(const ImageView &img, long long core_pos, uint32_t core_len) {
+    const long long before = core_pos - 16, after = core_pos + core_len;
+    return make_uint2((plane_bits(img.plane(0), before) & 0xffffu) | (plane_bits(img.plane(0), after) << 16),
+                      (plane_bits(img.plane(1), before) & 0xffffu) | (plane_bits(img.plane(1), after) << 16));
 }
 
 __global__ void __launch_bounds__(256) seed_fill_kernel(ImageView t, uint32_t n_pos, uint32_t core_len,
@@ -90,8 +91,7 @@ __global__ void __launch_bounds__(256) seed_fill_kernel(ImageView t, uint32_t n_
     if (!ok) return;
     const uint32_t slot = atomicAdd(cursor + b, 1u);
     pos[slot] = p;
-    // x = the 16 bases before the core (the front pad makes p < 16 readable), y = the 16 after it
-    sig[slot] = make_uint2(flank16(t, (long long)p - 16), flank16(t, (long long)p + core_len));
+    sig[slot] = flank_sig(t, p, core_len);  // the front pad makes p < 16 readable
 }
 
 // mismatches between the K-mer of `a` at pa and the K-mer of `b` at pb (b may hold non-ACGT
@@ -129,7 +129,7 @@ struct SeedCtx {  // launch-wide constants
 struct SeedItem {  // one (probe K-mer, strand, core)
     uint32_t p, strand, c;  // probe position, 0 sense / 1 antisense, core number
     long long pp;           // position of the (reverse-complemented) K-mer in its image
-    uint32_t ql, qr, ml, mr;  // the probe's own flanks of the core and the masks of what lies inside the K-mer
+    uint32_t q0, q1, m;     // the probe's own flank signature of the core and the mask of what lies inside the K-mer
     uint32_t cur;           // running minimum when the item was set up (<= clamp)
 };
 
@@ -161,19 +161,23 @@ __device__ __forceinline__ bool seed_item_setup(const SeedCtx &cx, uint32_t p, u
     const uint32_t nl = shift < 16 ? shift : 16u;
     const uint32_t after = cx.K - shift - cx.core_len;
     const uint32_t nr = after < 16 ? after : 16u;
-    it.ql = flank16(img, it.pp + shift - 16);
-    it.qr = flank16(img, it.pp + shift + cx.core_len);
-    it.ml = nl ? (0xffffu << (16 - nl)) & 0xffffu : 0u;  // the LAST nl of the 16 bases before the core
-    it.mr = nr == 16 ? 0xffffu : ((1u << nr) - 1u);      // the FIRST nr of the 16 bases after it
+    const uint2 qs = flank_sig(img, it.pp + shift, cx.core_len);
+    it.q0 = qs.x;
+    it.q1 = qs.y;
+    const uint32_t ml = nl ? (0xffffu << (16 - nl)) & 0xffffu : 0u;  // the LAST nl of the 16 bases before the core
+    const uint32_t mr = nr == 16 ? 0xffffu : ((1u << nr) - 1u);      // the FIRST nr of the 16 bases after it
+    it.m = ml | (mr << 16);
     return true;
 }
 
-// one index entry (signature sg, core position tpos) against one item; lowers `mine`
-__device__ __forceinline__ void seed_test_entry(const SeedCtx &cx, const SeedItem &it, uint2 sg, uint32_t tpos,
-                                                uint32_t &mine) {
-    const uint32_t xl = sg.x ^ it.ql, xr = sg.y ^ it.qr;
-    const uint32_t lb = __popc((xl | (xl >> 16)) & it.ml) + __popc((xr | (xr >> 16)) & it.mr);
-    if (lb >= mine) return;  // already as far as the best hit so far: no need to look at the target
+// mismatches between an entry's flank signature and the probe's own flanks: a lower bound of the
+// distance (3 LOP3 + 1 POPC); almost every unrelated entry is dismissed by it
+__device__ __forceinline__ uint32_t seed_sig_bound(const SeedItem &it, uint2 sg) {
+    return __popc(((sg.x ^ it.q0) | (sg.y ^ it.q1)) & it.m);
+}
+
+// full verification of the entry whose core sits at target position tpos; lowers `mine`
+__device__ __noinline__ void seed_verify(const SeedCtx &cx, const SeedItem &it, uint32_t tpos, uint32_t &mine) {
     const long long ts = (long long)tpos - (long long)it.c * cx.core_len;
     if (ts < 0 || ts > (long long)cx.t.len - cx.K) return;
     const ImageView &img = it.strand ? cx.rcq : cx.q;
@@ -214,7 +218,8 @@ __global__ void __launch_bounds__(256) seed_query_kernel(SeedCtx cx, const uint3
     const uint32_t lo = __ldg(off + b), hi = __ldg(off + b + 1);
     if (occ && lane == 0) atomicAdd(occ + (blockIdx.x & (kSeedOccSlots - 1)), (unsigned long long)(hi - lo));
     uint32_t mine = it.cur;
-    for (uint32_t i = lo + lane; i < hi && mine; i += 32) seed_test_entry(cx, it, __ldg(sig + i), __ldg(pos + i), mine);
+    for (uint32_t i = lo + lane; i < hi && mine; i += 32)
+        if (seed_sig_bound(it, __ldg(sig + i)) < mine) seed_verify(cx, it, __ldg(pos + i), mine);
     mine = __reduce_min_sync(0xffffffffu, mine);
     if (lane == 0 && mine < it.cur) atomicMin(best + it.p, mine);
 }
@@ -304,7 +309,20 @@ __global__ void __launch_bounds__(256) seed_join_kernel(SeedCtx cx, const uint32
                 uint32_t mine = s_mine[j];
                 if (mine == 0) continue;
                 const SeedItem it = items[j];
-                for (uint32_t e = lane; e < n && mine; e += 32) seed_test_entry(cx, it, tile_sig[e], tile_pos[e], mine);
+                // 4 entries per lane and round: independent loads and POPCs in flight
+                for (uint32_t e0 = 0; e0 < n && mine; e0 += 128) {
+                    uint32_t lb[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t e = e0 + u * 32 + lane;
+                        lb[u] = e < n ? seed_sig_bound(it, tile_sig[e]) : 0xffffffffu;
+                    }
+                    if (min(min(lb[0], lb[1]), min(lb[2], lb[3])) < mine) {  // rare: one branch per 4 entries
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (lb[u] < mine) seed_verify(cx, it, tile_pos[e0 + u * 32 + lane], mine);
+                    }
+                }
                 mine = __reduce_min_sync(0xffffffffu, mine);
                 if (lane == 0) s_mine[j] = mine;
             }
