@@ -286,9 +286,35 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
     // (IMAD; measured to overlap LOP3 fully, profiles/r01_intpipe_microbench.json).  (R, s) of the
     // 32 rows of a block come from a per-warp shared-memory table (one LDS.128 per row and side,
     // broadcast) instead of 2 uniform-pipe shifts per word, and the OR of the two plane terms is
-    // folded into the LOP3s that consume the mismatch words: 2*NP + 18 ALU ops per row pair.
-    constexpr bool kFma = (P == 2 && !WILD);
-    __shared__ uint4 rowtab[kFma ? kDiagWarps : 1][32][2];
+    // folded into the LOP3s that consume the mismatch words: 2*NP + 18 ALU ops per row pair
+    // (two planes; three planes: + 4 SHF + 4 LOP3).
+    // Three planes ride the same path: identity compare adds a third IMAD term (x2 ^ R2) and one OR
+    // per word; the wildcard rule ((m & ~R2) | x2, mism_word above) masks with the row's plane-2 bit
+    // inside that OR and takes the column's plane-2 window as the second term.  Either way a mismatch
+    // word is the OR of two terms (t1, t2), which the consumers fold in.
+    constexpr bool kFma = true;
+    __shared__ uint4 rowtab[kDiagWarps][32][2];
+    __shared__ uint4 rowtab2[P == 3 ? kDiagWarps : 1][32];  // plane 2: {R2 enter, s2 enter, R2 leave, s2 leave}
+    // the two terms of the mismatch word of row step t of one side; ER = the side's row of rowtab,
+    // r2 / s2 = its plane-2 entries of rowtab2
+    auto terms = [&](const SideWords<P> &w, uint32_t t, const uint4 &ER, uint32_t r2, uint32_t s2, uint32_t &t1,
+                     uint32_t &t2) {
+        const uint32_t a = __funnelshift_r(w.xa[0], w.xb[0], t) * ER.y + ER.x;
+        const uint32_t b = __funnelshift_r(w.xa[1], w.xb[1], t) * ER.w + ER.z;
+        if constexpr (P == 2) {
+            t1 = a;
+            t2 = b;
+        } else {
+            const uint32_t x2 = __funnelshift_r(w.xa[2], w.xb[2], t);
+            if constexpr (WILD) {
+                t1 = lop3<0x54>(a, b, r2);  // (a | b) & ~R2: a wildcard row symbol mismatches only a column N
+                t2 = x2;
+            } else {
+                t1 = lop3<0xfc>(a, b, 0u);
+                t2 = x2 * s2 + r2;
+            }
+        }
+    };
     long long row = r_start + 1;
     while (row < r_end) {
         const long long left = r_end - row;
@@ -303,20 +329,26 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
                     const uint32_t l0 = sext_bit(wl.ra[0], lane), l1 = sext_bit(wl.ra[1], lane);
                     rowtab[warp][lane][0] = make_uint4(e0, e0 | 1u, e1, e1 | 1u);
                     rowtab[warp][lane][1] = make_uint4(l0, l0 | 1u, l1, l1 | 1u);
+                    if constexpr (P == 3) {
+                        const uint32_t e2 = sext_bit(we.ra[2], lane), l2 = sext_bit(wl.ra[2], lane);
+                        rowtab2[warp][lane] = make_uint4(e2, e2 | 1u, l2, l2 | 1u);
+                    }
                 }
                 __syncwarp();
 #pragma unroll
                 for (uint32_t t = 0; t < 32; t += 2) {
                     const uint4 E1 = rowtab[warp][t][0], L1 = rowtab[warp][t][1];
                     const uint4 E2 = rowtab[warp][t + 1][0], L2 = rowtab[warp][t + 1][1];
-                    const uint32_t a1 = __funnelshift_r(we.xa[0], we.xb[0], t) * E1.y + E1.x;
-                    const uint32_t b1 = __funnelshift_r(we.xa[1], we.xb[1], t) * E1.w + E1.z;
-                    const uint32_t c1 = __funnelshift_r(wl.xa[0], wl.xb[0], t) * L1.y + L1.x;
-                    const uint32_t d1 = __funnelshift_r(wl.xa[1], wl.xb[1], t) * L1.w + L1.z;
-                    const uint32_t a2 = __funnelshift_r(we.xa[0], we.xb[0], t + 1) * E2.y + E2.x;
-                    const uint32_t b2 = __funnelshift_r(we.xa[1], we.xb[1], t + 1) * E2.w + E2.z;
-                    const uint32_t c2 = __funnelshift_r(wl.xa[0], wl.xb[0], t + 1) * L2.y + L2.x;
-                    const uint32_t d2 = __funnelshift_r(wl.xa[1], wl.xb[1], t + 1) * L2.w + L2.z;
+                    uint4 X1 = make_uint4(0, 0, 0, 0), X2 = X1;
+                    if constexpr (P == 3) {
+                        X1 = rowtab2[warp][t];
+                        X2 = rowtab2[warp][t + 1];
+                    }
+                    uint32_t a1, b1, c1, d1, a2, b2, c2, d2;
+                    terms(we, t, E1, X1.x, X1.y, a1, b1);
+                    terms(wl, t, L1, X1.z, X1.w, c1, d1);
+                    terms(we, t + 1, E2, X2.x, X2.y, a2, b2);
+                    terms(wl, t + 1, L2, X2.z, X2.w, c2, d2);
                     const uint32_t l2 = lop3<0xfc>(c2, d2, 0u);     // lv2 = c2 | d2
                     const uint32_t pn = lop3<0x54>(a2, b2, l2);     // (a2 | b2) & ~lv2
                     const uint32_t q2 = lop3<0x02>(a2, b2, l2);     // lv2 & ~(a2 | b2)
