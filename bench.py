@@ -24,6 +24,9 @@ Printed JSON (one line, rank 0):
   cpu_baseline  the reference's own CPU engine (oracle/_ref, unmodified sources) timed on this
             host on a bounded sample of the same workload
 `--impl reference` times only that CPU engine, with all host threads, on the same config.
+`--workload cfg4` runs BASELINE configs[3] (targeted mode, -m0 -I) on the seed-and-verify engine:
+step = index of the 500 Mbp assembly + all 2e6 probe K-mers; its roofline entry is the HBM stream
+of the index (warp-per-item schedule) or the POPC pipe (bucket-major join).
 """
 import argparse
 import json
@@ -230,7 +233,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "kmer_comparisons_per_sec", "value": v, "unit": "Gcmp/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
         "config": {"workload": WORKLOAD_DESCR[args.workload], "K": K, "both_strands": both,
                    "step": "bounded sample: leading sweep offsets of the exhaustive run, all host threads"},
