@@ -38,6 +38,12 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
     return r;
 }
 
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {  // a * b + c on the FMA pipe
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
 __device__ __forceinline__ uint32_t sext_bit(uint32_t x, uint32_t t) {
     return (uint32_t)((int32_t)(x << (31u - t)) >> 31);
 }
@@ -315,6 +321,7 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
             }
         }
     };
+    const uint32_t lane_mul = 1u << (31u - lane);
     long long row = r_start + 1;
     while (row < r_end) {
         const long long left = r_end - row;
@@ -325,13 +332,24 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
             if constexpr (kFma) {
                 __syncwarp();
                 {
-                    const uint32_t e0 = sext_bit(we.ra[0], lane), e1 = sext_bit(we.ra[1], lane);
-                    const uint32_t l0 = sext_bit(wl.ra[0], lane), l1 = sext_bit(wl.ra[1], lane);
-                    rowtab[warp][lane][0] = make_uint4(e0, e0 | 1u, e1, e1 | 1u);
-                    rowtab[warp][lane][1] = make_uint4(l0, l0 | 1u, l1, l1 | 1u);
+                    // R = all-ones iff bit `lane` of the row word; the multiply (FMA pipe) brings the bit to
+                    // the top, one arithmetic shift spreads it; s = 2R + 1 = R | 1 on the FMA pipe as well
+                    auto rs = [&](uint32_t w, uint32_t &R, uint32_t &sgn) {
+                        R = (uint32_t)((int32_t)imad(w, lane_mul, 0u) >> 31);
+                        sgn = imad(R, 2u, 1u);
+                    };
+                    uint4 E, L;
+                    rs(we.ra[0], E.x, E.y);
+                    rs(we.ra[1], E.z, E.w);
+                    rs(wl.ra[0], L.x, L.y);
+                    rs(wl.ra[1], L.z, L.w);
+                    rowtab[warp][lane][0] = E;
+                    rowtab[warp][lane][1] = L;
                     if constexpr (P == 3) {
-                        const uint32_t e2 = sext_bit(we.ra[2], lane), l2 = sext_bit(wl.ra[2], lane);
-                        rowtab2[warp][lane] = make_uint4(e2, e2 | 1u, l2, l2 | 1u);
+                        uint4 X;
+                        rs(we.ra[2], X.x, X.y);
+                        rs(wl.ra[2], X.z, X.w);
+                        rowtab2[warp][lane] = X;
                     }
                 }
                 __syncwarp();
