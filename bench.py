@@ -389,6 +389,8 @@ def run_ours_bands(args):
         e2e_step()
         engine.keep.clear()
     barrier()
+    e2e_sampler = ClockSampler(local)  # the e2e leg follows ~40 s of sustained load: record its clocks too
+    e2e_sampler.start()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         r = e2e_step()
@@ -397,12 +399,14 @@ def run_ours_bands(args):
             e2e_sum = int(r.astype(np.int64).sum())
     barrier()
     dt = time.perf_counter() - t0
+    e2e_clocks = e2e_sampler.stop()
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e_val = cmps_per_step * e2e_steps / float(tt.item()) / 1e9 if e2e_steps else None
     e2e = {"value": e2e_val, "unit": "Gcmp/s", "h2d_bytes_per_step": int(L), "d2h_bytes_per_step": int(2 * L),
            "steps": e2e_steps, "result_checksum_equals_resident_run": (e2e_sum == checksum) if e2e_steps else None,
+           "clocks": e2e_clocks,
            "api": "k4b_hamm_exhaustive (host buffers)" if world == 1 else
                   "kit4b_b200.dist.exhaustive_distributed_bands (rank-0 host buffer, NCCL broadcast + all_reduce MIN after the bootstrap and every slab)"}
 
