@@ -36,6 +36,23 @@ def test_exhaustive_csv_writer_is_byte_exact(oracle, case, tmp_path):
     assert open(out, "rb").read() == open(os.path.join(GOLDEN, r["csv"]), "rb").read()
 
 
+def test_exhaustive_csv_writer_large_multi_threaded(oracle, tmp_path):
+    """The writer formats runs of more than 2^20 lines in several tasks and threads: a 2.3 M-base
+    chromosome, one shorter than K (the reference's mis-step), values above K (no line), against
+    the literal restatement of the reference loop (hammings.cpp:2899-2929)."""
+    rng = np.random.default_rng(5)
+    K = 25
+    entries = [("big", rng.integers(0, 4, size=2_300_000, dtype=np.uint8)), ("tiny", rng.integers(0, 4, size=11, dtype=np.uint8)),
+               ("mid", rng.integers(0, 4, size=70_000, dtype=np.uint8)), ("last", rng.integers(0, 4, size=1_200_000, dtype=np.uint8))]
+    seq = str(tmp_path / "g.seq")
+    oracle.write_bioseq(seq, entries, title="big")
+    concat, chroms, glen = hostlib.concat_from_bioseq(seq, K)
+    hd = rng.integers(0, K + 3, size=len(concat)).astype(np.uint16)  # K+1, K+2: nothing to report there
+    out = str(tmp_path / "o.csv")
+    hostlib.write_exhaustive_csv(seq, K, hd, out)
+    assert open(out, "rb").read() == oracle.exhaustive_csv(glen, chroms, K, hd)
+
+
 @pytest.mark.parametrize("mr", targeted_runs(), ids=lambda mr: mr[1]["out"])
 def test_restricted_writers_are_byte_exact(oracle, mr, tmp_path, monkeypatch):
     m, r = mr
