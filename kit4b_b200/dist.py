@@ -82,6 +82,17 @@ class CudaEngine:
         return hamm.diag_slabs_device(packed, both, part, nparts, slab_begin, slab_end, best.data_ptr(),
                                       torch.cuda.current_stream(self.device).cuda_stream)
 
+    # ---- targeted mode: seed-and-verify engine on a probe range ----
+    def seed(self, probes, targets, both: bool, clamp: int, core_len: int, b: int, e: int, best: torch.Tensor) -> int:
+        return hamm.targeted_seed_device(probes, targets, both, clamp, core_len, b, e, best.data_ptr(),
+                                         torch.cuda.current_stream(self.device).cuda_stream)
+
+    def targeted_finalize(self, probes, best: torch.Tensor, clamp: int) -> torch.Tensor:
+        out = torch.empty(best.numel(), dtype=torch.int16, device=self.device)
+        hamm.targeted_finalize_device(probes, best.data_ptr(), clamp, out.data_ptr(),
+                                      torch.cuda.current_stream(self.device).cuda_stream)
+        return out
+
     def finalize(self, packed, best: torch.Tensor) -> torch.Tensor:
         out = torch.empty(best.numel(), dtype=torch.int16, device=self.device)
         hamm.best_finalize_device(packed, best.data_ptr(), out.data_ptr(),
@@ -139,6 +150,56 @@ def bands_slabwise(engine, packed, both: bool, rank: int, world: int, best: torc
         launches += engine.slabs(packed, both, rank, world, slab, slab + 1, best)
         dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
     return launches
+
+
+def targeted_distributed(target: Optional[np.ndarray], probes: Optional[np.ndarray], K: int, R: int, both: bool,
+                         engine=None, group=None) -> Optional[np.ndarray]:
+    """Targeted mode (-m0 -I) over the ranks of `group` on the seed-and-verify engine: rank 0 passes
+    the assembly's sequence area and the probe concat (pure ACGT; probe sets with N / InDel go
+    through hamm.targeted, which adds the wildcard pass), both packed sets are broadcast once,
+    every rank indexes the assembly and answers its slice of the probes, the minima meet in one
+    all_reduce(MIN).  rank 0 gets uint8[len(probes)] (0xFF where no K-mer starts), others None."""
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    if engine is None:
+        engine = CudaEngine(torch.device("cuda", torch.cuda.current_device()))
+    dev = engine.device
+    core = K // (R + 1)
+    if R < 1 or R > 10 or core < 4:
+        raise ValueError("R outside 1..10 or K/(R+1) < 4 (hammings.cpp:399-404)")
+    clamp = K // core  # the reference's "not found" value (SfxArray.cpp:4462-4463)
+    if rank == 0 and ((probes >= 4) & (probes < 7)).any():
+        raise ValueError("probe K-mers with N / InDel need the wildcard pass: use kit4b_b200.targeted")
+    handles = []
+    for concat in (target, probes):
+        meta = torch.zeros(2, dtype=torch.int64, device=dev)
+        packed = image = None
+        if rank == 0:
+            image, packed, non_acgt = engine.pack(concat, K)
+            meta = torch.tensor([len(concat), int(non_acgt)], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.broadcast(meta, src=0, group=group)
+        length, non_acgt = (int(v) for v in meta.tolist())
+        if rank != 0:
+            image = engine.empty_image(length)
+        if world > 1:
+            dist.broadcast(image, src=0, group=group)
+        if rank != 0:
+            packed = engine.adopt(image, length, K, bool(non_acgt))
+        handles.append((packed, length))
+    (t_img, _), (q_img, q_len) = handles
+    best = engine.new_best(q_len, K)
+    b, e = shard_bounds(0, q_len, world)[rank]
+    engine.seed(q_img, t_img, both, clamp, core, b, e, best)
+    if world > 1:
+        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
+    if rank != 0:
+        return None
+    out = engine.targeted_finalize(q_img, best, clamp).cpu().numpy().view(np.uint16)
+    res = np.full(q_len, 0xFF, dtype=np.uint8)
+    ok = out <= K
+    res[ok] = out[ok].astype(np.uint8)
+    return res
 
 
 def exhaustive_distributed(concat: Optional[np.ndarray], K: int, both: bool, q_begin: int = 0,

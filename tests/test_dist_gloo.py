@@ -76,6 +76,23 @@ class OracleEngine:
                 torch.minimum(best, torch.from_numpy(hd.astype(np.int32)), out=best)
         return slab_end - slab_begin
 
+    # targeted stand-ins: the oracle answers this rank's slice of the probes
+    def seed(self, probes, targets, both, clamp, core_len, b, e, best):
+        from oracle import hamm_oracle as ho
+        R = self.K // core_len - 1
+        assert self.K // (R + 1) == core_len
+        h = ho.targeted_brute(targets, probes, self.K, R, both).astype(np.int32)
+        h[h == 0xFF] = self.K + 1
+        part = torch.from_numpy(h[b:e])
+        torch.minimum(best[b:e], part, out=best[b:e])
+        return 1
+
+    def targeted_finalize(self, probes, best, clamp):
+        out = torch.minimum(best, torch.tensor(clamp, dtype=torch.int32)).to(torch.int16)
+        from oracle import hamm_oracle as ho
+        out[torch.from_numpy(~ho.valid_starts(probes, self.K))] = self.K + 1
+        return out
+
     def finalize(self, packed, best):
         return best.to(torch.int16)
 
@@ -110,6 +127,29 @@ def _worker_bands(rank, world, port, K, both, ret):
         assert res is None
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _worker_targeted(rank, world, port, K, R, both, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from kit4b_b200.dist import targeted_distributed
+    target, probes = _targeted_case() if rank == 0 else (None, None)
+    res = targeted_distributed(target, probes, K, R, both, engine=OracleEngine.for_k(K))
+    if rank == 0:
+        ret["res"] = res
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _targeted_case():
+    target = random_genome(79, [2500, 1200])
+    probes = np.ascontiguousarray(np.concatenate([target[300:700], [7], random_genome(80, [300])]), dtype=np.uint8)
+    probes[40] = (probes[40] + 1) % 4
+    return target, probes
 
 
 def _free_port():
@@ -148,3 +188,13 @@ def test_two_rank_pair_matrix_partition_with_min_allreduce(oracle, K, both):
     mp.spawn(_worker_bands, args=(2, _free_port(), K, both, ret), nprocs=2, join=True)
     concat = random_genome(78, [300, 30, 260])
     assert np.array_equal(ret["res"], oracle.exhaustive_brute(concat, K, both))
+
+
+@pytest.mark.parametrize("K,R,both", [(32, 3, True), (25, 2, False)])
+def test_two_rank_targeted_probe_shards(oracle, K, R, both):
+    """targeted_distributed: both packed sets broadcast, probes sharded, all_reduce(MIN) == full result."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_targeted, args=(2, _free_port(), K, R, both, ret), nprocs=2, join=True)
+    target, probes = _targeted_case()
+    assert np.array_equal(ret["res"], oracle.targeted_brute(target, probes, K, R, both))

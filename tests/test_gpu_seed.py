@@ -182,3 +182,23 @@ def test_seed_engine_equals_band_engine_at_scale():
             k4b.set_engine(hamm.ENGINE_SEED)
         assert np.array_equal(got, want), (K, R)
         assert (got[:2900] == 0).all()
+
+
+def test_targeted_distributed_single_rank_on_cuda(oracle):
+    """kit4b_b200.dist.targeted_distributed with the real CudaEngine (one rank; the two-rank
+    collective flow is covered on CPU in tests/test_dist_gloo.py)."""
+    import socket
+    import torch.distributed as dist
+    from kit4b_b200.dist import targeted_distributed
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        target, probes = _planted(4500, [6000, 3000])
+        for K, R, both in [(32, 3, True), (50, 5, False)]:
+            assert np.array_equal(targeted_distributed(target, probes, K, R, both), oracle.targeted_brute(target, probes, K, R, both))
+    finally:
+        dist.destroy_process_group()
