@@ -68,6 +68,18 @@ def test_seed_engine_matches_oracle(oracle, K, R, both):
     assert np.array_equal(k4b.targeted(target, probes, K, R, both), oracle.targeted_brute(target, probes, K, R, both))
 
 
+@pytest.mark.parametrize("K,R,both", [(32, 3, True), (25, 2, False), (100, 4, True), (300, 2, False)])
+def test_seed_engine_bucket_major_join_matches_oracle(oracle, monkeypatch, K, R, both):
+    """the join schedule (items sorted by bucket, buckets staged in shared memory) is chosen for
+    long buckets only; K4B_SEED_JOIN=1 forces it on these small inputs (the library reads the
+    variable at every launch)"""
+    monkeypatch.setenv("K4B_SEED_JOIN", "1")
+    target, probes = _planted(4600 + K, [6000, 3000, 2500])
+    assert np.array_equal(k4b.targeted(target, probes, K, R, both), oracle.targeted_brute(target, probes, K, R, both))
+    assert np.array_equal(k4b.targeted(target, None, K, R, both, intra_inter_both=2),
+                          oracle.targeted_self_brute(target, K, R, both, 2))
+
+
 def test_seed_engine_targets_with_non_acgt(oracle):
     target, probes = _planted(4100, [5000, 4000], alpha_t=5)  # N in the targets, probes stay ACGT
     target[1000:1010] = 4
