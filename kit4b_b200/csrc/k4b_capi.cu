@@ -192,10 +192,10 @@ static uint32_t array_stride(uint32_t len) {
     return kFrontPadWords + (nw + kTileGroups - 1) / kTileGroups * kTileGroups + kBackPadWords;
 }
 extern "C" size_t k4b_packed_image_bytes(uint32_t concat_len) {
-    return (size_t)array_stride(concat_len) * 4 * sizeof(uint32_t);
+    return (size_t)array_stride(concat_len) * kImageArrays * sizeof(uint32_t);
 }
 extern "C" void *k4b_packed_image_ptr(k4b_packed *p) { return p ? p->d_image : nullptr; }
-extern "C" size_t k4b_packed_image_size(k4b_packed *p) { return p ? (size_t)p->stride * 16 : 0; }
+extern "C" size_t k4b_packed_image_size(k4b_packed *p) { return p ? (size_t)p->stride * kImageArrays * 4 : 0; }
 extern "C" int k4b_packed_has_non_acgt(k4b_packed *p) { return p ? p->has_non_acgt : 0; }
 extern "C" uint64_t k4b_packed_num_kmers(k4b_packed *p) { return p ? p->num_kmers : 0; }
 extern "C" void k4b_packed_free(k4b_packed *p) {
@@ -426,7 +426,7 @@ static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_stra
     const bool generic = W > (uint32_t)kMaxRegW;
 
     if (generic && crick && !queries->d_rc_planes) {
-        CU(cudaMalloc(&queries->d_rc_planes, (size_t)queries->stride * 12));
+        CU(cudaMalloc(&queries->d_rc_planes, (size_t)queries->stride * kImageArrays * 4));
         CU(launch_revcomp_planes(queries->view(), queries->rc_view(), st));
     }
 
@@ -525,7 +525,7 @@ extern "C" int k4b_best_finalize_device(k4b_packed *g, const uint32_t *d_best, u
 static int diag_prepare(k4b_packed *g, bool crick, cudaStream_t st, int *nl) {
     CU(cudaSetDevice(g->device));
     if (crick && !g->d_rc_planes) {
-        CU(cudaMalloc(&g->d_rc_planes, (size_t)g->stride * 12));
+        CU(cudaMalloc(&g->d_rc_planes, (size_t)g->stride * kImageArrays * 4));
         CU(launch_revcomp_planes(g->view(), g->rc_view(), st));
         ++*nl;
     }
@@ -581,7 +581,8 @@ extern "C" int k4b_diag_bootstrap_device(k4b_packed *g, int both_strands, uint32
 }
 
 // bookkeeping of the most recent band run of this thread (which counter width each slab used)
-static thread_local uint32_t *g_h_tmax = nullptr;  // pinned, 64 entries
+constexpr uint32_t kMaxSlabs = 64;  // slots per bookkeeping array (d_tmax, d_low on the device; the halves of g_h_tmax)
+static thread_local uint32_t *g_h_tmax = nullptr;  // pinned, 2 * kMaxSlabs entries
 static thread_local uint32_t g_info_slabs = 0, g_info_np_full = 0, g_info_np_small = 0, g_info_limit = 0,
                              g_info_low_max = 0;
 
@@ -592,7 +593,7 @@ extern "C" int k4b_last_diag_info(uint32_t *np_full, uint32_t *np_small, uint32_
     CU(cudaDeviceSynchronize());
     uint32_t narrow = 0;
     for (uint32_t i = 0; i < g_info_slabs; ++i)
-        if (g_info_np_small && g_h_tmax[i] <= g_info_limit && g_h_tmax[64 + i] <= g_info_low_max) ++narrow;
+        if (g_info_np_small && g_h_tmax[i] <= g_info_limit && g_h_tmax[kMaxSlabs + i] <= g_info_low_max) ++narrow;
     if (np_full) *np_full = g_info_np_full;
     if (np_small) *np_small = g_info_np_small;
     if (slabs) *slabs = g_info_slabs;
@@ -615,12 +616,14 @@ SlabPlan make_slab_plan(uint64_t groups_per_part) {
     SlabPlan p;
     const char *sl = getenv("K4B_DIAG_SLABS");  // experiments: n equal slabs
     if (sl && atoi(sl) > 0) {
-        p.R = (uint32_t)std::min(64, atoi(sl));
+        p.R = (uint32_t)std::min((int)kMaxSlabs, atoi(sl));
         for (uint32_t i = 0; i <= p.R; ++i) p.bounds.push_back(i);
         return p;
     }
     const char *pr = getenv("K4B_DIAG_PERIOD"), *cp = getenv("K4B_DIAG_CAP");
-    uint32_t rmax = pr ? (uint32_t)atoi(pr) : 64u;
+    // at most kMaxSlabs slabs exist (per-slab bookkeeping slots of d_bm and g_h_tmax): the period,
+    // which bounds the slab count, is clamped to it
+    uint32_t rmax = pr ? (uint32_t)std::min(std::max(atoi(pr), 1), (int)kMaxSlabs) : kMaxSlabs;
     while (p.R < rmax && (uint64_t)p.R * 8 <= groups_per_part) p.R *= 2;
     const uint32_t cap = cp ? std::max(1, atoi(cp)) : std::max(1u, p.R / 8);
     p.bounds.push_back(0);
@@ -673,10 +676,11 @@ extern "C" int k4b_diag_slabs_device(k4b_packed *g, int both_strands, uint32_t p
     const uint32_t bm_shift = 8;
     const uint32_t n_blocks = (M >> bm_shift) + 1;
     uint32_t *d_bm = nullptr;  // [n_blocks] block maxima + per slab: [64] global maxima, [64] low-block counts
-    CU(cudaMallocAsync(&d_bm, ((size_t)n_blocks + 128) * 4, st));
-    CU(cudaMemsetAsync(d_bm + n_blocks, 0, 128 * 4, st));
+    if (n_slabs > kMaxSlabs) return fail(K4B_ERR_PARAMS, "%u slabs exceed the %u bookkeeping slots", n_slabs, kMaxSlabs);
+    CU(cudaMallocAsync(&d_bm, ((size_t)n_blocks + 2 * kMaxSlabs) * 4, st));
+    CU(cudaMemsetAsync(d_bm + n_blocks, 0, 2 * kMaxSlabs * 4, st));
     const char *rs = getenv("K4B_DIAG_ROWS");
-    const uint32_t rows_per_seg = rs ? (uint32_t)atoi(rs) : 4096u;
+    const uint32_t rows_per_seg = rs ? (uint32_t)atoi(rs) : 8192u;
     DiagParams dp;
     dp.a = g->view();
     dp.va = g->view();
@@ -706,7 +710,7 @@ extern "C" int k4b_diag_slabs_device(k4b_packed *g, int both_strands, uint32_t p
     RC(g_tp.begin(g->device, slab_begin == 0, st));
     cudaError_t e = cudaSuccess;
     for (uint32_t slab = slab_begin; slab < slab_end && e == cudaSuccess; ++slab) {
-        uint32_t *d_tmax = d_bm + n_blocks + slab, *d_low = d_bm + n_blocks + 64 + slab;
+        uint32_t *d_tmax = d_bm + n_blocks + slab, *d_low = d_bm + n_blocks + kMaxSlabs + slab;
         e = launch_blockmax(d_best, g->view(), M + 1, bm_shift, d_bm, n_blocks, d_tmax, low_floor, d_low, st);
         dp.tmax_ptr = d_tmax;
         dp.sel_limit = np_small ? (1u << (np_small - 1)) : 0u;
@@ -746,12 +750,12 @@ extern "C" int k4b_diag_slabs_device(k4b_packed *g, int both_strands, uint32_t p
         }
     }
     if (e == cudaSuccess) e = g_tp.end(st);
-    if (e == cudaSuccess && !g_h_tmax) e = cudaMallocHost(&g_h_tmax, 128 * sizeof(uint32_t));
+    if (e == cudaSuccess && !g_h_tmax) e = cudaMallocHost(&g_h_tmax, 2 * kMaxSlabs * sizeof(uint32_t));
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(g_h_tmax + slab_begin, d_bm + n_blocks + slab_begin,
                             (slab_end - slab_begin) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(g_h_tmax + 64 + slab_begin, d_bm + n_blocks + 64 + slab_begin,
+        e = cudaMemcpyAsync(g_h_tmax + kMaxSlabs + slab_begin, d_bm + n_blocks + kMaxSlabs + slab_begin,
                             (slab_end - slab_begin) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
     g_info_low_max = n_blocks / 64;
     g_info_slabs = n_slabs;
@@ -808,7 +812,7 @@ extern "C" int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets,
     dp.update_cols = 0;
     dp.wild = three ? 1 : 0;
     dp.t_fixed = std::min(clamp, K + 1);
-    dp.rows_per_seg = rs ? (uint32_t)atoi(rs) : 4096u;
+    dp.rows_per_seg = rs ? (uint32_t)atoi(rs) : 8192u;
     dp.n_seg = (uint32_t)(((uint64_t)dp.Mrow + 1 + dp.rows_per_seg - 1) / dp.rows_per_seg);
     dp.best = d_best;
     dp.blockmax = nullptr;

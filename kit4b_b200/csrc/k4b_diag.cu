@@ -25,6 +25,8 @@
 // Exact, bit-identical results; measured against the same oracle as the POPC engine.
 #include "k4b_kernels.cuh"
 
+#include <stdlib.h>
+
 namespace k4b {
 
 constexpr int kDiagWarps = 8;        // super-bands (of 1024 diagonals) per CTA
@@ -153,8 +155,11 @@ __device__ __noinline__ void diag_flush(Counters<NP> cs, uint32_t flags, uint32_
     if (rows == 2) diag_flush_row<NP>(cs, flags, bias, row + 1, s0, adj1, fc);
 }
 
-template <int NP, int P, bool WILD>
+// EWIN (two planes only): the mismatch words of a 32-row block come from a per-thread table of the
+// four possible mismatch WINDOWS (one per row base) in shared memory - see the main loop.
+template <int NP, int P, bool WILD, bool EWIN>
 __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagParams prm) {
+    static_assert(!EWIN || (P == 2 && !WILD), "the window-table path handles pure ACGT sets");
     if (prm.sel) {  // device-side choice between the narrow- and the full-counter instance
         const uint32_t tg = __ldg(prm.tmax_ptr);
         const bool narrow = tg <= prm.sel_limit && __ldg(prm.low_ptr) <= prm.low_max;
@@ -299,8 +304,18 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
     // inside that OR and takes the column's plane-2 window as the second term.  Either way a mismatch
     // word is the OR of two terms (t1, t2), which the consumers fold in.
     constexpr bool kFma = true;
-    __shared__ uint4 rowtab[kDiagWarps][32][2];
+    __shared__ uint4 rowtab[EWIN ? 1 : kDiagWarps][EWIN ? 1 : 32][2];
     __shared__ uint4 rowtab2[P == 3 ? kDiagWarps : 1][32];  // plane 2: {R2 enter, s2 enter, R2 leave, s2 leave}
+    // Window-table path (EWIN).  For a block of 32 rows the column window of a thread is fixed
+    // (64 bits per plane), and the mismatch word of row step t is bits [t, t+32) of
+    //     M_b = (x0 ^ b0) | (x1 ^ b1)          b = the row's base (2 bits, warp uniform)
+    // so each thread keeps M_A, M_C, M_G, M_T of the enter and of the leave side (2 x 4 x 8 bytes) in its
+    // OWN shared-memory slots (no synchronisation) and a row step is one LDS.64 at [slot + base offset]
+    // and one funnel shift: 4 SHF + (2*NP + 8) LOP3 + 1 ISETP per row PAIR instead of 8 SHF + (2*NP + 9)
+    // LOP3 + 1 ISETP + 8 IMAD, and the per-warp row table disappears from the block prologue.  The base
+    // offsets of the 32 rows are packed 2 bits per row into a 64-bit word that REDUX leaves in uniform
+    // registers, so the per-row address arithmetic runs on the uniform datapath.
+    __shared__ uint2 mtab[EWIN ? 2 : 1][EWIN ? 4 : 1][EWIN ? kDiagWarps * 32 : 1];
     // the two terms of the mismatch word of row step t of one side; ER = the side's row of rowtab,
     // r2 / s2 = its plane-2 entries of rowtab2
     auto terms = [&](const SideWords<P> &w, uint32_t t, const uint4 &ER, uint32_t r2, uint32_t s2, uint32_t &t1,
@@ -325,10 +340,65 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
     long long row = r_start + 1;
     while (row < r_end) {
         const long long left = r_end - row;
+        if constexpr (EWIN) {
+            if (left >= 32) {
+                uint32_t ce_lo, ce_hi, cl_lo, cl_hi;  // 2-bit base codes of the 32 enter / leave rows (uniform)
+                auto build = [&](long long idx, int side, uint32_t &c_lo, uint32_t &c_hi) {
+                    // base codes of rows idx .. idx+31: a 64-bit window of the 2-bit code array (warp
+                    // uniform; REDUX leaves it in uniform registers)
+                    const uint32_t *cw = prm.a.code2() + (idx >> 4);
+                    const uint32_t csh = (uint32_t)(idx & 15) * 2u;
+                    const uint32_t k0 = __ldg(cw), k1 = __ldg(cw + 1), k2 = __ldg(cw + 2);
+                    c_lo = __reduce_or_sync(0xffffffffu, __funnelshift_r(k0, k1, csh));
+                    c_hi = __reduce_or_sync(0xffffffffu, __funnelshift_r(k1, k2, csh));
+                    const long long wb = idx + s0;
+                    const long long wj = wb >> 5;  // floor: may be slightly negative (front pad)
+                    const uint32_t ws = (uint32_t)(wb & 31);
+                    const uint32_t *b0 = prm.b.plane(0) + wj, *b1 = prm.b.plane(1) + wj;
+                    const uint32_t p0 = __ldg(b0), p1 = __ldg(b0 + 1), p2 = __ldg(b0 + 2);
+                    const uint32_t q0 = __ldg(b1), q1 = __ldg(b1 + 1), q2w = __ldg(b1 + 2);
+                    const uint32_t x0a = __funnelshift_r(p0, p1, ws), x0b = __funnelshift_r(p1, p2, ws);
+                    const uint32_t x1a = __funnelshift_r(q0, q1, ws), x1b = __funnelshift_r(q1, q2w, ws);
+                    // mismatch windows (x0 ^ b0) | (x1 ^ b1) for the four row bases, one LOP3 per word
+                    mtab[side][0][threadIdx.x] = make_uint2(lop3<0xfc>(x0a, x1a, 0u), lop3<0xfc>(x0b, x1b, 0u));  // A (00):  x0 |  x1
+                    mtab[side][1][threadIdx.x] = make_uint2(lop3<0xcf>(x0a, x1a, 0u), lop3<0xcf>(x0b, x1b, 0u));  // C (01): ~x0 |  x1
+                    mtab[side][2][threadIdx.x] = make_uint2(lop3<0xf3>(x0a, x1a, 0u), lop3<0xf3>(x0b, x1b, 0u));  // G (10):  x0 | ~x1
+                    mtab[side][3][threadIdx.x] = make_uint2(lop3<0x3f>(x0a, x1a, 0u), lop3<0x3f>(x0b, x1b, 0u));  // T (11): ~x0 | ~x1
+                };
+                build(row + K - 1, 0, ce_lo, ce_hi);
+                build(row - 1, 1, cl_lo, cl_hi);
+                const char *slot = reinterpret_cast<const char *>(&mtab[0][0][threadIdx.x]);
+                constexpr uint32_t kBaseStride = kDiagWarps * 32 * sizeof(uint2);  // 2048 B: bits 11, 12 select the base
+                constexpr uint32_t kSideStride = 4 * kBaseStride;
+                static_assert(kBaseStride == 2048, "offset extraction below assumes a 2 KB base stride");
+                // byte offset of the window of row step t: (code of row t) * 2048
+                auto off = [&](uint32_t c_lo, uint32_t c_hi, uint32_t t) -> uint32_t {
+                    const uint32_t w = t < 16 ? c_lo : c_hi, b = (t & 15u) * 2u;  // the code sits at bits b, b+1 of w
+                    return (b <= 11 ? (w << (11 - b)) : (w >> (b - 11))) & 0x1800u;
+                };
+                auto word = [&](uint32_t side_off, uint32_t o, uint32_t t) -> uint32_t {
+                    const uint2 w = *reinterpret_cast<const uint2 *>(slot + side_off + o);
+                    return __funnelshift_r(w.x, w.y, t);
+                };
+#pragma unroll
+                for (uint32_t t = 0; t < 32; t += 2) {
+                    const uint32_t e1 = word(0, off(ce_lo, ce_hi, t), t);
+                    const uint32_t l1 = word(kSideStride, off(cl_lo, cl_hi, t), t);
+                    const uint32_t e2 = word(0, off(ce_lo, ce_hi, t + 1), t + 1);
+                    const uint32_t l2 = word(kSideStride, off(cl_lo, cl_hi, t + 1), t + 1);
+                    uint32_t q2;
+                    pair_step(e1, l1, e2, l2, q2);
+                    const uint32_t f = ~c[NP - 1];
+                    if (__builtin_expect(f != 0, 0)) flush(f, row + t, q2, pprev, 2);
+                }
+                row += 32;
+                continue;
+            }
+        }
         SideWords<P> we, wl;
         load_side<P>(prm.a, prm.b, row + K - 1, s0, we);
         load_side<P>(prm.a, prm.b, row - 1, s0, wl);
-        if (left >= 32) {
+        if (!EWIN && left >= 32) {
             if constexpr (kFma) {
                 __syncwarp();
                 {
@@ -417,11 +487,11 @@ int diag_planes_for_k(uint32_t K) {
     return b + 1;
 }
 
-template <int P, bool WILD>
+template <int P, bool WILD, bool EWIN>
 static cudaError_t launch_diag_p(const DiagParams &p, int np, dim3 grid, cudaStream_t st) {
     switch (np) {
 #define K4B_DIAG_CASE(N) \
-    case N: diag_min_kernel<N, P, WILD><<<grid, kDiagWarps * 32, 0, st>>>(p); break
+    case N: diag_min_kernel<N, P, WILD, EWIN><<<grid, kDiagWarps * 32, 0, st>>>(p); break
         K4B_DIAG_CASE(5);
         K4B_DIAG_CASE(6);
         K4B_DIAG_CASE(7);
@@ -448,8 +518,13 @@ cudaError_t launch_diag(const DiagParams &p, bool three_planes, int np, uint32_t
     if (np < 5) np = 5;
     if ((1u << np) < p.K + 1) return cudaErrorInvalidValue;  // K + bias would not fit
     dim3 grid((unsigned)total);
-    if (!three_planes) return launch_diag_p<2, false>(p, np, grid, st);
-    return p.wild ? launch_diag_p<3, true>(p, np, grid, st) : launch_diag_p<3, false>(p, np, grid, st);
+    if (!three_planes) {
+        // K4B_DIAG_EWIN=0 selects the previous two-plane path (row table + IMAD broadcast XOR)
+        const char *e = getenv("K4B_DIAG_EWIN");  // read per launch: tests toggle it
+        const int ewin = e ? atoi(e) : 1;
+        return ewin ? launch_diag_p<2, false, true>(p, np, grid, st) : launch_diag_p<2, false, false>(p, np, grid, st);
+    }
+    return p.wild ? launch_diag_p<3, true, false>(p, np, grid, st) : launch_diag_p<3, false, false>(p, np, grid, st);
 }
 
 }  // namespace k4b

@@ -54,6 +54,15 @@ __device__ __forceinline__ uint32_t gather4(uint32_t x, int p) {
     return (t * 0x10204080u) >> 28;
 }
 
+// 16 bits -> 32 bits with a zero between neighbours (bit i -> bit 2i)
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+    x &= 0xffffu;
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    return (x | (x << 1)) & 0x55555555u;
+}
+
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ concat, ImageView img,
                                                    uint32_t *__restrict__ image, uint32_t *__restrict__ flags) {
     // thread i packs 16 bases into 16 bits per plane; lane pairs merge to a word.  Array words
@@ -88,6 +97,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ c
     // codes 4..6 (N, Undef, InDel): bit 2 set but not all three bits
     const uint32_t non_acgt = frag[2] & ~(frag[0] & frag[1]);
     if (__any_sync(0xffffffffu, non_acgt != 0) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
+    // 2-bit code array: this thread's 16 bases are exactly one of its words
+    if (w_abs < img.stride) image[(size_t)4 * img.stride + i] = spread16(frag[0]) | (spread16(frag[1]) << 1);
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
         const uint32_t hi = __shfl_down_sync(0xffffffffu, frag[p], 1);
@@ -554,7 +565,8 @@ __global__ void __launch_bounds__(kThreads, 2) allpairs_min_generic_kernel(const
 }
 
 // planes of the reverse-complemented sequence: rc[i] = cpl(x[len-1-i]); positions >= len are
-// EOS in all planes.  One thread per output word.
+// EOS in all planes.  One thread per output word.  rc_arr has the geometry of a packed image
+// (kImageArrays arrays; the valid array stays unused).
 __device__ __forceinline__ uint32_t bits_at(const uint32_t *pl, int64_t start) {
     // 32 bits of the plane starting at bit offset start (may be negative: those bits read 0)
     if (start <= -32) return 0;
@@ -580,7 +592,14 @@ __global__ void __launch_bounds__(256) revcomp_planes_kernel(ImageView q, uint32
         o[1] ^= flip;
     }
 #pragma unroll
-    for (int p = 0; p < 3; ++p) rc_arr[(size_t)p * q.stride + w_abs] = o[p] | ~in;
+    for (int p = 0; p < 3; ++p) {
+        o[p] |= ~in;
+        rc_arr[(size_t)p * q.stride + w_abs] = o[p];
+    }
+    // 2-bit code array of the reverse-complemented sequence (rows of the rectangular band mode)
+    uint32_t *code = rc_arr + (size_t)4 * q.stride + 2 * (size_t)w_abs;
+    code[0] = spread16(o[0]) | (spread16(o[1]) << 1);
+    code[1] = spread16(o[0] >> 16) | (spread16(o[1] >> 16) << 1);
 }
 
 // ---------------------------------------------------------------------------------------

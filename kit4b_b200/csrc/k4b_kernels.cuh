@@ -28,8 +28,12 @@ constexpr int kFrontPadWords = 320;  // EOS-filled words before logical position
                                      // reads columns at slightly negative offsets)
 constexpr int kBackPadWords = 576;   // EOS-filled words after the last sequence word
 
-// Layout of one packed image: 4 arrays (plane0, plane1, plane2, valid) of `stride` words each;
-// logical word 0 of an array sits kFrontPadWords into it.
+// Layout of one packed image: 4 arrays (plane0, plane1, plane2, valid) of `stride` words each,
+// logical word 0 of an array sits kFrontPadWords into it; then the 2-bit CODE array of 2 * stride
+// words (bits 2i, 2i+1 of its logical word i/16 = plane-0 / plane-1 bit of base i; 16 bases per
+// word, logical word 0 sits 2 * kFrontPadWords into it): the band engine reads the base codes of
+// 32 consecutive rows as one 64-bit window of it.  kImageArrays words of stride in total.
+constexpr int kImageArrays = 6;
 struct ImageView {
     const uint32_t *base;  // device pointer to logical word 0 of plane 0
     uint32_t stride;       // words between consecutive arrays
@@ -37,6 +41,7 @@ struct ImageView {
     uint32_t len;          // bases (incl. EOS separators)
     __host__ __device__ const uint32_t *plane(int p) const { return base + (size_t)p * stride; }
     __host__ __device__ const uint32_t *valid() const { return base + (size_t)3 * stride; }
+    __host__ __device__ const uint32_t *code2() const { return base + (size_t)4 * stride + kFrontPadWords; }
 };
 
 struct AllPairsParams {

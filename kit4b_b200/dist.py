@@ -1,12 +1,22 @@
-"""One-process-per-GPU sharding of the exhaustive engine (torchrun / torch.distributed).
+"""One-process-per-GPU drivers of the engines (torchrun / torch.distributed).
 
 Mirrors the reference's only parallel axis - independent workers with private result arrays
 that are merged at the end (ngskit4b/hammings.cpp:2752-2766 thread blocks, :2855-2867 merge;
--m2/-m3 node slices :2660-2689, :1126-1343) - but shards QUERY K-mers instead of sweep offsets,
-so no merge is needed: rank r owns the queries whose flat start position lies in its slice and
-compares them with every target.  The only collective on the data path is ONE broadcast of
-the bit-plane packed target set from rank 0 (NCCL over NVLink on GPUs); per-rank minima are
-gathered to rank 0 and concatenated on the host.
+-m2/-m3 node slices :2660-2689, :1126-1343).  Every driver starts with ONE broadcast of the
+bit-plane packed sequence set(s) from rank 0 (NCCL over NVLink on GPUs); what is partitioned
+depends on the engine:
+  * exhaustive_distributed        POPC all-pairs engine: QUERY K-mers are sharded, no exchange after
+                                  the broadcast, per-rank minima are gathered and concatenated on
+                                  the host of rank 0;
+  * exhaustive_distributed_bands  diagonal-band engine: the PAIR MATRIX is partitioned (every cell
+                                  lowers both K-mers of its pair), every rank keeps a complete
+                                  minima array, thresholds are exchanged between slabs and the
+                                  arrays meet in one all_reduce(MIN) at the end;
+  * targeted_distributed          seed-and-verify engine: probe K-mers are sharded, one
+                                  all_reduce(MIN) at the end.
+A failure on rank 0 before the first broadcast (bad parameters, out of memory while packing) is
+carried to every rank in the metadata broadcast and raised everywhere - no rank is left waiting in
+a collective.
 
 torch is plumbing here (device buffers, streams, process group); the arithmetic is the CUDA
 engine behind the C ABI (kit4b_b200.hamm).  `engine` is pluggable so that the host-side
@@ -34,7 +44,6 @@ class CudaEngine:
 
     def __init__(self, device: torch.device):
         self.device = device
-        self.keep = []  # tensors that must outlive the handles built on them
 
     def empty_image(self, length: int) -> torch.Tensor:
         return torch.empty(hamm.packed_image_bytes(length), dtype=torch.uint8, device=self.device)
@@ -47,12 +56,13 @@ class CudaEngine:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         packed = hamm.Packed.from_device_into(d_concat.data_ptr(), len(concat), K, image.data_ptr(),
                                               image.numel(), stream)
-        self.keep.append(image)
+        packed._image = image  # the image tensor lives exactly as long as the handle built on it
         return image, packed, bool(packed.has_non_acgt)
 
     def adopt(self, image: torch.Tensor, length: int, K: int, has_non_acgt: bool):
-        self.keep.append(image)
-        return hamm.Packed.from_image(image.data_ptr(), image.numel(), length, K, has_non_acgt)
+        packed = hamm.Packed.from_image(image.data_ptr(), image.numel(), length, K, has_non_acgt)
+        packed._image = image
+        return packed
 
     def compute(self, packed, both: bool, b: int, e: int, out: torch.Tensor) -> int:
         """Enqueues the shard [b,e) on the current stream; out: int16[e-b] on the device."""
@@ -100,35 +110,54 @@ class CudaEngine:
         return out
 
 
+def _broadcast_packed(engine, concat, K: int, rank: int, world: int, group, extra=(), check=None):
+    """rank 0 packs `concat` (after running `check()`, if given); a status word, the length, the
+    non-ACGT flag and the integers of `extra` travel in ONE metadata broadcast, the packed image in
+    a second one.  A failure on rank 0 is raised on EVERY rank (ranks != 0 get a RuntimeError naming
+    it), so nobody is left waiting in a collective.  Returns (packed handle, length, extra values)."""
+    dev = engine.device
+    meta = torch.zeros(3 + len(extra), dtype=torch.int64, device=dev)
+    packed = image = err = None
+    if rank == 0:
+        try:
+            if check is not None:
+                check()
+            image, packed, non_acgt = engine.pack(concat, K)
+            meta = torch.tensor([0, len(concat), int(non_acgt), *[int(v) for v in extra]], dtype=torch.int64, device=dev)
+        except Exception as exc:  # carried to the other ranks below, then re-raised here
+            err = exc
+            meta[0] = 1
+    if world > 1:
+        dist.broadcast(meta, src=0, group=group)
+    vals = [int(v) for v in meta.tolist()]
+    if vals[0]:
+        if err is not None:
+            raise err
+        raise RuntimeError("rank 0 failed before the broadcast of the packed sequence set (its exception has the cause)")
+    length, non_acgt = vals[1], vals[2]
+    if rank != 0:
+        image = engine.empty_image(length)
+    if world > 1:
+        dist.broadcast(image, src=0, group=group)  # the one broadcast of this packed sequence set
+    if rank != 0:
+        packed = engine.adopt(image, length, K, bool(non_acgt))
+    return packed, length, vals[3:]
+
+
 def exhaustive_distributed_bands(concat: Optional[np.ndarray], K: int, both: bool, engine=None,
                                  group=None) -> Optional[np.ndarray]:
     """Full all-vs-all minima on the diagonal-band engine over the ranks of `group`.
 
     The symmetric formulation visits every unordered pair once and lowers both K-mers, so the
     PAIR MATRIX (interleaved groups of diagonals) is partitioned instead of the queries; every
-    rank keeps a complete minima array and the arrays meet in all_reduce(MIN) - once after the
-    sharded bootstrap, once after the bands.  rank 0 passes the concat and gets
-    uint16[len(concat)] (K+1 where no K-mer starts); other ranks get None."""
+    rank keeps a complete minima array and the arrays meet in all_reduce(MIN): after the sharded
+    bootstrap and (overlapped with the next slab, see bands_slabwise) after every slab.  rank 0
+    passes the concat and gets uint16[len(concat)] (K+1 where no K-mer starts); others get None."""
     rank = dist.get_rank(group)
     world = dist.get_world_size(group)
     if engine is None:
         engine = CudaEngine(torch.device("cuda", torch.cuda.current_device()))
-    dev = engine.device
-    meta = torch.zeros(2, dtype=torch.int64, device=dev)
-    packed = None
-    image = None
-    if rank == 0:
-        image, packed, non_acgt = engine.pack(concat, K)
-        meta = torch.tensor([len(concat), int(non_acgt)], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.broadcast(meta, src=0, group=group)
-    length, non_acgt = (int(v) for v in meta.tolist())
-    if rank != 0:
-        image = engine.empty_image(length)
-    if world > 1:
-        dist.broadcast(image, src=0, group=group)  # the one broadcast of the packed sequence set
-    if rank != 0:
-        packed = engine.adopt(image, length, K, bool(non_acgt))
+    packed, length, _ = _broadcast_packed(engine, concat, K, rank, world, group)
     best = engine.new_best(length, K)
     b, e = shard_bounds(0, length, world)[rank]
     engine.bootstrap(packed, both, b, e, best)
@@ -140,15 +169,35 @@ def exhaustive_distributed_bands(concat: Optional[np.ndarray], K: int, both: boo
     return engine.finalize(packed, best).cpu().numpy().view(np.uint16)
 
 
-def bands_slabwise(engine, packed, both: bool, rank: int, world: int, best: torch.Tensor, group=None) -> int:
-    """This rank's part of the pair matrix, slab by slab, with all_reduce(MIN) after every slab
-    (every rank runs the same number of slabs).  Returns the number of kernel launches."""
+def bands_slabwise(engine, packed, both: bool, rank: int, world: int, best: torch.Tensor, group=None,
+                   lag: int = 1) -> int:
+    """This rank's part of the pair matrix, slab by slab (every rank runs the same number of slabs).
+
+    After every slab the minima of all ranks meet in all_reduce(MIN), so that each rank thresholds
+    against what all of them have found.  The exchange works on a SNAPSHOT of `best` and is
+    asynchronous: slab j starts as soon as the exchange issued after slab j-1-lag has landed (its
+    result is folded in with an element-wise minimum), so with lag = 1 a collective overlaps the
+    following slab and no rank idles at a slab boundary waiting for the slowest one; lag = 0 is the
+    synchronous schedule.  Thresholds only need to be upper bounds of the final minima, which any
+    state of `best` is - the results do not depend on the schedule.  All exchanges are drained
+    before returning, the last one holding every rank's final minima.  Returns the kernel launches."""
     if world == 1:
         return engine.bands(packed, both, 0, 1, best)
     launches = 0
+    pending = []  # (work, snapshot) of exchanges in flight, oldest first
+
+    def land(n_keep: int):
+        while len(pending) > n_keep:
+            work, snap = pending.pop(0)
+            work.wait()  # NCCL: the current stream waits for the collective; the host does not block
+            torch.minimum(best, snap, out=best)
+
     for slab in range(engine.slab_count(packed, both, world)):
+        land(lag)
         launches += engine.slabs(packed, both, rank, world, slab, slab + 1, best)
-        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
+        snap = best.clone()
+        pending.append((dist.all_reduce(snap, op=dist.ReduceOp.MIN, group=group, async_op=True), snap))
+    land(0)
     return launches
 
 
@@ -163,31 +212,17 @@ def targeted_distributed(target: Optional[np.ndarray], probes: Optional[np.ndarr
     world = dist.get_world_size(group)
     if engine is None:
         engine = CudaEngine(torch.device("cuda", torch.cuda.current_device()))
-    dev = engine.device
     core = K // (R + 1)
-    if R < 1 or R > 10 or core < 4:
+    if R < 1 or R > 10 or core < 4:  # same arguments on every rank: raised everywhere
         raise ValueError("R outside 1..10 or K/(R+1) < 4 (hammings.cpp:399-404)")
     clamp = K // core  # the reference's "not found" value (SfxArray.cpp:4462-4463)
-    if rank == 0 and ((probes >= 4) & (probes < 7)).any():
-        raise ValueError("probe K-mers with N / InDel need the wildcard pass: use kit4b_b200.targeted")
-    handles = []
-    for concat in (target, probes):
-        meta = torch.zeros(2, dtype=torch.int64, device=dev)
-        packed = image = None
-        if rank == 0:
-            image, packed, non_acgt = engine.pack(concat, K)
-            meta = torch.tensor([len(concat), int(non_acgt)], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.broadcast(meta, src=0, group=group)
-        length, non_acgt = (int(v) for v in meta.tolist())
-        if rank != 0:
-            image = engine.empty_image(length)
-        if world > 1:
-            dist.broadcast(image, src=0, group=group)
-        if rank != 0:
-            packed = engine.adopt(image, length, K, bool(non_acgt))
-        handles.append((packed, length))
-    (t_img, _), (q_img, q_len) = handles
+
+    def check_probes():  # rank 0 only (it alone holds the probes): travels in the status word
+        if ((probes >= 4) & (probes < 7)).any():
+            raise ValueError("probe K-mers with N / InDel need the wildcard pass: use kit4b_b200.targeted")
+
+    q_img, q_len, _ = _broadcast_packed(engine, probes, K, rank, world, group, check=check_probes)
+    t_img, _, _ = _broadcast_packed(engine, target, K, rank, world, group)
     best = engine.new_best(q_len, K)
     b, e = shard_bounds(0, q_len, world)[rank]
     engine.seed(q_img, t_img, both, clamp, core, b, e, best)
@@ -204,7 +239,7 @@ def targeted_distributed(target: Optional[np.ndarray], probes: Optional[np.ndarr
 
 def exhaustive_distributed(concat: Optional[np.ndarray], K: int, both: bool, q_begin: int = 0,
                            q_end: Optional[int] = None, engine=None, group=None) -> Optional[np.ndarray]:
-    """All-vs-all minima with queries sharded over the ranks of `group`.
+    """All-vs-all minima with queries sharded over the ranks of `group` (POPC engine).
 
     rank 0 passes the concat (others pass None) and gets uint16[len(concat)] laid out like the
     reference's m_pHamDist (K+1 where nothing was computed); other ranks get None."""
@@ -215,20 +250,11 @@ def exhaustive_distributed(concat: Optional[np.ndarray], K: int, both: bool, q_b
     dev = engine.device
 
     # --- metadata, then ONE broadcast of the packed target set ---
-    meta = torch.zeros(4, dtype=torch.int64, device=dev)
-    packed = None
-    image = None
+    extra = ()
     if rank == 0:
-        image, packed, non_acgt = engine.pack(concat, K)
-        qe = len(concat) if q_end is None else min(q_end, len(concat))
-        meta = torch.tensor([len(concat), int(non_acgt), q_begin, qe], dtype=torch.int64, device=dev)
-    dist.broadcast(meta, src=0, group=group)
-    length, non_acgt, qb, qe = (int(v) for v in meta.tolist())
-    if rank != 0:
-        image = engine.empty_image(length)
-    dist.broadcast(image, src=0, group=group)
-    if rank != 0:
-        packed = engine.adopt(image, length, K, bool(non_acgt))
+        extra = (q_begin, len(concat) if q_end is None else min(q_end, len(concat)))
+    packed, length, (qb, qe) = _broadcast_packed(engine, concat, K, rank, world, group,
+                                                 extra=extra if rank == 0 else (0, 0))
 
     # --- every rank: its own query slice against all targets, no further exchange ---
     bounds = shard_bounds(qb, qe, world)

@@ -198,3 +198,74 @@ def test_two_rank_targeted_probe_shards(oracle, K, R, both):
     mp.spawn(_worker_targeted, args=(2, _free_port(), K, R, both, ret), nprocs=2, join=True)
     target, probes = _targeted_case()
     assert np.array_equal(ret["res"], oracle.targeted_brute(target, probes, K, R, both))
+
+
+def _worker_error(rank, world, port, which, ret):
+    """Rank 0 fails before the first broadcast; every rank must raise instead of blocking in it."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from kit4b_b200 import dist as kd
+
+    class FailingEngine(OracleEngine):
+        def pack(self, concat, K):
+            raise MemoryError("pack failed on rank 0")
+
+    try:
+        if which == "wildcard":
+            target, probes = _targeted_case() if rank == 0 else (None, None)
+            if rank == 0:
+                probes[10] = 4  # N in a probe: rejected by rank 0 only (it alone holds the probes)
+            kd.targeted_distributed(target, probes, 32, 3, True, engine=OracleEngine.for_k(32))
+        elif which == "pack_bands":
+            concat = random_genome(78, [300, 30, 260]) if rank == 0 else None
+            kd.exhaustive_distributed_bands(concat, 20, True, engine=FailingEngine.for_k(20))
+        else:
+            concat = random_genome(77, [900, 41, 700]) if rank == 0 else None
+            kd.exhaustive_distributed(concat, 25, True, engine=FailingEngine.for_k(25))
+        ret[rank] = "no error"
+    except Exception as exc:  # noqa: BLE001 - the test inspects the type
+        ret[rank] = type(exc).__name__
+    dist.barrier()  # reachable on every rank: nobody is stuck in the broadcast
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("which,rank0_error", [("wildcard", "ValueError"), ("pack_bands", "MemoryError"),
+                                                ("pack_shards", "MemoryError")])
+def test_rank0_failure_is_raised_on_every_rank(which, rank0_error):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_error, args=(2, _free_port(), which, ret), nprocs=2, join=True)
+    assert ret[0] == rank0_error and ret[1] == "RuntimeError"
+
+
+def _worker_bands_lag(rank, world, port, lag, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from kit4b_b200 import dist as kd
+    K, both = 20, True
+    concat = random_genome(78, [300, 30, 260])
+    eng = OracleEngine.for_k(K)
+    _, packed, _ = eng.pack(concat, K)
+    best = eng.new_best(len(concat), K)
+    kd.bands_slabwise(eng, packed, both, rank, world, best, lag=lag)
+    if rank == 0:
+        ret["res"] = best.numpy().copy()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("lag", [0, 1, 2])
+def test_slab_exchange_schedule_does_not_change_the_result(oracle, lag):
+    """bands_slabwise: synchronous (lag 0) and overlapped (lag >= 1) exchanges give the same minima."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_bands_lag, args=(2, _free_port(), lag, ret), nprocs=2, join=True)
+    concat = random_genome(78, [300, 30, 260])
+    want = oracle.exhaustive_brute(concat, 20, True).astype(np.int32)
+    got = ret["res"]
+    valid = want <= 20
+    assert np.array_equal(got[valid], want[valid])

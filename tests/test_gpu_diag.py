@@ -185,3 +185,72 @@ def test_band_engine_targeted_equals_popc_engine_at_scale():
         k4b.set_engine(hamm.ENGINE_DIAG)
     assert np.array_equal(got, want)
     assert (got[:2900] == 0).all() and got[got != 0xFF].max() <= 4 and (got == 0xFF).sum() < 5 * 32
+
+
+def test_window_table_path_equals_row_table_path(monkeypatch):
+    """The two two-plane instances of diag_min_kernel (K4B_DIAG_EWIN=1: per-thread mismatch-window
+    table in shared memory, the default; =0: per-warp row table + IMAD broadcast XOR) and both row
+    segment lengths give identical minima, exhaustive and rectangular (targeted) mode."""
+    c = random_genome(960, [350000, 60000, 900])
+    c[7000:9500] = c[200000:202500]
+    c[30000:30400] = np.array([3, 2, 1, 0, 4, 5, 6, 7], np.uint8)[c[250000:250400][::-1]]
+    c = np.ascontiguousarray(c)
+    probes = np.ascontiguousarray(np.concatenate([c[1000:9000], [7], random_genome(961, [5000])]), dtype=np.uint8)
+    probes[100] = (probes[100] + 1) % 4
+    res = {}
+    for ewin in ("1", "0"):
+        for rows in ("8192", "4096"):
+            monkeypatch.setenv("K4B_DIAG_EWIN", ewin)
+            monkeypatch.setenv("K4B_DIAG_ROWS", rows)
+            res[(ewin, rows)] = (k4b.exhaustive(c, 40, True), k4b.targeted(c, probes, 32, 3, True))
+    ref = res[("0", "4096")]
+    for key, (ex, tg) in res.items():
+        assert np.array_equal(ex, ref[0]), key
+        assert np.array_equal(tg, ref[1]), key
+
+
+def _numpy_min_distance(concat, valid, K, q, both, self_pos):
+    """Independent check: minimum distance of the K-mer q (codes 0..3) to every valid K-mer of
+    concat (forward, excluding self_pos; reverse complement incl. self), K passes over the array."""
+    M = len(concat) - K + 1
+    best = K + 1
+    for strand in range(2 if both else 1):
+        kq = q if strand == 0 else (3 - q[::-1])
+        acc = np.zeros(M, dtype=np.uint8)
+        for p in range(K):
+            acc += concat[p:p + M] != kq[p]
+        acc = acc.astype(np.int32)
+        acc[~valid[:M]] = K + 1
+        if strand == 0:
+            acc[self_pos] = K + 1
+        best = min(best, int(acc.min()))
+    return best
+
+
+def test_band_engine_at_config2_size_against_popc_samples_and_brute_force():
+    """BASELINE configs[1] size (10 Mbp multifasta, K=50, both strands): the band result is compared
+    with the POPC engine on 64 x 256 sampled query K-mers (k4b_hamm_exhaustive_shard, a different
+    kernel and formulation) and with a NumPy brute force on 6 of them."""
+    import bench
+    concat, chroms, K, both = bench.synth_genome("cfg2")
+    got = k4b.exhaustive(concat, K, both)
+    L = len(concat)
+    rng = np.random.default_rng(5)
+    starts = sorted(int(v) for v in rng.integers(0, L - 300, size=64))
+    starts[0] = 0
+    starts[-1] = L - 256                      # the tail: positions without a K-mer report K+1
+    starts[10] = chroms[1][1] - 128           # across a chromosome boundary
+    k4b.set_engine(hamm.ENGINE_POPC)
+    try:
+        for b in starts:
+            want = np.full(L, K + 1, dtype=np.uint16)
+            hamm.exhaustive_shard(concat, K, both, b, b + 256, want)
+            assert np.array_equal(got[b:b + 256], want[b:b + 256]), b
+    finally:
+        k4b.set_engine(hamm.ENGINE_DIAG)
+    valid = np.zeros(L, dtype=bool)
+    for _, st, n in chroms:
+        valid[st:st + max(0, n - K + 1)] = True
+    for pos in (starts[3], starts[20] + 7, chroms[2][1] + 11, starts[40], chroms[4][1] + 5, starts[55] + 100):
+        assert valid[pos]
+        assert got[pos] == _numpy_min_distance(concat, valid, K, concat[pos:pos + K], both, pos), pos
