@@ -475,9 +475,12 @@ def _profile_note(key):
     """figures of the committed ncu --set full capture of a kernel (profiles/dram_bytes.json, written
     by tools/ncu_summary.py): per-launch DRAM traffic and pipe utilisation"""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "dram_bytes.json"))).get(key) or {}
+        v = json.load(open(os.path.join(ROOT, "profiles", "dram_bytes.json"))).get(key)
     except Exception:
         return {}
+    if isinstance(v, (int, float)):
+        return {"dram_bytes_per_launch": v}
+    return v or {}
 
 
 # ------------------------------------------------------------------------------------------
@@ -678,11 +681,11 @@ def targeted_leg(c, scale, steps, warmup, e2e_steps, with_cpu):
     L = len(probes)
     best = torch.empty(L, dtype=torch.int32, device=c.dev)
     out = torch.empty(L, dtype=torch.int16, device=c.dev)
-    qb, qe = c.kdist.shard_bounds(0, L, c.world)[c.rank]
 
-    def step():
+    def step():  # this rank: its share of the index buckets, every probe K-mer
         hamm.best_init_device(best.data_ptr(), L, K, c.stream.cuda_stream)
-        n = 1 + hamm.targeted_seed_device(q_img, t_img, both, clamp, core, qb, qe, best.data_ptr(), c.stream.cuda_stream)
+        n = 1 + hamm.targeted_seed_part_device(q_img, t_img, both, clamp, core, c.rank, c.world, best.data_ptr(),
+                                               c.stream.cuda_stream)
         if c.world > 1:
             c.dist.all_reduce(best, op=c.dist.ReduceOp.MIN)
         if c.rank == 0:
@@ -801,7 +804,7 @@ def targeted_leg(c, scale, steps, warmup, e2e_steps, with_cpu):
             "comparisons_per_step": cmps, "probe_kmers": int(Nq), "target_kmers": int(Nt),
             "engine": "seed-and-verify (pigeonhole cores of %d bases, bucket index with flank signatures, %s)"
                       % (core, "bucket-major join" if join else "warp per item"),
-            "parallelism": "probe shards x%d + all_reduce(MIN)" % c.world,
+            "parallelism": "index-bucket shards x%d (each rank builds 1/%d of the index, answers all probes) + all_reduce(MIN)" % (c.world, c.world),
             "e2e": e2e, "roofline": roofline, "result_checksum": checksum, "parity": parity, "cpu_baseline": cpu,
             "gpu_launches": launches, "clocks": clocks}
 

@@ -66,7 +66,11 @@ const char *k4b_last_error(void);
  *                   defaults 1 and m_GenomeLen (= concat_len+2) select every pair
  *   out_min      concat_len entries PRE-FILLED by the caller (K+1, hammings.cpp:3120-3122);
  *                   lowered (min) at valid K-mer start positions only
- * Queries are sharded over all initialised GPUs; minima are gathered on the host. */
+ * Engine and multi-GPU partition (all k4b_gpu_init devices are used, one NCCL broadcast of the
+ * packed set first): a full sweep of >= 200 kb runs on the diagonal-band engine - the PAIR MATRIX
+ * is partitioned over the devices, every device keeps a complete minima array and the arrays meet
+ * in ncclAllReduce(min) after every slab; sweep sub-ranges and small inputs run on the POPC
+ * all-pairs engine with the QUERIES sharded and the per-device minima concatenated on the host. */
 int k4b_hamm_exhaustive(const uint8_t *concat, uint32_t concat_len, uint32_t K, int both_strands,
                         uint32_t sweep_start, uint32_t sweep_end, uint16_t *out_min);
 
@@ -81,7 +85,10 @@ int k4b_hamm_exhaustive_shard(const uint8_t *concat, uint32_t concat_len, uint32
 /* ---- targeted probes-vs-assembly (-m0 -I) -------------------------------------------------- */
 
 /* Replaces RestrictedHammingThread + CSfxArray::LocateHammings (hammings.cpp:1593-1708,
- * SfxArray.cpp:4227-4627) by exact brute force on the GPU.
+ * SfxArray.cpp:4227-4627).  Whole probe sets of pure ACGT (cores of >= 6 bases) run on the
+ * seed-and-verify engine - the reference's pigeonhole search on a bucket index, without its depth
+ * cut-offs, each device building and joining its share of the index buckets; wildcard probe
+ * K-mers, probe sub-ranges and short cores run on the exact brute-force engines (bands / POPC).
  *   target_concat/target_len  the .sfx sequence area: each entry's bases followed by EOS
  *                             (SfxArray.cpp:1746-1750)
  *   probe_concat/probe_len    probes in the LoadGenome layout (hammings.cpp:2201-2310); NULL
@@ -112,7 +119,8 @@ typedef struct k4b_packed k4b_packed; /* opaque: bit-plane packed sequence set o
 
 /* bytes of one device-resident packed image for a concat of this length (for NCCL broadcast) */
 size_t k4b_packed_image_bytes(uint32_t concat_len);
-/* Packs a HOST concat (H2D copy + pack kernel on the current device of this process). */
+/* Packs a HOST concat (H2D copy + pack kernel on the current device of this process).  An image is
+ * 6 arrays: bit-planes 0-2, the valid-K-mer-start plane, and a 2-bit-per-base code array (2 arrays). */
 int k4b_pack_host(const uint8_t *concat, uint32_t concat_len, uint32_t K, k4b_packed **out);
 /* Packs a DEVICE-resident concat (16-byte aligned; pack + valid-start kernels only). */
 int k4b_pack_device(const void *d_concat, uint32_t concat_len, uint32_t K, void *stream,
@@ -201,11 +209,26 @@ int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets, int both_s
 int k4b_targeted_seed_device(k4b_packed *probes, k4b_packed *targets, int both_strands, uint32_t clamp,
                              uint32_t core_len, uint32_t q_begin, uint32_t q_end, uint32_t *d_best,
                              void *stream, int *launches);
-/* Work of the most recent k4b_targeted_seed_device call of this thread: bucket entries streamed by
- * the query kernel (12 bytes each) and cores held by the index.  Blocks until that call finished. */
+/* Same engine, split by INDEX BUCKETS instead of probes: part `part` of `nparts` indexes only its
+ * share of the core buckets (1/nparts of the index build) and answers every probe K-mer for those
+ * buckets.  Parts combine by an element-wise minimum of d_best (e.g. ncclAllReduce(min)). */
+int k4b_targeted_seed_part_device(k4b_packed *probes, k4b_packed *targets, int both_strands, uint32_t clamp,
+                                  uint32_t core_len, uint32_t part, uint32_t nparts, uint32_t *d_best,
+                                  void *stream, int *launches);
+/* Work of the most recent seed-engine call of this thread: bucket entries tested by the query
+ * kernel (16-byte entries) and cores held by the index.  Blocks until that call finished. */
 int k4b_last_seed_info(uint64_t *occurrences, uint64_t *indexed_cores);
 int k4b_targeted_finalize_device(k4b_packed *probes, const uint32_t *d_best, uint32_t clamp,
                                  uint16_t *d_out_min, void *stream);
+
+/* ---- distribution of the minima -------------------------------------------------------------
+ * The table `hammings` logs after an exhaustive run (hammings.cpp:2939-2962) and the downstream
+ * HammingDist tool tabulates from the CSV (HammingDist/HammingDist.cpp:371-705): hist[d] = number of
+ * positions whose minimum is d (d = 0..K); hist[K+1] collects the positions where no K-mer starts
+ * (they hold K+1).  hist has K+2 entries.  Host-buffer form and device form (d_hist is zeroed by the
+ * callee; asynchronous on `stream`). */
+int k4b_hamm_histogram(const uint16_t *min, uint32_t n, uint32_t K, uint64_t *hist);
+int k4b_histogram_device(const uint16_t *d_min, uint32_t n, uint32_t K, unsigned long long *d_hist, void *stream);
 
 /* ---- integer-pipe roofline microbenchmark ----------------------------------- */
 /* which: 0 POPC only, 1 LOP3 only, 2 engine mix (2 LOP3 + 1 POPC + min), 3 IADD3 only.

@@ -118,7 +118,7 @@ void print_usage(const char *prog) {
     printf(
         "%s hammings [-hv] [-f <int>] [-F <file>] [-m <int>] [-p <str>] [-s <int>] [-r <int>] [-S <int>] [-c] "
         "[-z <int>] [-n <int>] [-N <int>] [-b <int>] [-B <int>] [-K <int>] [-k <int>] -i <file> [-I <file>] "
-        "[-o <file>] [-T <int>] [--gpus=<int>]\n",
+        "[-o <file>] [-T <int>] [--gpus=<int>] [--dist=<file>]\n",
         prog);
     printf(
         "  -h, --help                print this help and exit\n"
@@ -145,7 +145,8 @@ void print_usage(const char *prog) {
         "  -k, --sample=<int>        sample every Nth sweep instance / K-mer (default is 1)\n"
         "  -o, --out=<file>          output (merged) Hamming distances to this file\n"
         "  -T, --threads=<int>       number of host threads 0..128 (accepted for compatibility; the engine runs on the GPUs)\n"
-        "      --gpus=<int>          number of B200 GPUs to shard the query K-mers over (default 0 = all visible)\n");
+        "      --gpus=<int>          number of B200 GPUs to use (default 0 = all visible)\n"
+        "      --dist=<file>         (-m1/-m2) also write the distribution of the minima in the HammingDist tool's format\n");
 }
 
 int parse_args(int argc, char **argv, Options &o, std::string &err) {
@@ -161,7 +162,7 @@ int parse_args(int argc, char **argv, Options &o, std::string &err) {
         {"seqlen", required_argument, nullptr, 'K'},   {"in", required_argument, nullptr, 'i'},
         {"seq", required_argument, nullptr, 'I'},      {"sample", required_argument, nullptr, 'k'},
         {"out", required_argument, nullptr, 'o'},      {"threads", required_argument, nullptr, 'T'},
-        {"gpus", required_argument, nullptr, 1000},    {nullptr, 0, nullptr, 0}};
+        {"gpus", required_argument, nullptr, 1000},    {"dist", required_argument, nullptr, 1001},    {nullptr, 0, nullptr, 0}};
     bool have_in = false;
     optind = 0;  // full re-initialisation of glibc getopt
     opterr = 0;
@@ -194,6 +195,7 @@ int parse_args(int argc, char **argv, Options &o, std::string &err) {
             case 'k': if (!want_int("-k|--sample=<int>", o.sample)) return -1; break;
             case 'T': if (!want_int("-T|--threads=<int>", o.threads)) return -1; break;
             case 1000: if (!want_int("--gpus=<int>", o.gpus)) return -1; break;
+            case 1001: o.dist_file = optarg; break;
             case 'F': o.log_file = optarg; break;
             case 'p': o.prefix = optarg; break;
             case 'i': o.in_file = optarg; have_in = true; break;

@@ -12,6 +12,8 @@
 
 #include "k4b_host.h"
 
+#include <zlib.h>
+
 namespace k4bhost {
 
 namespace {
@@ -190,15 +192,19 @@ int write_bioseq(const std::string &path, const std::vector<SeqEntry> &entries,
     return kOk;
 }
 
+// FASTA, plain or gzip-compressed (zlib's gzFile reads both).  Rules of the reference's front end
+// (genbioseq -> CFasta): descriptor lines start with '>', the entry name is the first
+// whitespace-delimited token, at most 80 characters (genbioseq.cpp:402-404, commdefs.h:140);
+// sequence symbols aAcCgGtTuU -> 0..3 with the soft-mask flag on lower case, '-' -> InDel (6), any
+// other letter -> N (4), everything else is dropped (Fasta.cpp:1167, :1658-1705).
 int read_fasta(const std::string &path, std::vector<SeqEntry> &entries, std::string &err) {
     entries.clear();
-    std::ifstream in(path);
+    gzFile in = gzopen(path.c_str(), "rb");
     if (!in) {
         err = "unable to open '" + path + "'";
         return kErrOpnFile;
     }
-    // symbol map: aAcCgGtTuU -> 0..3 (lower case sets the soft-mask flag), '-' -> InDel (6), any
-    // other letter -> N (4); everything else is dropped
+    gzbuffer(in, 1 << 20);
     uint8_t map[256];
     memset(map, 0xff, sizeof(map));
     for (int c = 'a'; c <= 'z'; ++c) map[c] = map[c - 32] = 4;
@@ -210,29 +216,111 @@ int read_fasta(const std::string &path, std::vector<SeqEntry> &entries, std::str
     map['u'] = 3 | 0x08;
     map['U'] = 3;
     map['-'] = 6;
-    std::string line;
-    bool have = false;
-    while (std::getline(in, line)) {
-        if (!line.empty() && line[0] == '>') {
-            SeqEntry se;
-            size_t b = 1;
-            while (b < line.size() && isspace((unsigned char)line[b])) ++b;
-            size_t e = b;
-            while (e < line.size() && !isspace((unsigned char)line[e])) ++e;
-            se.name = line.substr(b, std::min<size_t>(e - b, 80));
-            entries.push_back(std::move(se));
-            have = true;
-        } else if (have) {
-            std::vector<uint8_t> &c = entries.back().codes;
-            for (unsigned char ch : line)
-                if (map[ch] != 0xff) c.push_back(map[ch]);
+    std::vector<unsigned char> buf(4 << 20);
+    std::string descr;       // descriptor line being collected (may span read chunks)
+    bool in_descr = false, at_line_start = true, have = false;
+    int n;
+    while ((n = gzread(in, buf.data(), (unsigned)buf.size())) > 0) {
+        for (int k = 0; k < n; ++k) {
+            const unsigned char ch = buf[k];
+            if (in_descr) {
+                if (ch == '\n') {
+                    SeqEntry se;
+                    size_t b = 0;
+                    while (b < descr.size() && isspace((unsigned char)descr[b])) ++b;
+                    size_t e = b;
+                    while (e < descr.size() && !isspace((unsigned char)descr[e])) ++e;
+                    se.name = descr.substr(b, std::min<size_t>(e - b, 80));
+                    entries.push_back(std::move(se));
+                    have = true;
+                    in_descr = false;
+                    at_line_start = true;
+                } else {
+                    descr.push_back((char)ch);
+                }
+                continue;
+            }
+            if (ch == '\n') {
+                at_line_start = true;
+                continue;
+            }
+            if (at_line_start && ch == '>') {
+                in_descr = true;
+                descr.clear();
+                continue;
+            }
+            at_line_start = false;
+            if (have && map[ch] != 0xff) entries.back().codes.push_back(map[ch]);
         }
+    }
+    int zerr = 0;
+    const char *zmsg = gzerror(in, &zerr);
+    const bool bad = n < 0 || (zerr != Z_OK && zerr != Z_STREAM_END);
+    const std::string zs = zmsg ? zmsg : "";
+    gzclose(in);
+    if (bad) {
+        err = "error while reading '" + path + "': " + zs;
+        return kErrFileAccess;
+    }
+    if (in_descr) {  // descriptor on the last line without a newline: an entry without sequence
+        SeqEntry se;
+        size_t e = 0;
+        while (e < descr.size() && !isspace((unsigned char)descr[e])) ++e;
+        se.name = descr.substr(0, std::min<size_t>(e, 80));
+        entries.push_back(std::move(se));
+        have = true;
     }
     if (!have) {
         err = "'" + path + "' holds no FASTA descriptor line";
         return kErrParse;
     }
     return kOk;
+}
+
+// 'b' bioseq container, 's' suffix-array container, 'f' FASTA (plain or gzip), 0 unknown / unreadable
+int sniff_format(const std::string &path) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return 0;
+    unsigned char m[4] = {0, 0, 0, 0};
+    const size_t got = fread(m, 1, 4, f);
+    fclose(f);
+    if (got >= 4 && !memcmp(m, "bios", 4)) return 'b';
+    if (got >= 4 && !memcmp(m, "sfx5", 4)) return 's';
+    if (got >= 2 && m[0] == 0x1f && m[1] == 0x8b) return 'f';
+    for (size_t k = 0; k < got; ++k) {
+        if (m[k] == '>') return 'f';
+        if (!isspace(m[k])) return 0;
+    }
+    return 0;
+}
+
+// sequences from a bioseq container or straight from FASTA / FASTA.gz (skipping genbioseq)
+int read_sequences(const std::string &path, std::vector<SeqEntry> &entries, std::string &title, std::string &err) {
+    if (sniff_format(path) == 'f') {
+        title = path;
+        return read_fasta(path, entries, err);
+    }
+    return read_bioseq(path, entries, title, err);
+}
+
+// the sequence area an `index` run would have produced for these entries: every entry's bases (mask
+// stripped) followed by EOS (SfxArray.cpp:1746-1750) - all the GPU engines need of a suffix array file
+void sfx_from_entries(const std::vector<SeqEntry> &entries, const std::string &title, SfxData &out) {
+    out = SfxData();
+    out.title = title;
+    out.version = 5;
+    uint64_t total = 0;
+    for (const SeqEntry &e : entries) total += e.codes.size() + 1;
+    out.seq.reserve(total);
+    for (const SeqEntry &e : entries) {
+        SfxEntry se;
+        se.name = e.name;
+        se.len = (uint32_t)e.codes.size();
+        se.start = out.seq.size();
+        for (uint8_t c : e.codes) out.seq.push_back(c & 0x07);
+        out.seq.push_back(7);
+        out.entries.push_back(std::move(se));
+    }
 }
 
 int read_sfx(const std::string &path, SfxData &out, std::string &err) {

@@ -77,7 +77,7 @@ static int gpu_ready() {
 static int run_exhaustive(const Options &o) {
     std::vector<SeqEntry> entries;
     std::string title, err;
-    int rc = read_bioseq(o.in_file, entries, title, err);
+    int rc = read_sequences(o.in_file, entries, title, err);  // bioseq, or FASTA / FASTA.gz directly
     if (rc) {
         logmsg(0, "%s", err.c_str());
         logmsg(0, "Unable to open assembly sequence file '%s'", o.in_file.c_str());
@@ -125,10 +125,21 @@ static int run_exhaustive(const Options &o) {
             return rc;
         }
     }
-    // distribution to the log (hammings.cpp:2939-2962)
+    // distribution to the log (hammings.cpp:2939-2962): GPU histogram of the minima; positions without a
+    // K-mer hold K+1 and fall into the last bin
     std::vector<uint64_t> hist(K + 2, 0);
-    for (const Chrom &c : g.chroms)
-        for (uint32_t i = 0; i < c.num_subseqs; ++i) hist[std::min<uint32_t>(hd[c.start + i], K + 1)]++;
+    if ((rc = k4b_hamm_histogram(hd.data(), flat, K, hist.data()))) {
+        logmsg(0, "Histogram of the minima failed (%d): %s", rc, k4b_last_error());
+        return rc;
+    }
+    if (!o.dist_file.empty()) {  // extension: the HammingDist tool's file without the CSV round trip
+        std::vector<uint64_t> counts(hist.begin(), hist.begin() + K + 1);
+        logmsg(2, "Writing the distribution of the minima to file: '%s'", o.dist_file.c_str());
+        if ((rc = write_hamming_distribution(o.dist_file, counts, err))) {
+            logmsg(0, "%s", err.c_str());
+            return rc;
+        }
+    }
     logmsg(2, "Distribution:\nEditDist,Freq,Proportion");
     for (uint32_t d = 0; d < std::min(66u, K); ++d)
         printf("%u,%llu,%1.3f\n", d, (unsigned long long)hist[d],
@@ -140,8 +151,18 @@ static int run_exhaustive(const Options &o) {
 static int run_restricted(const Options &o) {
     std::string err, title;
     SfxData sfx;
-    logmsg(2, "Loading suffix array file '%s'", o.in_file.c_str());
-    int rc = read_sfx(o.in_file, sfx, err);
+    int rc;
+    if (sniff_format(o.in_file) == 's') {
+        logmsg(2, "Loading suffix array file '%s'", o.in_file.c_str());
+        rc = read_sfx(o.in_file, sfx, err);
+    } else {
+        // extension: the assembly as bioseq / FASTA / FASTA.gz - only the sequence area of a suffix
+        // array file is ever used here, and it is fully determined by the entries
+        logmsg(2, "Loading assembly sequences '%s' (no suffix array file needed)", o.in_file.c_str());
+        std::vector<SeqEntry> asm_entries;
+        rc = read_sequences(o.in_file, asm_entries, title, err);
+        if (!rc) sfx_from_entries(asm_entries, title, sfx);
+    }
     if (rc) {
         logmsg(0, "%s", err.c_str());
         logmsg(0, "Unable to open input bioseq suffix array file '%s'", o.in_file.c_str());
@@ -156,7 +177,7 @@ static int run_restricted(const Options &o) {
     double secs = 0;
     if (sep_probes) {
         std::vector<SeqEntry> entries;
-        rc = read_bioseq(o.in_seq_file, entries, title, err);
+        rc = read_sequences(o.in_seq_file, entries, title, err);
         if (rc) {
             logmsg(0, "%s", err.c_str());
             logmsg(0, "Unable to open assembly sequence file '%s'", o.in_seq_file.c_str());

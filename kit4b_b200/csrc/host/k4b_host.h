@@ -37,8 +37,13 @@ int read_bioseq(const std::string &path, std::vector<SeqEntry> &entries, std::st
 // minimal writer of the same container (used by the FASTA front end and by tests)
 int write_bioseq(const std::string &path, const std::vector<SeqEntry> &entries,
                  const std::string &title, std::string &err);
-// FASTA text -> entries (libkit4b/Fasta.cpp:1658-1705 Ascii2Sense, :1167; genbioseq.cpp:402-404)
+// FASTA text, plain or gzip -> entries (libkit4b/Fasta.cpp:967-1209, :1658-1705 Ascii2Sense, :1167;
+// genbioseq.cpp:402-404)
 int read_fasta(const std::string &path, std::vector<SeqEntry> &entries, std::string &err);
+// 'b' bioseq, 's' suffix array, 'f' FASTA (plain or gzip), 0 unknown; and the reader the CLI uses for
+// -i (-m1/-m2) and -I: a bioseq container or, skipping genbioseq, FASTA / FASTA.gz directly
+int sniff_format(const std::string &path);
+int read_sequences(const std::string &path, std::vector<SeqEntry> &entries, std::string &title, std::string &err);
 
 // 'sfx5' suffix-array container: only the entries and the concatenated sequence are read
 // (libkit4b/SfxArray.h:98-123, :194-207; SfxArray.cpp:499-580, :629-825)
@@ -54,6 +59,9 @@ struct SfxData {
     std::vector<uint8_t> seq;  // ConcatSeqLen bytes: each entry's bases followed by EOS (7)
 };
 int read_sfx(const std::string &path, SfxData &out, std::string &err);
+// what `index` would lay out for these entries (bases + EOS per entry): lets -m0 take its -i assembly
+// as bioseq or FASTA, no suffix-array file needed (the GPU engines never read the suffix array)
+void sfx_from_entries(const std::vector<SeqEntry> &entries, const std::string &title, SfxData &out);
 
 // ---- concatenated layout (hammings.cpp:2981-3134 LoadGenome) -------------------------------
 struct Chrom {
@@ -106,6 +114,19 @@ int merge_hamming_csv(const std::string &from, const std::string &into, std::str
 int csv_to_bham(const std::string &csv, const std::string &bham, std::string &err);
 int bham_to_csv(const std::string &bham, const std::string &csv, std::string &err);
 
+// ---- HammingDist (HammingDist/HammingDist.cpp:371-705), region-less mode -----------------------------
+// Distribution file of the reference's downstream tool: header `,"All","Proportion All","Cumulative All"`,
+// then one row `\n<d>,<count>,<proportion %f>,<cumulative %f>` for d = 0 .. max-1 (the reference's loops
+// stop BEFORE the largest value seen, :631-641; kept, so the proportions are over the rows shown).
+// counts[d] = number of K-mers whose minimum Hamming distance is d.
+int write_hamming_distribution(const std::string &path, const std::vector<uint64_t> &counts, std::string &err);
+// counts from `"chrom",loci,hamming` CSV files (hammings -m1 / -m5 output): field 3 is the distance - the
+// reference's INTENDED semantics; its region-less mode never assigns the variable it histograms
+// (HammingDist.cpp:380, :437-446, :472-478), so there is no reference output to be bit-exact with.
+// Leading header lines and the `G,b,B` descriptor row of -m1 files are skipped.
+int hamming_counts_from_csv(const std::vector<std::string> &files, std::vector<uint64_t> &counts, uint64_t &rows,
+                            std::string &err);
+
 // ---- CLI ----------------------------------------------------------------------------------------
 struct Options {
     int mode = 0;            // -m (default 0 = restricted, hammings.cpp:312)
@@ -123,6 +144,7 @@ struct Options {
     int file_log_level = 3;  // -f
     int threads = 0;         // -T
     int gpus = 0;            // --gpus (extension; 0 = all visible)
+    std::string dist_file;   // --dist (extension, -m1/-m2): HammingDist-format distribution of the minima
     bool help = false, version = false;
 };
 // returns 0, or -1 after printing the problem (caller prints usage and exits 1)

@@ -128,6 +128,17 @@ int k4bh_bham_to_csv(const char *bham, const char *csv) {
     return rc ? set_err(rc, err) : 0;
 }
 
+// HammingDist region-less mode: distribution file of the `"chrom",loci,hamming` rows of n CSV files
+int k4bh_hamming_dist(int n, const char **csvs, const char *out) {
+    std::vector<std::string> files(csvs, csvs + n);
+    std::vector<uint64_t> counts;
+    uint64_t rows = 0;
+    std::string err;
+    int rc = hamming_counts_from_csv(files, counts, rows, err);
+    if (!rc) rc = write_hamming_distribution(out, counts, err);
+    return rc ? set_err(rc, err) : 0;
+}
+
 // parses a command line (argv[0] = program); fills ints[0..15] and strs (4 x 512 chars:
 // in, inseq, out, prefix).  Returns 0, or -1 with k4bh_last_error() set.
 int k4bh_parse_cli(int argc, char **argv, int *ints, char *strs) {

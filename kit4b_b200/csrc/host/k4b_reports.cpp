@@ -553,4 +553,125 @@ int bham_to_csv(const std::string &bham, const std::string &csv, std::string &er
     return out.close_sync(err);
 }
 
+// ---- HammingDist, region-less mode (HammingDist/HammingDist.cpp:371-705) ------------------------------
+int write_hamming_distribution(const std::string &path, const std::vector<uint64_t> &counts, std::string &err) {
+    long maxh = -1;
+    for (size_t d = 0; d < counts.size(); ++d)
+        if (counts[d]) maxh = (long)d;
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) {
+        err = "Unable to create " + path + " - " + strerror(errno);
+        return kErrCreateFile;
+    }
+    if (maxh >= 0) {  // "any to report?" (:616)
+        fputs(",\"All\",\"Proportion All\",\"Cumulative All\"", f);
+        uint64_t total = 0;
+        for (long d = 0; d < maxh; ++d) total += counts[d];  // the reference's loops exclude the largest value (:631)
+        double cumulative = 0.0;
+        for (long d = 0; d < maxh; ++d) {
+            const double prop = total ? (double)counts[d] / (double)total : 0.0;
+            cumulative += prop;
+            fprintf(f, "\n%ld,%llu,%f,%f", d, (unsigned long long)counts[d], prop, cumulative);
+        }
+    }
+    const bool ok = fflush(f) == 0 && fsync(fileno(f)) == 0;
+    fclose(f);
+    if (!ok) {
+        err = "Error on write to file '" + path + "'";
+        return kErrFileAccess;
+    }
+    return kOk;
+}
+
+namespace {
+// one CSV line -> fields (double quotes stripped; quoted[i] tells whether field i was quoted)
+void split_csv(const std::string &line, std::vector<std::string> &fields, std::vector<bool> &quoted) {
+    fields.clear();
+    quoted.clear();
+    size_t i = 0;
+    const size_t n = line.size();
+    while (i <= n) {
+        while (i < n && (line[i] == ' ' || line[i] == '\t')) ++i;
+        std::string v;
+        bool q = false;
+        if (i < n && line[i] == '"') {
+            q = true;
+            ++i;
+            while (i < n && line[i] != '"') v.push_back(line[i++]);
+            while (i < n && line[i] != ',') ++i;
+        } else {
+            while (i < n && line[i] != ',') v.push_back(line[i++]);
+            while (!v.empty() && (v.back() == ' ' || v.back() == '\r' || v.back() == '\t')) v.pop_back();
+        }
+        fields.push_back(v);
+        quoted.push_back(q);
+        if (i >= n) break;
+        ++i;  // the comma
+        if (i == n) {  // trailing comma: one more empty field
+            fields.emplace_back();
+            quoted.push_back(false);
+            break;
+        }
+    }
+}
+bool is_number(const std::string &s) {
+    if (s.empty()) return false;
+    char *end = nullptr;
+    strtod(s.c_str(), &end);
+    return end && *end == '\0';
+}
+}  // namespace
+
+int hamming_counts_from_csv(const std::vector<std::string> &files, std::vector<uint64_t> &counts, uint64_t &rows,
+                            std::string &err) {
+    counts.clear();
+    rows = 0;
+    std::vector<std::string> fields;
+    std::vector<bool> quoted;
+    for (const std::string &path : files) {
+        std::ifstream in(path);
+        if (!in) {
+            err = "Unable to open file: " + path;
+            return kErrOpnFile;
+        }
+        std::string line;
+        uint64_t processed = 0, lineno = 0;
+        while (std::getline(in, line)) {
+            ++lineno;
+            if (line.empty() || line == "\r") continue;
+            split_csv(line, fields, quoted);
+            if (fields.size() < 3) {
+                err = "Expected 3+ fields in '" + path + "', line " + std::to_string(lineno);
+                return kErrParse;
+            }
+            if (!processed) {
+                // CCSVFile::IsLikelyHeaderLine (CSVFile.cpp:757-789): every field quoted or non-numeric, <= 2 empty
+                bool header = true;
+                int empty = 0;
+                for (size_t k = 0; k < fields.size() && header; ++k) {
+                    if (quoted[k]) continue;
+                    if (fields[k].empty()) {
+                        if (++empty > 2) header = false;
+                        continue;
+                    }
+                    if (is_number(fields[k])) header = false;
+                }
+                if (header) continue;
+                // the `m_GenomeLen,SSeqStart,SSeqEnd` descriptor row of -m1 output (hammings.cpp:2899): no chromosome name
+                if (!quoted[0] && is_number(fields[0])) continue;
+            }
+            ++processed;
+            const long h = atol(fields[2].c_str());
+            if (h < 0 || h > 65535) {
+                err = "Hamming distance " + std::to_string(h) + " out of range in '" + path + "', line " + std::to_string(lineno);
+                return kErrParse;
+            }
+            if ((size_t)h >= counts.size()) counts.resize((size_t)h + 1, 0);
+            ++counts[(size_t)h];
+        }
+        rows += processed;
+    }
+    return kOk;
+}
+
 }  // namespace k4bhost

@@ -75,11 +75,55 @@ struct Engine {
     std::vector<int> devs;
     std::vector<cudaStream_t> streams;
     std::vector<ncclComm_t> comms;
+    // pinned host staging for results, one grow-only buffer per device slot: cudaMallocHost costs
+    // milliseconds (hundreds for a gigabyte), the host-buffer entry points would pay it per call
+    std::vector<void *> pinned;
+    std::vector<size_t> pinned_bytes;
     NcclApi nccl;
     bool inited = false;
 };
 static Engine g_eng;
 static std::mutex g_mu;
+
+// Stream-ordered device scratch from the retained default pool (k4b_gpu_init sets the release
+// threshold to "never"): after the first call of a given size an allocation is a pointer bump, and
+// the destructor returns the block on every path, early error returns included.
+struct DevScratch {
+    void *p = nullptr;
+    cudaStream_t st = nullptr;
+    DevScratch() = default;
+    DevScratch(const DevScratch &) = delete;
+    DevScratch &operator=(const DevScratch &) = delete;
+    ~DevScratch() { release(); }
+    cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+        release();
+        st = stream;
+        return cudaMallocAsync(&p, bytes ? bytes : 16, stream);
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, st);
+        p = nullptr;
+    }
+    template <typename T>
+    T *as() const { return static_cast<T *>(p); }
+};
+
+static void *pinned_result(int slot, size_t bytes) {
+    if ((size_t)slot >= g_eng.pinned.size()) return nullptr;
+    if (g_eng.pinned_bytes[slot] < bytes) {
+        if (g_eng.pinned[slot]) cudaFreeHost(g_eng.pinned[slot]);
+        g_eng.pinned[slot] = nullptr;
+        g_eng.pinned_bytes[slot] = 0;
+        const size_t want = bytes + bytes / 8 + 4096;
+        if (cudaMallocHost(&g_eng.pinned[slot], want) != cudaSuccess) {
+            cudaGetLastError();
+            g_eng.pinned[slot] = nullptr;
+            return nullptr;
+        }
+        g_eng.pinned_bytes[slot] = want;
+    }
+    return g_eng.pinned[slot];
+}
 
 static int load_nccl(NcclApi &n) {
     if (n.h) return 0;
@@ -120,6 +164,8 @@ extern "C" int k4b_gpu_init(int n_gpus, const int *device_ids) {
         g_eng.devs.push_back(d);
     }
     g_eng.streams.assign(n_gpus, nullptr);
+    g_eng.pinned.assign(n_gpus, nullptr);
+    g_eng.pinned_bytes.assign(n_gpus, 0);
     for (int i = 0; i < n_gpus; ++i) {
         CU(cudaSetDevice(g_eng.devs[i]));
         CU(cudaStreamCreateWithFlags(&g_eng.streams[i], cudaStreamNonBlocking));
@@ -152,8 +198,16 @@ extern "C" void k4b_gpu_shutdown(void) {
     g_eng.comms.clear();
     for (size_t i = 0; i < g_eng.devs.size(); ++i) {
         cudaSetDevice(g_eng.devs[i]);
-        if (g_eng.streams[i]) cudaStreamDestroy(g_eng.streams[i]);
+        if (g_eng.streams[i]) {
+            cudaStreamSynchronize(g_eng.streams[i]);
+            cudaStreamDestroy(g_eng.streams[i]);
+        }
+        if (i < g_eng.pinned.size() && g_eng.pinned[i]) cudaFreeHost(g_eng.pinned[i]);
+        cudaMemPool_t pool = nullptr;  // hand the retained scratch back to the driver
+        if (cudaDeviceGetDefaultMemPool(&pool, g_eng.devs[i]) == cudaSuccess && pool) cudaMemPoolTrimTo(pool, 0);
     }
+    g_eng.pinned.clear();
+    g_eng.pinned_bytes.clear();
     g_eng.streams.clear();
     g_eng.devs.clear();
     g_eng.inited = false;
@@ -173,6 +227,11 @@ static int ensure_init() {
 struct k4b_packed {
     uint32_t *d_image = nullptr;
     bool owns = false;
+    // pooled: image and reverse-complement planes come from the stream-ordered pool and go back to it
+    // on pool_stream (the host-buffer entry points); otherwise cudaMalloc / cudaFree, which is safe
+    // whatever stream the caller used the handle on
+    bool pooled = false;
+    cudaStream_t pool_stream = nullptr;
     int device = 0;
     uint32_t len = 0, K = 0, nw = 0, stride = 0;
     int has_non_acgt = 0;
@@ -203,8 +262,13 @@ extern "C" void k4b_packed_free(k4b_packed *p) {
     int cur = 0;
     cudaGetDevice(&cur);
     cudaSetDevice(p->device);
-    if (p->owns && p->d_image) cudaFree(p->d_image);
-    if (p->d_rc_planes) cudaFree(p->d_rc_planes);
+    if (p->pooled) {
+        if (p->owns && p->d_image) cudaFreeAsync(p->d_image, p->pool_stream);
+        if (p->d_rc_planes) cudaFreeAsync(p->d_rc_planes, p->pool_stream);
+    } else {
+        if (p->owns && p->d_image) cudaFree(p->d_image);
+        if (p->d_rc_planes) cudaFree(p->d_rc_planes);  // valid for stream-ordered allocations too
+    }
     cudaSetDevice(cur);
     delete p;
 }
@@ -237,9 +301,10 @@ static int pack_into(const void *d_concat, uint32_t concat_len, uint32_t K, uint
         uint32_t pad;
         unsigned long long count;
     };
-    Scratch *d_s = nullptr;
+    DevScratch scratch;
     Scratch h_s = {0, 0, 0};
-    cudaError_t e = cudaMalloc(&d_s, sizeof(Scratch));
+    cudaError_t e = scratch.alloc(sizeof(Scratch), st);
+    Scratch *d_s = scratch.as<Scratch>();
     if (e == cudaSuccess) e = cudaMemsetAsync(d_s, 0, sizeof(Scratch), st);
     if (e == cudaSuccess)
         e = launch_pack((const uint8_t *)d_concat, p->view(), &d_s->flags, st);
@@ -247,7 +312,7 @@ static int pack_into(const void *d_concat, uint32_t concat_len, uint32_t K, uint
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(&h_s, d_s, sizeof(Scratch), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (d_s) cudaFree(d_s);
+    scratch.release();
     if (e != cudaSuccess) {
         k4b_packed_free(p);
         return fail(cuda_code(e), "pack (%u bases): %s", concat_len, cudaGetErrorString(e));
@@ -288,6 +353,26 @@ extern "C" int k4b_pack_device_into(const void *d_concat, uint32_t concat_len, u
         return fail(K4B_ERR_PARAMS, "image buffer must be 16-byte aligned and %zu bytes",
                     k4b_packed_image_bytes(concat_len));
     return pack_into(d_concat, concat_len, K, (uint32_t *)d_image, false, (cudaStream_t)stream, out);
+}
+
+// host concat -> packed image on engine device slot `slot`, everything from the stream-ordered pool
+// on that device's engine stream (the host-buffer entry points).  A pinned source is copied at full
+// PCIe rate; a pageable one is staged by the driver.
+static int pack_host_pooled(const uint8_t *concat, uint32_t concat_len, uint32_t K, int slot, k4b_packed **out) {
+    *out = nullptr;
+    RC(check_k(K, K4B_MIN_K, K4B_MAX_K));
+    RC(check_len(concat_len));
+    CU(cudaSetDevice(g_eng.devs[slot]));
+    cudaStream_t st = g_eng.streams[slot];
+    DevScratch d_c;
+    CU(d_c.alloc(((size_t)concat_len + 15) / 16 * 16, st));
+    CU(cudaMemcpyAsync(d_c.p, concat, concat_len, cudaMemcpyHostToDevice, st));
+    uint32_t *image = nullptr;
+    CU(cudaMallocAsync(&image, k4b_packed_image_bytes(concat_len), st));
+    RC(pack_into(d_c.p, concat_len, K, image, true, st, out));  // synchronises st; owns the image even on failure
+    (*out)->pooled = true;
+    (*out)->pool_stream = st;
+    return K4B_OK;
 }
 
 extern "C" int k4b_pack_host(const uint8_t *concat, uint32_t concat_len, uint32_t K,
@@ -426,12 +511,13 @@ static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_stra
     const bool generic = W > (uint32_t)kMaxRegW;
 
     if (generic && crick && !queries->d_rc_planes) {
-        CU(cudaMalloc(&queries->d_rc_planes, (size_t)queries->stride * kImageArrays * 4));
+        CU(cudaMallocAsync(&queries->d_rc_planes, (size_t)queries->stride * kImageArrays * 4, st));
         CU(launch_revcomp_planes(queries->view(), queries->rc_view(), st));
     }
 
-    uint32_t *d_min32 = nullptr;
-    CU(cudaMallocAsync(&d_min32, (size_t)nq * 4, st));
+    DevScratch min_buf, ent_buf;  // returned to the pool on every path
+    CU(min_buf.alloc((size_t)nq * 4, st));
+    uint32_t *d_min32 = min_buf.as<uint32_t>();
     CU(launch_fill_u32(d_min32, nq, K + 1, st));
 
     AllPairsParams prm;
@@ -448,12 +534,11 @@ static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_stra
     prm.zfilt = 0;
     prm.ent_starts = nullptr;
     prm.n_ent = 0;
-    uint32_t *d_ent = nullptr;
     if (g_zf.mode && targeted_rules && self_exclude && queries == targets && !g_zf.starts.empty()) {
-        CU(cudaMallocAsync(&d_ent, g_zf.starts.size() * 4, st));
-        CU(cudaMemcpyAsync(d_ent, g_zf.starts.data(), g_zf.starts.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(ent_buf.alloc(g_zf.starts.size() * 4, st));
+        CU(cudaMemcpyAsync(ent_buf.p, g_zf.starts.data(), g_zf.starts.size() * 4, cudaMemcpyHostToDevice, st));
         prm.zfilt = g_zf.mode;
-        prm.ent_starts = d_ent;
+        prm.ent_starts = ent_buf.as<uint32_t>();
         prm.n_ent = (uint32_t)g_zf.starts.size();
     }
     prm.ranged = sweep.ranged ? 1 : 0;
@@ -480,8 +565,6 @@ static int allpairs_impl(k4b_packed *queries, k4b_packed *targets, int both_stra
     if (e == cudaSuccess)
         e = launch_finalize(d_min32, queries->view(), q_begin, nq, K, clamp, targeted_rules ? 4 : -1,
                             d_out_min, st);
-    cudaFreeAsync(d_min32, st);
-    if (d_ent) cudaFreeAsync(d_ent, st);
     if (e != cudaSuccess) return fail(cuda_code(e), "allpairs launch: %s", cudaGetErrorString(e));
     if (launches) *launches = 3;  // fill + allpairs + finalize
     return K4B_OK;
@@ -525,11 +608,24 @@ extern "C" int k4b_best_finalize_device(k4b_packed *g, const uint32_t *d_best, u
 static int diag_prepare(k4b_packed *g, bool crick, cudaStream_t st, int *nl) {
     CU(cudaSetDevice(g->device));
     if (crick && !g->d_rc_planes) {
-        CU(cudaMalloc(&g->d_rc_planes, (size_t)g->stride * kImageArrays * 4));
+        CU(cudaMallocAsync(&g->d_rc_planes, (size_t)g->stride * kImageArrays * 4, st));
         CU(launch_revcomp_planes(g->view(), g->rc_view(), st));
         ++*nl;
     }
     return 0;
+}
+
+// test hook: the image (6 arrays of stride words) and, when rc != 0, the lazily built
+// reverse-complemented image of a handle, copied to the host
+extern "C" int k4b_debug_copy_image(k4b_packed *g, int rc, uint32_t *host_out, size_t words) {
+    if (!g || !host_out) return fail(K4B_ERR_PARAMS, "NULL argument");
+    if (words != (size_t)g->stride * kImageArrays) return fail(K4B_ERR_PARAMS, "expected %zu words", (size_t)g->stride * kImageArrays);
+    int nl = 0;
+    if (rc) RC(diag_prepare(g, true, nullptr, &nl));
+    CU(cudaSetDevice(g->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(host_out, rc ? g->d_rc_planes : g->d_image, words * 4, cudaMemcpyDeviceToHost));
+    return K4B_OK;
 }
 
 // Bootstrap of the band engine: the K-mers starting in [q_begin, q_end) against a small sample
@@ -675,9 +771,10 @@ extern "C" int k4b_diag_slabs_device(k4b_packed *g, int both_strands, uint32_t p
     RC(diag_prepare(g, crick, st, &nl));
     const uint32_t bm_shift = 8;
     const uint32_t n_blocks = (M >> bm_shift) + 1;
-    uint32_t *d_bm = nullptr;  // [n_blocks] block maxima + per slab: [64] global maxima, [64] low-block counts
     if (n_slabs > kMaxSlabs) return fail(K4B_ERR_PARAMS, "%u slabs exceed the %u bookkeeping slots", n_slabs, kMaxSlabs);
-    CU(cudaMallocAsync(&d_bm, ((size_t)n_blocks + 2 * kMaxSlabs) * 4, st));
+    DevScratch bm_buf;  // [n_blocks] block maxima + per slab: [kMaxSlabs] global maxima, [kMaxSlabs] low-block counts
+    CU(bm_buf.alloc(((size_t)n_blocks + 2 * kMaxSlabs) * 4, st));
+    uint32_t *d_bm = bm_buf.as<uint32_t>();
     CU(cudaMemsetAsync(d_bm + n_blocks, 0, 2 * kMaxSlabs * 4, st));
     const char *rs = getenv("K4B_DIAG_ROWS");
     const uint32_t rows_per_seg = rs ? (uint32_t)atoi(rs) : 8192u;
@@ -762,7 +859,6 @@ extern "C" int k4b_diag_slabs_device(k4b_packed *g, int both_strands, uint32_t p
     g_info_np_full = (uint32_t)np_full;
     g_info_np_small = (uint32_t)np_small;
     g_info_limit = np_small ? (1u << (np_small - 1)) : 0u;
-    cudaFreeAsync(d_bm, st);
     if (e != cudaSuccess) return fail(cuda_code(e), "diagonal engine launch: %s", cudaGetErrorString(e));
     if (launches) *launches = nl;
     return K4B_OK;
@@ -873,65 +969,78 @@ extern "C" int k4b_last_seed_info(uint64_t *occurrences, uint64_t *indexed_cores
 // clamp, the "not found" value, as long as clamp <= K / core_len (pigeonhole over the disjoint
 // cores).  Probe K-mers holding N / InDel are skipped (d_best keeps its value): wildcard probes need
 // the reference's substitution rule and belong to the brute-force engines.  probes == targets (the
-// same handle) selects the rules of probes drawn from the assembly itself.  Handles the probe
-// K-mers starting in [q_begin, q_end); ranges combine by element-wise minimum of d_best.
-extern "C" int k4b_targeted_seed_device(k4b_packed *probes, k4b_packed *targets, int both_strands,
-                                        uint32_t clamp, uint32_t core_len, uint32_t q_begin,
-                                        uint32_t q_end, uint32_t *d_best, void *stream, int *launches) {
+// same handle) selects the rules of probes drawn from the assembly itself.  Two ways to split the
+// work, both combining by element-wise minimum of d_best: a RANGE of probe K-mers [q_begin, q_end)
+// against the whole index, or (part, nparts) = a share of the index BUCKETS against all probes -
+// then only 1/nparts of the index is built, which is what scales when the index build matters.
+static int seed_run(k4b_packed *probes, k4b_packed *targets, int both_strands, uint32_t clamp, uint32_t core_len,
+                    uint32_t q_begin, uint32_t q_end, uint32_t part, uint32_t nparts, uint32_t *d_best, void *stream,
+                    int *launches) {
     if (launches) *launches = 0;
     if (!probes || !targets || !d_best) return fail(K4B_ERR_PARAMS, "NULL argument");
     if (probes->K != targets->K) return fail(K4B_ERR_PARAMS, "probe/target K differ");
     if (probes->device != targets->device) return fail(K4B_ERR_PARAMS, "images live on different devices");
+    if (!nparts || part >= nparts) return fail(K4B_ERR_PARAMS, "part %u of %u", part, nparts);
     const uint32_t K = probes->K;
     if (!core_len || core_len > K || !clamp || clamp > K / core_len)
         return fail(K4B_ERR_PARAMS, "core_len=%u clamp=%u: the pigeonhole bound needs clamp <= K/core_len", core_len, clamp);
     cudaStream_t st = (cudaStream_t)stream;
     if (q_end > probes->len) q_end = probes->len;
     if (probes->len < K || targets->len < K || q_begin >= q_end) return K4B_OK;
+    CU(cudaSetDevice(probes->device));
     const bool crick = both_strands != 0;
     int nl = 0;
     RC(diag_prepare(probes, crick, st, &nl));  // reverse-complemented probe planes
     const uint32_t nb = 1u << seed_bucket_bits(core_len);
+    const uint32_t b_lo = (uint32_t)((uint64_t)nb * part / nparts), b_hi = (uint32_t)((uint64_t)nb * (part + 1) / nparts);
     const size_t temp_bytes = seed_scan_temp_bytes(nb);
-    uint32_t *d_idx = nullptr;  // occ slots | sig (targets->len x 8 B) | pos (targets->len) | cnt | off | cursor (nb+1 each)
-    void *d_temp = nullptr;
-    const size_t words = 2 * (size_t)kSeedOccSlots + 3 * ((size_t)nb + 1) + 3 * (size_t)targets->len;
-    CU(cudaMallocAsync(&d_idx, words * 4, st));
-    CU(cudaMallocAsync(&d_temp, temp_bytes ? temp_bytes : 4, st));
-    unsigned long long *d_occ = (unsigned long long *)d_idx;
-    CU(cudaMemsetAsync(d_occ, 0, kSeedOccSlots * 8, st));
-    uint2 *d_sig = (uint2 *)(d_idx + 2 * (size_t)kSeedOccSlots);
-    uint32_t *d_pos = d_idx + 2 * (size_t)kSeedOccSlots + 2 * (size_t)targets->len;
-    uint32_t *d_cnt = d_pos + targets->len, *d_off = d_cnt + nb + 1, *d_cur = d_off + nb + 1;
-    CU(cudaMemsetAsync(d_cnt, 0, ((size_t)nb + 1) * 4, st));
+    // index: 16-byte entries | occ slots | cnt | off | cursor (nb+1 each); scan scratch; -z entry starts
+    DevScratch idx_buf, tmp_buf, ent_buf;
+    const size_t ent_bytes = (size_t)targets->len * sizeof(uint4);
+    CU(idx_buf.alloc(ent_bytes + (size_t)kSeedOccSlots * 8 + 3 * ((size_t)nb + 1) * 4, st));
+    CU(tmp_buf.alloc(temp_bytes, st));
+    uint4 *d_ent = idx_buf.as<uint4>();
+    unsigned long long *d_occ = (unsigned long long *)((char *)idx_buf.p + ent_bytes);
+    uint32_t *d_cnt = (uint32_t *)(d_occ + kSeedOccSlots), *d_off = d_cnt + nb + 1, *d_cur = d_off + nb + 1;
+    CU(cudaMemsetAsync(d_occ, 0, (size_t)kSeedOccSlots * 8 + ((size_t)nb + 1) * 4, st));  // occ slots + counters
     // probes == targets: the K-mers of the assembly against the assembly itself (exact sense self hit
     // skipped; -z of the k4b_hamm_targeted_z call in progress on this thread)
     SeedSelfRules self{probes == targets ? 1 : 0, 0, nullptr, 0};
-    uint32_t *d_ent = nullptr;
     if (self.on && g_zf.mode && !g_zf.starts.empty()) {
-        CU(cudaMallocAsync(&d_ent, g_zf.starts.size() * 4, st));
-        CU(cudaMemcpyAsync(d_ent, g_zf.starts.data(), g_zf.starts.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(ent_buf.alloc(g_zf.starts.size() * 4, st));
+        CU(cudaMemcpyAsync(ent_buf.p, g_zf.starts.data(), g_zf.starts.size() * 4, cudaMemcpyHostToDevice, st));
         self.zfilt = g_zf.mode;
-        self.ent_starts = d_ent;
+        self.ent_starts = ent_buf.as<uint32_t>();
         self.n_ent = (uint32_t)g_zf.starts.size();
     }
     RC(g_tp.begin(probes->device, true, st));
-    cudaError_t e = launch_seed_index(targets->view(), core_len, d_cnt, d_off, d_cur, d_pos, d_sig, d_temp, temp_bytes, st);
+    cudaError_t e = launch_seed_index(targets->view(), core_len, b_lo, b_hi, d_cnt, d_off, d_cur, d_ent, tmp_buf.p,
+                                      temp_bytes, st);
     if (e == cudaSuccess)
         e = launch_seed_query(probes->view(), crick ? probes->rc_view() : probes->view(), targets->view(), K, core_len,
-                              d_off, d_pos, d_sig, q_begin, q_end, clamp, crick, targets->has_non_acgt != 0,
+                              d_off, d_ent, q_begin, q_end, b_lo, b_hi, clamp, crick, targets->has_non_acgt != 0,
                               probes->has_non_acgt != 0, self, d_best, d_occ, st);
     if (e == cudaSuccess) e = g_tp.end(st);
     if (e == cudaSuccess && !g_h_seed) e = cudaMallocHost(&g_h_seed, (kSeedOccSlots + 1) * 8);
     if (e == cudaSuccess) e = cudaMemcpyAsync(g_h_seed, d_occ, kSeedOccSlots * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)  // number of indexed cores = the last bucket offset
         e = cudaMemcpyAsync(g_h_seed + kSeedOccSlots, d_off + nb, 4, cudaMemcpyDeviceToHost, st);
-    cudaFreeAsync(d_temp, st);
-    cudaFreeAsync(d_idx, st);
-    if (d_ent) cudaFreeAsync(d_ent, st);
     if (e != cudaSuccess) return fail(cuda_code(e), "seed engine launch: %s", cudaGetErrorString(e));
     if (launches) *launches = nl + 4;
     return K4B_OK;
+}
+
+extern "C" int k4b_targeted_seed_device(k4b_packed *probes, k4b_packed *targets, int both_strands,
+                                        uint32_t clamp, uint32_t core_len, uint32_t q_begin,
+                                        uint32_t q_end, uint32_t *d_best, void *stream, int *launches) {
+    return seed_run(probes, targets, both_strands, clamp, core_len, q_begin, q_end, 0, 1, d_best, stream, launches);
+}
+
+extern "C" int k4b_targeted_seed_part_device(k4b_packed *probes, k4b_packed *targets, int both_strands,
+                                             uint32_t clamp, uint32_t core_len, uint32_t part, uint32_t nparts,
+                                             uint32_t *d_best, void *stream, int *launches) {
+    return seed_run(probes, targets, both_strands, clamp, core_len, 0, 0xffffffffu, part, nparts, d_best, stream,
+                    launches);
 }
 
 // minima -> uint16 with the targeted rules applied (cap at clamp, > 4 wildcards -> 0)
@@ -962,21 +1071,18 @@ extern "C" int k4b_exhaustive_diag_device(k4b_packed *g, int both_strands, uint3
 namespace {
 struct DevJob {
     k4b_packed *q = nullptr, *t = nullptr;  // t == q for all-vs-all
-    uint16_t *d_out = nullptr;
-    uint16_t *h_out = nullptr;  // pinned
+    DevScratch d_out;                       // stream-ordered, back to the pool when the job dies
+    uint16_t *h_out = nullptr;              // the engine's cached pinned staging of this device slot
     uint32_t q_begin = 0, q_end = 0;
     void release() {
-        if (d_out) cudaFree(d_out);
-        if (h_out) cudaFreeHost(h_out);
+        d_out.release();
         if (t && t != q) k4b_packed_free(t);
         if (q) k4b_packed_free(q);
-        d_out = nullptr;
-        h_out = nullptr;
         q = t = nullptr;
     }
 };
 
-// broadcast the image of `src` (on device index 0 of the engine) to fresh images on every
+// broadcast the image of `src` (on device slot 0 of the engine) to fresh pooled images on every
 // other engine device: ONE ncclBroadcast per set, nothing else crosses NVLink afterwards
 int broadcast_packed(k4b_packed *src, std::vector<k4b_packed *> &out) {
     const int n = (int)g_eng.devs.size();
@@ -987,13 +1093,15 @@ int broadcast_packed(k4b_packed *src, std::vector<k4b_packed *> &out) {
     for (int i = 1; i < n; ++i) {
         CU(cudaSetDevice(g_eng.devs[i]));
         void *img = nullptr;
-        CU(cudaMalloc(&img, bytes));
+        CU(cudaMallocAsync(&img, bytes, g_eng.streams[i]));
         int rc = k4b_packed_from_image(img, bytes, src->len, src->K, src->has_non_acgt, &out[i]);
         if (rc) {
-            cudaFree(img);
+            cudaFreeAsync(img, g_eng.streams[i]);
             return rc;
         }
         out[i]->owns = true;
+        out[i]->pooled = true;
+        out[i]->pool_stream = g_eng.streams[i];
         out[i]->num_kmers = src->num_kmers;
     }
     int nr = g_eng.nccl.GroupStart();
@@ -1003,11 +1111,7 @@ int broadcast_packed(k4b_packed *src, std::vector<k4b_packed *> &out) {
     int nr2 = g_eng.nccl.GroupEnd();
     if (nr || nr2)
         return fail(K4B_ERR_NCCL, "ncclBroadcast: %s", g_eng.nccl.GetErrorString(nr ? nr : nr2));
-    for (int i = 0; i < n; ++i) {
-        CU(cudaSetDevice(g_eng.devs[i]));
-        CU(cudaStreamSynchronize(g_eng.streams[i]));
-    }
-    return 0;
+    return 0;  // stream ordered: every later use of the images is enqueued on the same streams
 }
 
 // K4B_TRACE=1 prints the host-side phase times of each host-buffer call to stderr
@@ -1048,13 +1152,13 @@ int run_sharded(const uint8_t *q_concat, uint32_t q_len, const uint8_t *t_concat
         // pack once on device 0, broadcast to the rest
         CU(cudaSetDevice(g_eng.devs[0]));
         k4b_packed *q0 = nullptr, *t0 = nullptr;
-        if ((rc = k4b_pack_host(q_concat, q_len, K, &q0))) break;
+        if ((rc = pack_host_pooled(q_concat, q_len, K, 0, &q0))) break;
         jobs[0].q = q0;
         const bool same = (t_concat == nullptr);
         if (same) {
             jobs[0].t = q0;
         } else {
-            if ((rc = k4b_pack_host(t_concat, t_len, K, &t0))) break;
+            if ((rc = pack_host_pooled(t_concat, t_len, K, 0, &t0))) break;
             jobs[0].t = t0;
         }
         if (n > 1) {
@@ -1080,16 +1184,16 @@ int run_sharded(const uint8_t *q_concat, uint32_t q_len, const uint8_t *t_concat
             const uint32_t nq = j.q_end - j.q_begin;
             if (!nq) continue;
             cudaError_t e = cudaSetDevice(g_eng.devs[i]);
-            if (e == cudaSuccess) e = cudaMalloc(&j.d_out, (size_t)nq * 2);
-            if (e == cudaSuccess) e = cudaMallocHost(&j.h_out, (size_t)nq * 2);
+            if (e == cudaSuccess) e = j.d_out.alloc((size_t)nq * 2, g_eng.streams[i]);
+            if (e == cudaSuccess && !(j.h_out = (uint16_t *)pinned_result(i, (size_t)nq * 2))) e = cudaErrorMemoryAllocation;
             if (e != cudaSuccess) {
                 rc = fail(cuda_code(e), "shard buffers: %s", cudaGetErrorString(e));
                 break;
             }
-            rc = allpairs_impl(j.q, j.t, both, self_ex, j.q_begin, j.q_end, clamp, sweep, j.d_out,
+            rc = allpairs_impl(j.q, j.t, both, self_ex, j.q_begin, j.q_end, clamp, sweep, j.d_out.as<uint16_t>(),
                                g_eng.streams[i], nullptr);
             if (rc) break;
-            e = cudaMemcpyAsync(j.h_out, j.d_out, (size_t)nq * 2, cudaMemcpyDeviceToHost,
+            e = cudaMemcpyAsync(j.h_out, j.d_out.p, (size_t)nq * 2, cudaMemcpyDeviceToHost,
                                 g_eng.streams[i]);
             if (e != cudaSuccess) rc = fail(cuda_code(e), "D2H: %s", cudaGetErrorString(e));
         }
@@ -1146,42 +1250,42 @@ int make_sweep(uint32_t len, uint32_t K, uint32_t sweep_start, uint32_t sweep_en
 // full-sweep exhaustive run on the diagonal engine: the pair matrix (not the queries) is
 // partitioned over the devices, each keeps a complete array of running minima, and the arrays
 // meet in ncclAllReduce(min) after the bootstrap and after every slab - the exchange step of
-// the symmetric formulation
+// the symmetric formulation.  All device memory comes from the stream-ordered pool, the result
+// staging is the engine's cached pinned buffer: a warm call allocates nothing from the driver.
 static int run_exhaustive_diag(const uint8_t *concat, uint32_t len, uint32_t K, int both,
                                uint16_t *out_min) {
     RC(ensure_init());
     const int n = (int)g_eng.devs.size();
     PhaseTrace trace;
     std::vector<k4b_packed *> imgs;
-    std::vector<uint32_t *> bests(n, nullptr);
-    uint16_t *d_out = nullptr, *h_out = nullptr;
+    std::vector<DevScratch> bests(n);
+    DevScratch d_out;
     int rc = 0;
     do {
-        CU(cudaSetDevice(g_eng.devs[0]));
         k4b_packed *g0 = nullptr;
-        if ((rc = k4b_pack_host(concat, len, K, &g0))) break;
+        if ((rc = pack_host_pooled(concat, len, K, 0, &g0))) break;
         rc = broadcast_packed(g0, imgs);
         if (imgs.empty()) imgs.push_back(g0);
         if (rc) break;
         trace.mark("H2D + pack (+bcast)");
         for (int i = 0; i < n && !rc; ++i) {
             cudaError_t e = cudaSetDevice(g_eng.devs[i]);
-            if (e == cudaSuccess) e = cudaMalloc(&bests[i], (size_t)len * 4);
+            if (e == cudaSuccess) e = bests[i].alloc((size_t)len * 4, g_eng.streams[i]);
             if (e != cudaSuccess) {
                 rc = fail(cuda_code(e), "minima buffer: %s", cudaGetErrorString(e));
                 break;
             }
-            rc = k4b_best_init_device(bests[i], len, K, g_eng.streams[i]);
+            rc = k4b_best_init_device(bests[i].as<uint32_t>(), len, K, g_eng.streams[i]);
             // bootstrap: every device takes a shard of the queries
             const uint32_t qb = (uint32_t)((uint64_t)len * i / n), qe = (uint32_t)((uint64_t)len * (i + 1) / n);
-            if (!rc) rc = k4b_diag_bootstrap_device(imgs[i], both, qb, qe, bests[i], g_eng.streams[i]);
+            if (!rc) rc = k4b_diag_bootstrap_device(imgs[i], both, qb, qe, bests[i].as<uint32_t>(), g_eng.streams[i]);
         }
         if (rc) break;
         auto allreduce_min = [&]() -> int {
             if (n == 1) return 0;
             int nr = g_eng.nccl.GroupStart();
             for (int i = 0; i < n && !nr; ++i)
-                nr = g_eng.nccl.AllReduce(bests[i], bests[i], len, kNcclUint32, kNcclMin, g_eng.comms[i], g_eng.streams[i]);
+                nr = g_eng.nccl.AllReduce(bests[i].p, bests[i].p, len, kNcclUint32, kNcclMin, g_eng.comms[i], g_eng.streams[i]);
             const int nr2 = g_eng.nccl.GroupEnd();
             if (nr || nr2) return fail(K4B_ERR_NCCL, "ncclAllReduce(min): %s", g_eng.nccl.GetErrorString(nr ? nr : nr2));
             return 0;
@@ -1195,21 +1299,22 @@ static int run_exhaustive_diag(const uint8_t *concat, uint32_t len, uint32_t K, 
             for (int i = 0; i < n && !rc; ++i) {
                 cudaSetDevice(g_eng.devs[i]);
                 rc = k4b_diag_slabs_device(imgs[i], both, (uint32_t)i, (uint32_t)n, slab,
-                                           n == 1 ? n_slabs : slab + 1, bests[i], g_eng.streams[i], nullptr);
+                                           n == 1 ? n_slabs : slab + 1, bests[i].as<uint32_t>(), g_eng.streams[i], nullptr);
             }
             if (!rc) rc = allreduce_min();
         }
         if (rc) break;
         trace.mark("launch");
         cudaError_t e = cudaSetDevice(g_eng.devs[0]);
-        if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)len * 2);
-        if (e == cudaSuccess) e = cudaMallocHost(&h_out, (size_t)len * 2);
+        uint16_t *h_out = nullptr;
+        if (e == cudaSuccess) e = d_out.alloc((size_t)len * 2, g_eng.streams[0]);
+        if (e == cudaSuccess && !(h_out = (uint16_t *)pinned_result(0, (size_t)len * 2))) e = cudaErrorMemoryAllocation;
         if (e != cudaSuccess) {
             rc = fail(cuda_code(e), "result buffers: %s", cudaGetErrorString(e));
             break;
         }
-        if ((rc = k4b_best_finalize_device(imgs[0], bests[0], d_out, g_eng.streams[0]))) break;
-        e = cudaMemcpyAsync(h_out, d_out, (size_t)len * 2, cudaMemcpyDeviceToHost, g_eng.streams[0]);
+        if ((rc = k4b_best_finalize_device(imgs[0], bests[0].as<uint32_t>(), d_out.as<uint16_t>(), g_eng.streams[0]))) break;
+        e = cudaMemcpyAsync(h_out, d_out.p, (size_t)len * 2, cudaMemcpyDeviceToHost, g_eng.streams[0]);
         for (int i = 0; i < n; ++i) {
             cudaSetDevice(g_eng.devs[i]);
             const cudaError_t e2 = cudaStreamSynchronize(g_eng.streams[i]);
@@ -1226,21 +1331,19 @@ static int run_exhaustive_diag(const uint8_t *concat, uint32_t len, uint32_t K, 
     } while (0);
     for (int i = 0; i < n; ++i) {
         cudaSetDevice(g_eng.devs[i]);
-        if (bests[i]) cudaFree(bests[i]);
+        bests[i].release();
         if ((size_t)i < imgs.size() && imgs[i]) k4b_packed_free(imgs[i]);
     }
     cudaSetDevice(g_eng.devs[0]);
-    if (d_out) cudaFree(d_out);
-    if (h_out) cudaFreeHost(h_out);
+    d_out.release();
+    trace.mark("free");
     return rc;
 }
 
-// probes-vs-assembly on the band engine over all devices (diagonals partitioned, one
-// ncclAllReduce(min) at the end)
 // Whole-probe-set targeted run on the seed-and-verify engine (pure-ACGT probes, cores of at
 // least 6 bases) or on the band engine; *used = 0 when neither applies (caller falls back to the
-// POPC engine).  Devices split the probes (seed) or the diagonals (bands); minima meet in one
-// ncclAllReduce(min).
+// POPC engine).  Devices split the index BUCKETS (seed: each builds and joins its share of the
+// index against all probes) or the diagonals (bands); minima meet in one ncclAllReduce(min).
 static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8_t *q_concat, uint32_t q_len,
                             uint32_t K, int both, uint32_t clamp, uint32_t core_len, bool allow_seed,
                             bool allow_diag, uint8_t *out_h, int *used) {
@@ -1249,19 +1352,18 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
     const int n = (int)g_eng.devs.size();
     PhaseTrace trace;
     std::vector<k4b_packed *> qs, ts;
-    std::vector<uint32_t *> bests(n, nullptr);
-    uint16_t *d_out = nullptr, *h_out = nullptr;
+    std::vector<DevScratch> bests(n);
+    DevScratch d_out;
     bool use_seed = false;
     int rc = 0;
     do {
-        CU(cudaSetDevice(g_eng.devs[0]));
         k4b_packed *q0 = nullptr, *t0 = nullptr;
         const bool same = q_concat == nullptr;  // probes = the K-mers of the assembly itself (no -I)
         if (same) {
             q_concat = t_concat;
             q_len = t_len;
         }
-        if ((rc = k4b_pack_host(q_concat, q_len, K, &q0))) break;
+        if ((rc = pack_host_pooled(q_concat, q_len, K, 0, &q0))) break;
         qs.push_back(q0);
         // a core of c bases occurs in ~len/4^c places: below 6 bases verifying every occurrence costs
         // as much as the bit-sliced bands
@@ -1288,7 +1390,7 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
         *used = 1;
         if (same) {
             t0 = q0;
-        } else if ((rc = k4b_pack_host(t_concat, t_len, K, &t0))) {
+        } else if ((rc = pack_host_pooled(t_concat, t_len, K, 0, &t0))) {
             break;
         }
         ts.push_back(t0);
@@ -1306,10 +1408,11 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
             }
         }
         trace.mark("H2D + pack (+bcast)");
-        {   // result buffers first: synchronous allocations behind queued work stall the host
+        uint16_t *h_out = nullptr;
+        {
             cudaError_t e = cudaSetDevice(g_eng.devs[0]);
-            if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)q_len * 2);
-            if (e == cudaSuccess) e = cudaMallocHost(&h_out, (size_t)q_len * 2);
+            if (e == cudaSuccess) e = d_out.alloc((size_t)q_len * 2, g_eng.streams[0]);
+            if (e == cudaSuccess && !(h_out = (uint16_t *)pinned_result(0, (size_t)q_len * 2))) e = cudaErrorMemoryAllocation;
             if (e != cudaSuccess) {
                 rc = fail(cuda_code(e), "result buffers: %s", cudaGetErrorString(e));
                 break;
@@ -1317,18 +1420,19 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
         }
         for (int i = 0; i < n && !rc; ++i) {
             cudaError_t e = cudaSetDevice(g_eng.devs[i]);
-            if (e == cudaSuccess) e = cudaMalloc(&bests[i], (size_t)q_len * 4);
+            if (e == cudaSuccess) e = bests[i].alloc((size_t)q_len * 4, g_eng.streams[i]);
             if (e != cudaSuccess) {
                 rc = fail(cuda_code(e), "minima buffer: %s", cudaGetErrorString(e));
                 break;
             }
-            rc = k4b_best_init_device(bests[i], q_len, K, g_eng.streams[i]);
+            rc = k4b_best_init_device(bests[i].as<uint32_t>(), q_len, K, g_eng.streams[i]);
             if (rc) break;
-            if (use_seed)
-                rc = k4b_targeted_seed_device(qs[i], ts[i], both, clamp, core_len, (uint32_t)((uint64_t)q_len * i / n),
-                                              (uint32_t)((uint64_t)q_len * (i + 1) / n), bests[i], g_eng.streams[i], nullptr);
+            if (use_seed)  // device i: its share of the index buckets, all probes
+                rc = seed_run(qs[i], ts[i], both, clamp, core_len, 0, q_len, (uint32_t)i, (uint32_t)n,
+                              bests[i].as<uint32_t>(), g_eng.streams[i], nullptr);
             else
-                rc = k4b_targeted_diag_device(qs[i], ts[i], both, clamp, (uint32_t)i, (uint32_t)n, bests[i], g_eng.streams[i], nullptr);
+                rc = k4b_targeted_diag_device(qs[i], ts[i], both, clamp, (uint32_t)i, (uint32_t)n, bests[i].as<uint32_t>(),
+                                              g_eng.streams[i], nullptr);
         }
         if (rc) break;
         trace.mark("alloc + enqueue");
@@ -1342,7 +1446,7 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
         if (n > 1) {
             int nr = g_eng.nccl.GroupStart();
             for (int i = 0; i < n && !nr; ++i)
-                nr = g_eng.nccl.AllReduce(bests[i], bests[i], q_len, kNcclUint32, kNcclMin, g_eng.comms[i], g_eng.streams[i]);
+                nr = g_eng.nccl.AllReduce(bests[i].p, bests[i].p, q_len, kNcclUint32, kNcclMin, g_eng.comms[i], g_eng.streams[i]);
             const int nr2 = g_eng.nccl.GroupEnd();
             if (nr || nr2) {
                 rc = fail(K4B_ERR_NCCL, "ncclAllReduce(min): %s", g_eng.nccl.GetErrorString(nr ? nr : nr2));
@@ -1350,14 +1454,14 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
             }
         }
         cudaError_t e = cudaSetDevice(g_eng.devs[0]);
-        if ((rc = k4b_targeted_finalize_device(qs[0], bests[0], clamp, d_out, g_eng.streams[0]))) break;
+        if ((rc = k4b_targeted_finalize_device(qs[0], bests[0].as<uint32_t>(), clamp, d_out.as<uint16_t>(), g_eng.streams[0]))) break;
         if (use_seed)  // the wildcard probe K-mers the seed engine skipped
             for (size_t k = 0; k < impure.size() && !rc; ++k)
                 rc = k4b_allpairs_min_device(qs[0], ts[0], both, same ? 1 : 0, impure[k].first, impure[k].second, clamp,
-                                             d_out + impure[k].first, g_eng.streams[0], nullptr);
+                                             d_out.as<uint16_t>() + impure[k].first, g_eng.streams[0], nullptr);
         if (rc) break;
         if (e == cudaSuccess)
-            e = cudaMemcpyAsync(h_out, d_out, (size_t)q_len * 2, cudaMemcpyDeviceToHost, g_eng.streams[0]);
+            e = cudaMemcpyAsync(h_out, d_out.p, (size_t)q_len * 2, cudaMemcpyDeviceToHost, g_eng.streams[0]);
         for (int i = 0; i < n; ++i) {
             cudaSetDevice(g_eng.devs[i]);
             const cudaError_t e2 = cudaStreamSynchronize(g_eng.streams[i]);
@@ -1373,13 +1477,13 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
     } while (0);
     for (int i = 0; i < n; ++i) {
         cudaSetDevice(g_eng.devs[i]);
-        if (bests[i]) cudaFree(bests[i]);
+        bests[i].release();
         if ((size_t)i < qs.size() && qs[i]) k4b_packed_free(qs[i]);
         if ((size_t)i < ts.size() && ts[i] && !((size_t)i < qs.size() && ts[i] == qs[i])) k4b_packed_free(ts[i]);
     }
     cudaSetDevice(g_eng.devs[0]);
-    if (d_out) cudaFree(d_out);
-    if (h_out) cudaFreeHost(h_out);
+    d_out.release();
+    trace.mark("free");
     return rc;
 }
 
@@ -1491,32 +1595,64 @@ extern "C" int k4b_hamm_targeted(const uint8_t *target_concat, uint64_t target_l
 }
 
 // ------------------------------------------------------------------------------------------
+// distribution of the minima
+// ------------------------------------------------------------------------------------------
+extern "C" int k4b_histogram_device(const uint16_t *d_min, uint32_t n, uint32_t K, unsigned long long *d_hist,
+                                    void *stream) {
+    if (!d_min || !d_hist) return fail(K4B_ERR_PARAMS, "NULL argument");
+    RC(check_k(K, 1, 65533));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(d_hist, 0, ((size_t)K + 2) * 8, st));
+    CU(launch_histogram_u16(d_min, n, K + 2, d_hist, st));
+    return K4B_OK;
+}
+
+extern "C" int k4b_hamm_histogram(const uint16_t *min, uint32_t n, uint32_t K, uint64_t *hist) {
+    if (!min || !hist) return fail(K4B_ERR_PARAMS, "NULL buffer");
+    RC(ensure_init());
+    RC(check_k(K, 1, 65533));
+    CU(cudaSetDevice(g_eng.devs[0]));
+    cudaStream_t st = g_eng.streams[0];
+    DevScratch d_v, d_h;
+    CU(d_v.alloc((size_t)n * 2, st));
+    CU(d_h.alloc(((size_t)K + 2) * 8, st));
+    CU(cudaMemcpyAsync(d_v.p, min, (size_t)n * 2, cudaMemcpyHostToDevice, st));
+    RC(k4b_histogram_device(d_v.as<uint16_t>(), n, K, d_h.as<unsigned long long>(), st));
+    CU(cudaMemcpyAsync(hist, d_h.p, ((size_t)K + 2) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return K4B_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // integer-pipe microbenchmark
 // ------------------------------------------------------------------------------------------
 extern "C" int k4b_microbench_intpipe(int which, int iters, double *gops) {
     if (!gops) return fail(K4B_ERR_PARAMS, "gops is NULL");
     RC(ensure_init());
-    uint32_t *d_sink = nullptr;
-    CU(cudaMalloc(&d_sink, 4));
-    cudaEvent_t a, b;
-    CU(cudaEventCreate(&a));
-    CU(cudaEventCreate(&b));
+    struct Events {  // destroyed on every path
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~Events() {
+            if (a) cudaEventDestroy(a);
+            if (b) cudaEventDestroy(b);
+        }
+    } ev;
+    DevScratch sink;
+    CU(sink.alloc(4, 0));
+    CU(cudaEventCreate(&ev.a));
+    CU(cudaEventCreate(&ev.b));
     int blocks = 0, threads = 0, ops = 0;
     double best = 0;
     for (int rep = 0; rep < 4; ++rep) {  // first rep is warm-up
-        CU(cudaEventRecord(a, 0));
-        cudaError_t e = launch_microbench(which, iters, d_sink, &blocks, &threads, &ops, 0);
+        CU(cudaEventRecord(ev.a, 0));
+        cudaError_t e = launch_microbench(which, iters, sink.as<uint32_t>(), &blocks, &threads, &ops, 0);
         if (e != cudaSuccess) return fail(K4B_ERR_CUDA, "microbench: %s", cudaGetErrorString(e));
-        CU(cudaEventRecord(b, 0));
-        CU(cudaEventSynchronize(b));
+        CU(cudaEventRecord(ev.b, 0));
+        CU(cudaEventSynchronize(ev.b));
         float ms = 0;
-        CU(cudaEventElapsedTime(&ms, a, b));
+        CU(cudaEventElapsedTime(&ms, ev.a, ev.b));
         const double g = (double)blocks * threads * ops * (double)iters / (ms * 1e-3) / 1e9;
         if (rep > 0 && g > best) best = g;
     }
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
-    cudaFree(d_sink);
     *gops = best;
     return K4B_OK;
 }

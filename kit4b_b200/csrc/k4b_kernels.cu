@@ -194,6 +194,24 @@ __global__ void finalize_kernel(const uint32_t *__restrict__ min32, ImageView q,
     out16[i] = ok ? (uint16_t)v : (uint16_t)(K + 1);
 }
 
+// Distribution of the minima (the table `hammings` logs, hammings.cpp:2939-2962, and the
+// downstream HammingDist tool builds from the CSV): bin d counts the positions whose minimum is d,
+// bin K+1 collects the positions where no K-mer starts.  Shared-memory privatised histogram,
+// HBM-bound: reads 2 B per position.
+__global__ void __launch_bounds__(256) histogram_u16_kernel(const uint16_t *__restrict__ v, uint32_t n, uint32_t nbins,
+                                                            unsigned long long *__restrict__ hist) {
+    extern __shared__ uint32_t sh_bins[];
+    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) sh_bins[b] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t d = v[i];
+        atomicAdd(&sh_bins[d < nbins ? d : nbins - 1], 1u);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x)
+        if (sh_bins[b]) atomicAdd(hist + b, (unsigned long long)sh_bins[b]);
+}
+
 // ---------------------------------------------------------------------------------------
 // all-pairs minimum
 // ---------------------------------------------------------------------------------------
@@ -624,6 +642,17 @@ cudaError_t launch_valid(ImageView img, uint32_t K, unsigned long long *d_count,
 cudaError_t launch_fill_u32(uint32_t *d, uint32_t n, uint32_t v, cudaStream_t st) {
     if (!n) return cudaSuccess;
     fill_u32_kernel<<<(n + 255) / 256, 256, 0, st>>>(d, n, v);
+    return cudaGetLastError();
+}
+cudaError_t launch_histogram_u16(const uint16_t *d_v, uint32_t n, uint32_t nbins, unsigned long long *d_hist,
+                                 cudaStream_t st) {
+    if (!n || !nbins) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t want = (n + 255) / 256;
+    const uint32_t grid = want < (uint32_t)sms * 8 ? want : (uint32_t)sms * 8;  // a few CTAs per SM, grid-stride
+    histogram_u16_kernel<<<grid, 256, nbins * sizeof(uint32_t), st>>>(d_v, n, nbins, d_hist);
     return cudaGetLastError();
 }
 cudaError_t launch_finalize(const uint32_t *d_min32, ImageView q, uint32_t q_begin, uint32_t n,

@@ -122,6 +122,9 @@ cudaError_t launch_fill_u32(uint32_t *d, uint32_t n, uint32_t v, cudaStream_t st
 cudaError_t launch_finalize(const uint32_t *d_min32, ImageView q, uint32_t q_begin, uint32_t n,
                             uint32_t K, uint32_t clamp, int max_wild, uint16_t *d_out16,
                             cudaStream_t st);
+// d_hist: nbins counters, zeroed by the caller; values >= nbins land in the last bin
+cudaError_t launch_histogram_u16(const uint16_t *d_v, uint32_t n, uint32_t nbins, unsigned long long *d_hist,
+                                 cudaStream_t st);
 // returns cudaErrorInvalidValue when K needs more than the supported words
 cudaError_t launch_allpairs(const AllPairsParams &p, bool three_planes, bool crick,
                             cudaStream_t st, int *n_ctas);
@@ -141,12 +144,13 @@ struct SeedSelfRules {          // probes drawn from the indexed assembly itself
 };
 uint32_t seed_bucket_bits(uint32_t core_len);
 size_t seed_scan_temp_bytes(uint32_t n_buckets);
-cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t *d_cnt, uint32_t *d_off,
-                              uint32_t *d_cursor, uint32_t *d_pos, uint2 *d_sig, void *d_temp, size_t temp_bytes,
+// only cores whose bucket lies in [b_lo, b_hi) are indexed / answered (bucket shards of a multi-GPU run)
+cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t b_lo, uint32_t b_hi, uint32_t *d_cnt,
+                              uint32_t *d_off, uint32_t *d_cursor, uint4 *d_ent, void *d_temp, size_t temp_bytes,
                               cudaStream_t st);
 cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t K, uint32_t core_len,
-                              const uint32_t *d_off, const uint32_t *d_pos, const uint2 *d_sig, uint32_t q_begin,
-                              uint32_t q_end, uint32_t clamp, bool crick, bool three, bool q_impure,
+                              const uint32_t *d_off, const uint4 *d_ent, uint32_t q_begin, uint32_t q_end,
+                              uint32_t b_lo, uint32_t b_hi, uint32_t clamp, bool crick, bool three, bool q_impure,
                               SeedSelfRules self, uint32_t *d_best, unsigned long long *d_occ, cudaStream_t st);
 constexpr int kSeedOccSlots = 1024;  // d_occ (nullable): bucket entries streamed, summed over these slots
 cudaError_t launch_microbench(int which, int iters, uint32_t *d_sink, int *blocks, int *threads,

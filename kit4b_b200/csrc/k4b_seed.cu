@@ -7,9 +7,11 @@
 // (suffix-array runs, :4480-4527) and to verify the full K bases of each occurrence (:4567-4581).
 // Same idea here, without the suffix array and without the reference's depth cut-offs:
 //   * index: every target position whose CoreLen window is pure ACGT is bucketed by the code (or a
-//     hash, for long cores) of that window - count, exclusive scan, fill (three streaming passes
-//     over the packed planes, HBM-bound);
-//     every entry carries the 16 bases before and the 16 bases after the core as a signature;
+//     hash, for long cores) of that window - count, exclusive scan, fill.  Both passes stage the
+//     planes of a 2048-position chunk in shared memory once (coalesced) and cut every window out of
+//     that copy; an entry is ONE 16-byte record {position, flank signature} = the 16 bases before
+//     and the 16 bases after the core, written with a single full-width store.  A bucket RANGE can
+//     be selected, so that several GPUs each index (and join) their own share of the buckets;
 //   * query: one warp per (probe K-mer, strand, core): the lanes walk the bucket of the core
 //     (12 coalesced bytes per occurrence); the mismatches between the signature and the probe's
 //     own flanks are a lower bound of the distance, so almost every unrelated occurrence is
@@ -42,17 +44,36 @@ __device__ __forceinline__ uint32_t plane_bits(const uint32_t *pl, long long pos
     return __funnelshift_r(__ldg(pl + wi), __ldg(pl + wi + 1), sh);
 }
 
+// where window bits come from: the planes in global memory, or a chunk of them staged in shared memory
+struct GlobalBits {
+    const uint32_t *base;  // logical word 0 of plane 0
+    uint32_t stride;       // words between planes
+    __device__ __forceinline__ explicit GlobalBits(const ImageView &img) : base(img.base), stride(img.stride) {}
+    __device__ __forceinline__ GlobalBits(const uint32_t *b, uint32_t s) : base(b), stride(s) {}
+    __device__ __forceinline__ uint32_t get(int p, long long pos) const { return plane_bits(base + (size_t)p * stride, pos); }
+};
+struct SmemBits {
+    const uint32_t *pl[3];
+    long long origin;  // sequence position of bit 0 of word 0 of the staged copy (a multiple of 32)
+    __device__ __forceinline__ uint32_t get(int p, long long pos) const {
+        const uint32_t lb = (uint32_t)(pos - origin);
+        const uint32_t *w = pl[p] + (lb >> 5);
+        return __funnelshift_r(w[0], w[1], lb & 31u);
+    }
+};
+
 // bucket of the core starting at pos; ok = the window is pure ACGT (plane 2 clear; EOS and the
 // pads have it set).  core_len <= 11 with bits == 2*core_len: the code itself, else a hash.
-__device__ __forceinline__ uint32_t core_bucket(const ImageView &img, long long pos, uint32_t core_len,
-                                                uint32_t bits, bool &ok) {
+template <class Src>
+__device__ __forceinline__ uint32_t core_bucket(const Src &src, long long pos, uint32_t core_len, uint32_t bits,
+                                                bool &ok) {
     uint32_t h = 0x9e3779b9u, bad = 0, key = 0;
     for (uint32_t o = 0; o < core_len; o += 32) {
         const uint32_t n = core_len - o < 32 ? core_len - o : 32;
         const uint32_t m = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
-        const uint32_t w0 = plane_bits(img.plane(0), pos + o) & m;
-        const uint32_t w1 = plane_bits(img.plane(1), pos + o) & m;
-        bad |= plane_bits(img.plane(2), pos + o) & m;
+        const uint32_t w0 = src.get(0, pos + o) & m;
+        const uint32_t w1 = src.get(1, pos + o) & m;
+        bad |= src.get(2, pos + o) & m;
         key = w0 | (w1 << (core_len & 31));  // used only when core_len <= 11
         h = (h ^ w0) * 0x85ebca6bu;
         h ^= h >> 13;
@@ -63,35 +84,56 @@ __device__ __forceinline__ uint32_t core_bucket(const ImageView &img, long long 
     return (2 * core_len == bits) ? key : (h & ((1u << bits) - 1u));
 }
 
-__global__ void __launch_bounds__(256) seed_count_kernel(ImageView t, uint32_t n_pos, uint32_t core_len,
-                                                         uint32_t bits, uint32_t *__restrict__ cnt) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pos) return;
-    bool ok;
-    const uint32_t b = core_bucket(t, p, core_len, bits, ok);
-    if (ok) atomicAdd(cnt + b, 1u);
-}
-
 // Flank signature of a core: the 16 bases before it (bits 0..15) and the 16 bases after it (bits
 // 16..31), x = their plane-0 bits, y = their plane-1 bits.  Planes 0/1 only: a non-ACGT symbol then
 // looks like a base, which can only LOWER the mismatch count taken from the signature.
-__device__ __forceinline__ uint2 flank_sig(const ImageView &img, long long core_pos, uint32_t core_len) {
-    const long long before = core_pos - 16, after = core_pos + core_len;
-    return make_uint2((plane_bits(img.plane(0), before) & 0xffffu) | (plane_bits(img.plane(0), after) << 16),
-                      (plane_bits(img.plane(1), before) & 0xffffu) | (plane_bits(img.plane(1), after) << 16));
+template <class Src>
+__device__ __forceinline__ uint2 flank_sig(const Src &src, long long core_pos, uint32_t core_len) {
+    const long long before = core_pos - 16, after = core_pos + core_len;  // the front pad makes pos < 16 readable
+    return make_uint2((src.get(0, before) & 0xffffu) | (src.get(0, after) << 16),
+                      (src.get(1, before) & 0xffffu) | (src.get(1, after) << 16));
 }
 
-__global__ void __launch_bounds__(256) seed_fill_kernel(ImageView t, uint32_t n_pos, uint32_t core_len,
-                                                        uint32_t bits, uint32_t *__restrict__ cursor,
-                                                        uint32_t *__restrict__ pos, uint2 *__restrict__ sig) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pos) return;
-    bool ok;
-    const uint32_t b = core_bucket(t, p, core_len, bits, ok);
-    if (!ok) return;
-    const uint32_t slot = atomicAdd(cursor + b, 1u);
-    pos[slot] = p;
-    sig[slot] = flank_sig(t, p, core_len);  // the front pad makes p < 16 readable
+// Index passes.  A CTA takes kSeedChunk consecutive target positions and stages the words of the
+// three planes that their windows touch (one word before the chunk for the 16 bases ahead of a
+// core, kSeedHalo words after it for core + flank) in shared memory: the planes are read once,
+// coalesced, instead of 14 scattered words per position.  FILL = false counts the cores per
+// bucket; FILL = true takes a slot from the bucket's cursor and writes the 16-byte entry.
+constexpr int kSeedChunk = 2048;                       // positions per CTA: 8 per thread
+constexpr int kSeedHalo = 10;                          // words after the chunk: cores of up to 250 bases + 16 + slack
+constexpr int kSeedStage = kSeedChunk / 32 + 1 + kSeedHalo;
+template <bool FILL>
+__global__ void __launch_bounds__(256) seed_scan_kernel(ImageView t, uint32_t n_pos, uint32_t core_len, uint32_t bits,
+                                                        uint32_t b_lo, uint32_t b_hi, uint32_t *__restrict__ counters,
+                                                        uint4 *__restrict__ ent) {
+    __shared__ uint32_t stage[3][kSeedStage + 1];
+    const uint32_t base = blockIdx.x * (uint32_t)kSeedChunk;
+    const long long w0 = (long long)(base >> 5) - 1;  // the front pad makes word -1 readable
+    for (uint32_t i = threadIdx.x; i < 3u * (kSeedStage + 1); i += 256) {
+        const uint32_t p = i / (kSeedStage + 1), w = i - p * (kSeedStage + 1);
+        stage[p][w] = __ldg(t.plane((int)p) + w0 + w);
+    }
+    __syncthreads();
+    SmemBits src;
+    src.pl[0] = stage[0];
+    src.pl[1] = stage[1];
+    src.pl[2] = stage[2];
+    src.origin = w0 * 32;
+#pragma unroll 2
+    for (uint32_t j = 0; j < (uint32_t)kSeedChunk / 256; ++j) {
+        const uint32_t pos = base + j * 256 + threadIdx.x;  // a warp covers 32 consecutive positions: broadcast reads
+        if (pos >= n_pos) break;
+        bool ok;
+        const uint32_t b = core_bucket(src, pos, core_len, bits, ok);
+        if (!ok || b < b_lo || b >= b_hi) continue;
+        if (!FILL) {
+            atomicAdd(counters + b, 1u);
+        } else {
+            const uint2 sg = flank_sig(src, pos, core_len);
+            const uint32_t slot = atomicAdd(counters + b, 1u);
+            ent[slot] = make_uint4(pos, sg.x, sg.y, b);
+        }
+    }
 }
 
 // mismatches between the K-mer of `a` at pa and the K-mer of `b` at pb (b may hold non-ACGT
@@ -123,9 +165,17 @@ __device__ __forceinline__ uint32_t seed_entry_of(const SeedSelfRules &r, uint32
 struct SeedCtx {  // launch-wide constants
     ImageView q, rcq, t;
     uint32_t K, core_len, n_cores, bits, clamp;
+    uint32_t b_lo, b_hi;  // bucket range this launch answers (the index holds only these buckets)
     int strands, three, q_impure;
     SeedSelfRules self;
 };
+struct SeedItem;
+// the probe planes an item reads: the forward image or the reverse-complemented one (same geometry).
+// Selected as a scalar pointer: brace-initialising an image-holding struct from `strand ? cx.rcq : cx.q`
+// made nvcc 12.9 drop the selection and always read the forward planes.
+__device__ __forceinline__ GlobalBits probe_bits(const SeedCtx &cx, uint32_t strand) {
+    return GlobalBits(strand ? cx.rcq.base : cx.q.base, cx.q.stride);
+}
 struct SeedItem {  // one (probe K-mer, strand, core)
     uint32_t p, strand, c;  // probe position, 0 sense / 1 antisense, core number
     long long pp;           // position of the (reverse-complemented) K-mer in its image
@@ -161,7 +211,7 @@ __device__ __forceinline__ bool seed_item_setup(const SeedCtx &cx, uint32_t p, u
     const uint32_t nl = shift < 16 ? shift : 16u;
     const uint32_t after = cx.K - shift - cx.core_len;
     const uint32_t nr = after < 16 ? after : 16u;
-    const uint2 qs = flank_sig(img, it.pp + shift, cx.core_len);
+    const uint2 qs = flank_sig(probe_bits(cx, it.strand), it.pp + shift, cx.core_len);
     it.q0 = qs.x;
     it.q1 = qs.y;
     const uint32_t ml = nl ? (0xffffu << (16 - nl)) & 0xffffu : 0u;  // the LAST nl of the 16 bases before the core
@@ -200,8 +250,7 @@ __device__ __noinline__ void seed_verify(const SeedCtx &cx, const SeedItem &it, 
 
 // ---- query, warp per item: one warp per (probe position, strand, core) streams the bucket ----
 __global__ void __launch_bounds__(256) seed_query_kernel(SeedCtx cx, const uint32_t *__restrict__ off,
-                                                         const uint32_t *__restrict__ pos,
-                                                         const uint2 *__restrict__ sig, uint32_t q_begin,
+                                                         const uint4 *__restrict__ ent, uint32_t q_begin,
                                                          uint32_t q_end, uint32_t *__restrict__ best,
                                                          unsigned long long *__restrict__ occ) {
     const unsigned long long warp_id = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -212,14 +261,16 @@ __global__ void __launch_bounds__(256) seed_query_kernel(SeedCtx cx, const uint3
     SeedItem it;
     if (!seed_item_setup(cx, q_begin + (uint32_t)pi, (uint32_t)(warp_id - pi * per_probe), best, it)) return;
     bool ok;
-    const uint32_t b = core_bucket(it.strand ? cx.rcq : cx.q, it.pp + (long long)it.c * cx.core_len, cx.core_len,
-                                   cx.bits, ok);
-    if (!ok) return;  // cannot happen for pure-ACGT probes; kept for safety
+    const uint32_t b = core_bucket(probe_bits(cx, it.strand), it.pp + (long long)it.c * cx.core_len, cx.core_len, cx.bits,
+                                   ok);
+    if (!ok || b < cx.b_lo || b >= cx.b_hi) return;  // !ok cannot happen for pure-ACGT probes; kept for safety
     const uint32_t lo = __ldg(off + b), hi = __ldg(off + b + 1);
     if (occ && lane == 0) atomicAdd(occ + (blockIdx.x & (kSeedOccSlots - 1)), (unsigned long long)(hi - lo));
     uint32_t mine = it.cur;
-    for (uint32_t i = lo + lane; i < hi && mine; i += 32)
-        if (seed_sig_bound(it, __ldg(sig + i)) < mine) seed_verify(cx, it, __ldg(pos + i), mine);
+    for (uint32_t i = lo + lane; i < hi && mine; i += 32) {
+        const uint4 e = __ldg(ent + i);
+        if (seed_sig_bound(it, make_uint2(e.y, e.z)) < mine) seed_verify(cx, it, e.x, mine);
+    }
     mine = __reduce_min_sync(0xffffffffu, mine);
     if (lane == 0 && mine < it.cur) atomicMin(best + it.p, mine);
 }
@@ -245,17 +296,16 @@ __global__ void __launch_bounds__(256) seed_item_keys_kernel(SeedCtx cx, uint32_
     uint32_t key = 1u << cx.bits;  // inactive: sorts behind every bucket
     if (seed_item_setup(cx, q0 + pl, i - pl * per_probe, best, it)) {
         bool ok;
-        const uint32_t b = core_bucket(it.strand ? cx.rcq : cx.q, it.pp + (long long)it.c * cx.core_len, cx.core_len,
+        const uint32_t b = core_bucket(probe_bits(cx, it.strand), it.pp + (long long)it.c * cx.core_len, cx.core_len,
                                        cx.bits, ok);
-        if (ok) key = b;
+        if (ok && b >= cx.b_lo && b < cx.b_hi) key = b;
     }
     keys[i] = key;
     ids[i] = i;
 }
 
 __global__ void __launch_bounds__(256) seed_join_kernel(SeedCtx cx, const uint32_t *__restrict__ off,
-                                                        const uint32_t *__restrict__ pos,
-                                                        const uint2 *__restrict__ sig, uint32_t q0, uint32_t n_items,
+                                                        const uint4 *__restrict__ ent, uint32_t q0, uint32_t n_items,
                                                         const uint32_t *__restrict__ keys,
                                                         const uint32_t *__restrict__ ids, uint32_t *__restrict__ best,
                                                         unsigned long long *__restrict__ occ) {
@@ -301,26 +351,34 @@ __global__ void __launch_bounds__(256) seed_join_kernel(SeedCtx cx, const uint32
             const uint32_t n = hi - t0 < (uint32_t)kJoinTile ? hi - t0 : (uint32_t)kJoinTile;
             __syncthreads();  // the previous tile has been consumed
             for (uint32_t e = tid; e < n; e += 256) {
-                tile_pos[e] = __ldg(pos + t0 + e);
-                tile_sig[e] = __ldg(sig + t0 + e);
+                const uint4 v = __ldg(ent + t0 + e);  // one 16-byte entry: position + flank signature
+                tile_pos[e] = v.x;
+                tile_sig[e] = make_uint2(v.y, v.z);
             }
             __syncthreads();
             for (uint32_t j = r + warp; j < r_end; j += 8) {
                 uint32_t mine = s_mine[j];
                 if (mine == 0) continue;
                 const SeedItem it = items[j];
-                // 4 entries per lane and round: independent loads and POPCs in flight
-                for (uint32_t e0 = 0; e0 < n && mine; e0 += 128) {
+                // 4 entries per lane and round: independent loads and POPCs in flight; whole rounds
+                // run without bounds checks, only the last round of a tile tests e < n
+                const uint32_t n_full = n & ~127u;
+                uint32_t e0 = 0;
+                for (; e0 < n_full && mine; e0 += 128) {
                     uint32_t lb[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t e = e0 + u * 32 + lane;
-                        lb[u] = e < n ? seed_sig_bound(it, tile_sig[e]) : 0xffffffffu;
-                    }
+                    for (int u = 0; u < 4; ++u) lb[u] = seed_sig_bound(it, tile_sig[e0 + u * 32 + lane]);
                     if (min(min(lb[0], lb[1]), min(lb[2], lb[3])) < mine) {  // rare: one branch per 4 entries
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
                             if (lb[u] < mine) seed_verify(cx, it, tile_pos[e0 + u * 32 + lane], mine);
+                    }
+                }
+                if (e0 < n && mine) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t e = e0 + u * 32 + lane;
+                        if (e < n && seed_sig_bound(it, tile_sig[e]) < mine) seed_verify(cx, it, tile_pos[e], mine);
                     }
                 }
                 mine = __reduce_min_sync(0xffffffffu, mine);
@@ -345,28 +403,28 @@ size_t seed_scan_temp_bytes(uint32_t n_buckets) {
 
 // d_cnt: n_buckets+1 counters (zeroed by the caller), turned into bucket offsets d_off
 // (n_buckets+1 entries, d_off[n_buckets] = number of indexed cores); d_cursor: n_buckets+1
-// scratch; d_pos, d_sig: t.len entries
-cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t *d_cnt, uint32_t *d_off,
-                              uint32_t *d_cursor, uint32_t *d_pos, uint2 *d_sig, void *d_temp, size_t temp_bytes,
+// scratch; d_ent: t.len entries.  Only cores whose bucket lies in [b_lo, b_hi) are indexed.
+cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t b_lo, uint32_t b_hi, uint32_t *d_cnt,
+                              uint32_t *d_off, uint32_t *d_cursor, uint4 *d_ent, void *d_temp, size_t temp_bytes,
                               cudaStream_t st) {
     if (t.len < core_len) return cudaSuccess;
     const uint32_t bits = seed_bucket_bits(core_len), nb = 1u << bits;
     const uint32_t n_pos = t.len - core_len + 1;
-    const uint32_t grid = (n_pos + 255) / 256;
-    seed_count_kernel<<<grid, 256, 0, st>>>(t, n_pos, core_len, bits, d_cnt);
+    const uint32_t grid = (n_pos + kSeedChunk - 1) / kSeedChunk;
+    seed_scan_kernel<false><<<grid, 256, 0, st>>>(t, n_pos, core_len, bits, b_lo, b_hi, d_cnt, nullptr);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_cnt, d_off, (int)nb + 1, st);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyAsync(d_cursor, d_off, ((size_t)nb + 1) * 4, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return e;
-    seed_fill_kernel<<<grid, 256, 0, st>>>(t, n_pos, core_len, bits, d_cursor, d_pos, d_sig);
+    seed_scan_kernel<true><<<grid, 256, 0, st>>>(t, n_pos, core_len, bits, b_lo, b_hi, d_cursor, d_ent);
     return cudaGetLastError();
 }
 
 cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t K, uint32_t core_len,
-                              const uint32_t *d_off, const uint32_t *d_pos, const uint2 *d_sig, uint32_t q_begin,
-                              uint32_t q_end, uint32_t clamp, bool crick, bool three, bool q_impure,
+                              const uint32_t *d_off, const uint4 *d_ent, uint32_t q_begin, uint32_t q_end,
+                              uint32_t b_lo, uint32_t b_hi, uint32_t clamp, bool crick, bool three, bool q_impure,
                               SeedSelfRules self, uint32_t *d_best, unsigned long long *d_occ, cudaStream_t st) {
     if (q_begin >= q_end || t.len < K || q.len < K) return cudaSuccess;
     SeedCtx cx;
@@ -378,6 +436,8 @@ cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t 
     cx.n_cores = K / core_len;
     cx.bits = seed_bucket_bits(core_len);
     cx.clamp = clamp;
+    cx.b_lo = b_lo;
+    cx.b_hi = b_hi;
     cx.strands = crick ? 2 : 1;
     cx.three = three ? 1 : 0;
     cx.q_impure = q_impure ? 1 : 0;
@@ -394,7 +454,7 @@ cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t 
         for (uint32_t b = q_begin; b < q_end;) {
             const uint32_t e = (q_end - b > max_probes) ? b + max_probes : q_end;
             const unsigned long long w = (unsigned long long)(e - b) * per_probe;
-            seed_query_kernel<<<(unsigned)((w + 7) / 8), 256, 0, st>>>(cx, d_off, d_pos, d_sig, b, e, d_best, d_occ);
+            seed_query_kernel<<<(unsigned)((w + 7) / 8), 256, 0, st>>>(cx, d_off, d_ent, b, e, d_best, d_occ);
             const cudaError_t err = cudaGetLastError();
             if (err != cudaSuccess) return err;
             b = e;
@@ -426,8 +486,8 @@ cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t 
             err = cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, k_in, k_out, i_in, i_out, (int)n_items, 0,
                                                   (int)cx.bits + 1, st);
         if (err == cudaSuccess) {
-            seed_join_kernel<<<(n_items + kJoinItems - 1) / kJoinItems, 256, 0, st>>>(cx, d_off, d_pos, d_sig, b, n_items,
-                                                                                    k_out, i_out, d_best, d_occ);
+            seed_join_kernel<<<(n_items + kJoinItems - 1) / kJoinItems, 256, 0, st>>>(cx, d_off, d_ent, b, n_items, k_out,
+                                                                                    i_out, d_best, d_occ);
             err = cudaGetLastError();
         }
         b = e;

@@ -12,7 +12,8 @@ depends on the engine:
                                   lowers both K-mers of its pair), every rank keeps a complete
                                   minima array, thresholds are exchanged between slabs and the
                                   arrays meet in one all_reduce(MIN) at the end;
-  * targeted_distributed          seed-and-verify engine: probe K-mers are sharded, one
+  * targeted_distributed          seed-and-verify engine: the index BUCKETS are sharded (each rank
+                                  builds 1/world of the index and answers all probes for it), one
                                   all_reduce(MIN) at the end.
 A failure on rank 0 before the first broadcast (bad parameters, out of memory while packing) is
 carried to every rank in the metadata broadcast and raised everywhere - no rank is left waiting in
@@ -92,10 +93,15 @@ class CudaEngine:
         return hamm.diag_slabs_device(packed, both, part, nparts, slab_begin, slab_end, best.data_ptr(),
                                       torch.cuda.current_stream(self.device).cuda_stream)
 
-    # ---- targeted mode: seed-and-verify engine on a probe range ----
+    # ---- targeted mode: seed-and-verify engine on a probe range / on a share of the index buckets ----
     def seed(self, probes, targets, both: bool, clamp: int, core_len: int, b: int, e: int, best: torch.Tensor) -> int:
         return hamm.targeted_seed_device(probes, targets, both, clamp, core_len, b, e, best.data_ptr(),
                                          torch.cuda.current_stream(self.device).cuda_stream)
+
+    def seed_part(self, probes, targets, both: bool, clamp: int, core_len: int, part: int, nparts: int,
+                  best: torch.Tensor) -> int:
+        return hamm.targeted_seed_part_device(probes, targets, both, clamp, core_len, part, nparts, best.data_ptr(),
+                                              torch.cuda.current_stream(self.device).cuda_stream)
 
     def targeted_finalize(self, probes, best: torch.Tensor, clamp: int) -> torch.Tensor:
         out = torch.empty(best.numel(), dtype=torch.int16, device=self.device)
@@ -206,8 +212,9 @@ def targeted_distributed(target: Optional[np.ndarray], probes: Optional[np.ndarr
     """Targeted mode (-m0 -I) over the ranks of `group` on the seed-and-verify engine: rank 0 passes
     the assembly's sequence area and the probe concat (pure ACGT; probe sets with N / InDel go
     through hamm.targeted, which adds the wildcard pass), both packed sets are broadcast once,
-    every rank indexes the assembly and answers its slice of the probes, the minima meet in one
-    all_reduce(MIN).  rank 0 gets uint8[len(probes)] (0xFF where no K-mer starts), others None."""
+    every rank builds ITS SHARE OF THE INDEX BUCKETS (1/world of the index) and answers every probe
+    K-mer for those buckets, the minima meet in one all_reduce(MIN).  rank 0 gets
+    uint8[len(probes)] (0xFF where no K-mer starts), others None."""
     rank = dist.get_rank(group)
     world = dist.get_world_size(group)
     if engine is None:
@@ -224,8 +231,7 @@ def targeted_distributed(target: Optional[np.ndarray], probes: Optional[np.ndarr
     q_img, q_len, _ = _broadcast_packed(engine, probes, K, rank, world, group, check=check_probes)
     t_img, _, _ = _broadcast_packed(engine, target, K, rank, world, group)
     best = engine.new_best(q_len, K)
-    b, e = shard_bounds(0, q_len, world)[rank]
-    engine.seed(q_img, t_img, both, clamp, core, b, e, best)
+    engine.seed_part(q_img, t_img, both, clamp, core, rank, world, best)
     if world > 1:
         dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
     if rank != 0:

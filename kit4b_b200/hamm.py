@@ -76,7 +76,11 @@ SIGNATURES = {
                                                 ctypes.c_uint32, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
     "k4b_targeted_seed_device": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                                 ctypes.c_uint32, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
+    "k4b_targeted_seed_part_device": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32,
+                                                     ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
     "k4b_last_seed_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64)] * 2),
+    "k4b_hamm_histogram": (ctypes.c_int, [_u16p, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint64)]),
+    "k4b_histogram_device": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
     "k4b_targeted_finalize_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, _vp]),
     "k4b_diag_bootstrap_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
     "k4b_diag_bands_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp,
@@ -305,6 +309,15 @@ def targeted_seed_device(probes: Packed, targets: Packed, both_strands: bool, cl
     return n.value
 
 
+def targeted_seed_part_device(probes: Packed, targets: Packed, both_strands: bool, clamp: int, core_len: int, part: int,
+                              nparts: int, d_best_ptr: int, stream: int = 0) -> int:
+    """Seed engine on part `part` of `nparts` of the index BUCKETS against every probe K-mer."""
+    n = ctypes.c_int(0)
+    _check(load_lib().k4b_targeted_seed_part_device(probes.handle, targets.handle, int(both_strands), clamp, core_len,
+                                                    part, nparts, _vp(d_best_ptr), _vp(stream), ctypes.byref(n)))
+    return n.value
+
+
 def last_seed_info() -> dict:
     a, b = ctypes.c_uint64(0), ctypes.c_uint64(0)
     _check(load_lib().k4b_last_seed_info(ctypes.byref(a), ctypes.byref(b)))
@@ -323,6 +336,15 @@ def last_diag_info() -> dict:
 
 def best_finalize_device(g: Packed, d_best_ptr: int, d_out_ptr: int, stream: int = 0) -> None:
     _check(load_lib().k4b_best_finalize_device(g.handle, _vp(d_best_ptr), _vp(d_out_ptr), _vp(stream)))
+
+
+def histogram(minima, K: int) -> np.ndarray:
+    """Distribution of an exhaustive result: uint64[K+2], bin d = positions whose minimum is d, bin K+1 =
+    positions where no K-mer starts (GPU histogram, k4b_hamm_histogram)."""
+    m = np.ascontiguousarray(minima, dtype=np.uint16)
+    hist = np.zeros(K + 2, dtype=np.uint64)
+    _check(load_lib().k4b_hamm_histogram(m.ctypes.data_as(_u16p), len(m), K, hist.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+    return hist
 
 
 def packed_image_bytes(length: int) -> int:

@@ -116,6 +116,12 @@ def csv_to_bham(csv: str, bham: str):
     _check(load().k4bh_csv_to_bham(csv.encode(), bham.encode()))
 
 
+def hamming_dist(csvs: List[str], out: str):
+    """HammingDist, region-less mode: distribution of field 3 of the `"chrom",loci,hamming` rows."""
+    arr = (ctypes.c_char_p * len(csvs))(*[c.encode() for c in csvs])
+    _check(load().k4bh_hamming_dist(len(csvs), arr, out.encode()))
+
+
 def bham_to_csv(bham: str, csv: str):
     _check(load().k4bh_bham_to_csv(bham.encode(), csv.encode()))
 

@@ -87,6 +87,27 @@ class OracleEngine:
         torch.minimum(best[b:e], part, out=best[b:e])
         return 1
 
+    def seed_part(self, probes, targets, both, clamp, core_len, part, nparts, best):
+        # stand-in for a share of the index buckets: this rank answers every probe against ITS share of
+        # the target K-mers (interleaved starts); the union over the ranks is the whole target set
+        from oracle import hamm_oracle as ho
+        R = self.K // core_len - 1
+        assert self.K // (R + 1) == core_len
+        tvalid = ho.valid_starts(targets, self.K)
+        pvalid = ho.valid_starts(probes, self.K)
+        tpos = np.flatnonzero(tvalid)[part::nparts]
+        h = np.full(len(probes), self.K + 1, dtype=np.int32)
+        cpl = ho.CPL
+        tk = np.stack([targets[p:p + self.K] for p in tpos]) if len(tpos) else np.zeros((0, self.K), np.uint8)
+        for q in np.flatnonzero(pvalid):
+            km = probes[q:q + self.K]
+            d = (tk != km).sum(axis=1).min(initial=self.K + 1)
+            if both:
+                d = min(d, (tk != cpl[km[::-1]]).sum(axis=1).min(initial=self.K + 1))
+            h[q] = d
+        torch.minimum(best, torch.from_numpy(h), out=best)
+        return 1
+
     def targeted_finalize(self, probes, best, clamp):
         out = torch.minimum(best, torch.tensor(clamp, dtype=torch.int32)).to(torch.int16)
         from oracle import hamm_oracle as ho

@@ -189,6 +189,42 @@ def test_cli_targeted_output_file_equals_reference(mr, tmp_path):
     assert open(os.path.join(str(tmp_path), r["out"]), "rb").read() == open(os.path.join(GOLDEN, r["out"]), "rb").read()
 
 
+def _gz(src, dst):
+    import gzip
+    import shutil
+    with open(src, "rb") as fi, gzip.open(dst, "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    return dst
+
+
+@pytest.mark.parametrize("case", golden_cases()[::2], ids=case_id)
+def test_cli_reads_fasta_and_gzip_directly(case, tmp_path):
+    """-i genome.fa / genome.fa.gz (no genbioseq step): same bytes as the reference produced from the
+    bioseq the reference's own genbioseq made of that FASTA (Fasta.cpp:967-1209, genbioseq.cpp:356-446)."""
+    from conftest import golden_manifest
+    name, r = case
+    fa = os.path.join(GOLDEN, golden_manifest()[name]["fasta"])
+    want = open(os.path.join(GOLDEN, r["csv"]), "rb").read()
+    for src in (fa, _gz(fa, str(tmp_path / "g.fa.gz"))):
+        out = str(tmp_path / "out.csv")
+        _run_cli(["hammings", "-m1"] + (["-c"] if r["both"] else []) + ["-K%d" % r["K"], "-i", src, "-o", out])
+        assert open(out, "rb").read() == want, src
+
+
+@pytest.mark.parametrize("mr", _targeted_runs()[::2], ids=lambda mr: mr[1]["out"])
+def test_cli_targeted_from_fasta_without_suffix_array_file(mr, tmp_path):
+    """-m0 -i assembly.fa(.gz) -I probes.fa(.gz): the engines need only the sequence area of the
+    suffix-array file, which the entries determine - same bytes as the reference run on .sfx + .seq."""
+    m, r = mr
+    tfa = os.path.join(GOLDEN, m["target_fasta"])
+    pfa = os.path.join(GOLDEN, m["probes"][r["probes"]]["fasta"])
+    for ti, pi in ((tfa, _gz(pfa, str(tmp_path / "p.fa.gz"))), (_gz(tfa, str(tmp_path / "t.fa.gz")), pfa)):
+        args = ["hammings", "-m0"] + (["-c"] if r["both"] else []) + ["-K%d" % r["K"], "-r%d" % r["R"], "-S%d" % r["fmt"],
+                                                                      "-i", ti, "-I", pi, "-o", r["out"]]
+        _run_cli(args, cwd=str(tmp_path))
+        assert open(os.path.join(str(tmp_path), r["out"]), "rb").read() == open(os.path.join(GOLDEN, r["out"]), "rb").read()
+
+
 def test_targeted_wildcards_and_n_rule(oracle):
     """probe symbols >= N are wildcards, > 4 of them report 0, target N never matches."""
     rng = np.random.default_rng(501)
@@ -328,3 +364,20 @@ def test_config1_full_output_md5_equals_reference_run(tmp_path):
     data = open(out, "rb").read()
     assert len(data) == 15_888_524 and data.count(b"\n") == 999_977
     assert hashlib.md5(data).hexdigest() == "f1b2e85a8f64dc68dcc60cc2403cfb1a"
+
+
+def test_gpu_histogram_and_cli_distribution_file(tmp_path):
+    """k4b_hamm_histogram (shared-memory privatised GPU histogram of the minima) equals np.bincount, and
+    `k4b_hammings --dist` writes what the HammingDist drop-in makes of the CSV of the same run."""
+    from conftest import golden_manifest
+    from kit4b_b200 import hamm, hostlib
+    rng = np.random.default_rng(77)
+    for K, n in ((25, 1_000_003), (5000, 70_001), (12, 5)):
+        v = rng.integers(0, K + 2, size=n).astype(np.uint16)
+        assert np.array_equal(hamm.histogram(v, K), np.bincount(v, minlength=K + 2).astype(np.uint64))
+    seq = os.path.join(GOLDEN, golden_manifest()["multiword"]["bioseq"])
+    csv, dist, want = str(tmp_path / "o.csv"), str(tmp_path / "d.csv"), str(tmp_path / "w.csv")
+    _run_cli(["hammings", "-m1", "-c", "-K50", "-i", seq, "-o", csv, "--dist=" + dist])
+    assert open(csv, "rb").read() == open(os.path.join(GOLDEN, "multiword.K50c.csv"), "rb").read()
+    hostlib.hamming_dist([csv], want)
+    assert open(dist, "rb").read() == open(want, "rb").read()

@@ -214,3 +214,43 @@ def test_targeted_distributed_single_rank_on_cuda(oracle):
             assert np.array_equal(targeted_distributed(target, probes, K, R, both), oracle.targeted_brute(target, probes, K, R, both))
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("join", ["0", "1"])
+@pytest.mark.parametrize("K,R,both,nparts", [(32, 3, True, 3), (100, 4, True, 2), (25, 2, False, 8)])
+def test_seed_engine_bucket_parts_combine_to_the_full_result(oracle, monkeypatch, K, R, both, nparts, join):
+    """k4b_targeted_seed_part_device: every part indexes only its share of the core buckets and
+    answers all probes for it; the element-wise minimum over the parts (what the multi-GPU drivers
+    all_reduce) equals the oracle, in both schedules."""
+    import torch
+    monkeypatch.setenv("K4B_SEED_JOIN", join)
+    target, probes = _planted(5200 + K, [7000, 2500, 3000])
+    want = oracle.targeted_brute(target, probes, K, R, both)
+    core = K // (R + 1)
+    clamp = K // core
+    t, q = hamm.Packed.from_host(target, K), hamm.Packed.from_host(probes, K)
+    try:
+        L = len(probes)
+        total = torch.empty(L, dtype=torch.int32, device="cuda")
+        hamm.best_init_device(total.data_ptr(), L, K)
+        cores_seen = 0
+        for part in range(nparts):
+            best = torch.empty(L, dtype=torch.int32, device="cuda")
+            hamm.best_init_device(best.data_ptr(), L, K)
+            assert hamm.targeted_seed_part_device(q, t, both, clamp, core, part, nparts, best.data_ptr()) > 0
+            cores_seen += hamm.last_seed_info()["indexed_cores"]
+            total = torch.minimum(total, best)
+        full = torch.empty(L, dtype=torch.int32, device="cuda")
+        hamm.best_init_device(full.data_ptr(), L, K)
+        hamm.targeted_seed_device(q, t, both, clamp, core, 0, L, full.data_ptr())
+        assert cores_seen == hamm.last_seed_info()["indexed_cores"]  # the parts partition the index
+        out = torch.empty(L, dtype=torch.int16, device="cuda")
+        hamm.targeted_finalize_device(q, total.data_ptr(), clamp, out.data_ptr())
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().view(np.uint16)
+        res = np.full(L, 0xFF, dtype=np.uint8)
+        res[got <= K] = got[got <= K].astype(np.uint8)
+        assert np.array_equal(res, want)
+    finally:
+        t.free()
+        q.free()

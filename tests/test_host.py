@@ -89,6 +89,28 @@ def test_fasta_front_end_equals_reference_genbioseq(oracle, tmp_path):
         assert np.array_equal(got, want)
 
 
+def test_gzip_fasta_reads_like_plain_fasta(oracle, tmp_path):
+    """read_fasta goes through zlib: .fa.gz, CRLF line ends and a last line without newline give the
+    same entries as the plain file."""
+    import gzip
+    case = golden_manifest()["nonacgt"]
+    plain = open(os.path.join(GOLDEN, case["fasta"]), "rb").read()
+    variants = {"g.fa.gz": gzip.compress(plain), "crlf.fa": plain.replace(b"\n", b"\r\n"),
+                "nonl.fa.gz": gzip.compress(plain.rstrip(b"\n"))}
+    ref = oracle.read_bioseq(os.path.join(GOLDEN, case["bioseq"]))
+    for fn, data in variants.items():
+        path, out = str(tmp_path / fn), str(tmp_path / (fn + ".seq"))
+        open(path, "wb").write(data)
+        hostlib.fasta_to_bioseq(path, out, "x")
+        mine = oracle.read_bioseq(out)
+        assert [n for n, _ in mine] == [n for n, _ in ref], fn
+        assert all(np.array_equal(a, b) for (_, a), (_, b) in zip(mine, ref)), fn
+    bad = str(tmp_path / "bad.fa.gz")
+    open(bad, "wb").write(gzip.compress(plain)[:-20])  # truncated stream: an error, not silent data
+    with pytest.raises(RuntimeError):
+        hostlib.fasta_to_bioseq(bad, str(tmp_path / "bad.seq"), "x")
+
+
 def test_merge_matches_reference(tmp_path):
     m = golden_manifest()["__merge__"]
     into = str(tmp_path / "into.csv")
@@ -155,3 +177,51 @@ def test_bham_round_trip(tmp_path):
     assert subprocess.run([exe, "-m4", "-i", src, "-o", b2], capture_output=True).returncode == 0
     assert subprocess.run([exe, "-m5", "-i", b2, "-o", back2], capture_output=True).returncode == 0
     assert open(b2, "rb").read() == raw and open(back2).read() == open(back).read()
+
+
+def _expected_distribution(values):
+    """HammingDist's file layout (HammingDist/HammingDist.cpp:616-700) for a list of distances, field-3
+    semantics: rows 0 .. max-1 (the reference's loops stop before the largest value), %f proportions."""
+    counts = np.bincount(np.asarray(values, dtype=np.int64))
+    maxh = len(counts) - 1
+    out = ',"All","Proportion All","Cumulative All"'
+    total = int(counts[:maxh].sum())
+    cum = 0.0
+    for d in range(maxh):
+        prop = counts[d] / total if total else 0.0
+        cum += prop
+        out += "\n%d,%d,%f,%f" % (d, counts[d], prop, cum)
+    return out.encode()
+
+
+def test_hammingdist_distribution_of_exhaustive_csv(tmp_path):
+    """region-less HammingDist: rows of a hammings -m1 CSV (descriptor row skipped) and of its -m5 form
+    (header row skipped) give the same distribution file; two inputs add up; the binary takes the
+    reference's flags."""
+    import subprocess
+    src = os.path.join(GOLDEN, "multiword.K50c.csv")
+    values = [int(line.rsplit(",", 1)[1]) for line in open(src).read().split("\n")[1:] if line]
+    want = _expected_distribution(values)
+    out = str(tmp_path / "dist.csv")
+    hostlib.hamming_dist([src], out)
+    assert open(out, "rb").read() == want
+    b, back = str(tmp_path / "h.bham"), str(tmp_path / "back.csv")
+    hostlib.csv_to_bham(src, b)
+    hostlib.bham_to_csv(b, back)  # carries the "Chrom","Loci","Hamming" header line
+    hostlib.hamming_dist([back], out)
+    assert open(out, "rb").read() == want
+    hostlib.hamming_dist([src, back], out)
+    assert open(out, "rb").read() == _expected_distribution(values + values)
+    exe = os.path.join(os.path.dirname(hostlib.cli_path()), "k4b_hammingdist")
+    out2 = str(tmp_path / "dist2.csv")
+    p = subprocess.run([exe, "-m0", "-s0", "-r2000", "-i", str(tmp_path / "*.csv").replace("*.csv", "back.csv"), "--incsv=" + src,
+                        "-o", out2], capture_output=True)
+    assert p.returncode == 0, p.stdout
+    assert open(out2, "rb").read() == _expected_distribution(values + values)
+    assert subprocess.run([exe, "-h"], capture_output=True).returncode == 1
+    assert subprocess.run([exe, "-i", src], capture_output=True).returncode == 1           # -o is required
+    assert subprocess.run([exe, "-i", src, "-o", out2, "-I", "genes.bed"], capture_output=True).returncode == 1  # region mode
+    bad = str(tmp_path / "bad.csv")
+    open(bad, "w").write('"chr1",5\n')
+    with pytest.raises(RuntimeError):
+        hostlib.hamming_dist([bad], out)
