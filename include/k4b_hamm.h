@@ -221,6 +221,22 @@ int k4b_last_seed_info(uint64_t *occurrences, uint64_t *indexed_cores);
 int k4b_targeted_finalize_device(k4b_packed *probes, const uint32_t *d_best, uint32_t clamp,
                                  uint16_t *d_out_min, void *stream);
 
+/* ---- where the reference's own answer may differ ------------------------------------------------
+ * The reference's pigeonhole search walks at most MaxCoreDepth suffix-array entries per core and gives
+ * a core up when it has more copies than that (SfxArray.cpp:4480-4494; MaxCoreDepth by -s,
+ * hammings.cpp:2366-2386, times a per-level multiplier, SfxArray.cpp:4297-4311); on repeat-rich
+ * assemblies it then reports a LARGER value than the true minimum.  The seed engine has no such cut.
+ * k4b_set_reference_sensitivity tells it the caller's -s (0 default, 1 more, 2 ultra, 3 less);
+ * k4b_last_depth_cut returns, for the most recent seed-engine k4b_hamm_targeted[_z] call of this thread,
+ * how many probe K-mers (a) hold a core occurring more than *max_copies times in the assembly (the cap of
+ * the last cascade level) and (b) were answered below the "not found" value - the only places where a
+ * file diff against the reference can show a difference.  Device API: k4b_seed_watch_depth arms the next
+ * k4b_targeted_seed[_part]_device call of this thread (d_deep: one byte per probe position, zeroed by the
+ * caller, set to 1 for flagged positions; pass 0 / NULL to disarm). */
+int k4b_set_reference_sensitivity(int sensitivity);
+int k4b_last_depth_cut(uint64_t *probe_kmers, uint32_t *max_copies);
+int k4b_seed_watch_depth(uint32_t max_copies, uint8_t *d_deep);
+
 /* ---- distribution of the minima -------------------------------------------------------------
  * The table `hammings` logs after an exhaustive run (hammings.cpp:2939-2962) and the downstream
  * HammingDist tool tabulates from the CSV (HammingDist/HammingDist.cpp:371-705): hist[d] = number of

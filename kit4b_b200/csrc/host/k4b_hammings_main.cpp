@@ -191,6 +191,7 @@ static int run_restricted(const Options &o) {
         flat.assign(plen, 0xff);
         const auto t0 = std::chrono::steady_clock::now();
         if ((rc = gpu_ready())) return rc;
+        k4b_set_reference_sensitivity(o.sensitivity);
         rc = k4b_hamm_targeted(sfx.seq.data(), sfx.seq.size(), g.concat.data(), plen, K, o.rhamm, o.crick ? 1 : 0, 0,
                                plen, flat.data());
         secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -214,6 +215,7 @@ static int run_restricted(const Options &o) {
         // -z (hammings.cpp:228) takes effect only here: with -I the reference passes entry 0 and
         // the filter never fires (hammings.cpp:1691-1694)
         if ((rc = gpu_ready())) return rc;
+        k4b_set_reference_sensitivity(o.sensitivity);
         rc = k4b_hamm_targeted_z(sfx.seq.data(), sfx.seq.size(), K, o.rhamm, o.crick ? 1 : 0, o.intrainterboth, 0, 0,
                                  flat.data());
         secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -224,6 +226,20 @@ static int run_restricted(const Options &o) {
     }
     logmsg(2, "Engine: %.3f s for %llu probe K-mers vs %zu target bases", secs,
            (unsigned long long)g.num_subseqs, sfx.seq.size());
+    {   // where a file diff against the reference can legitimately differ (its depth cut, SfxArray.cpp:4487-4494)
+        uint64_t deep = 0;
+        uint32_t cap = 0;
+        if (k4b_last_depth_cut(&deep, &cap) == 0) {
+            if (deep)
+                logmsg(2, "%llu probe K-mers answered below the not-found value hold a core with more than %u copies in the "
+                          "assembly: the reference (-s%d) truncates its search of such cores and may report a larger value "
+                          "there; the values written here are the exact minima",
+                       (unsigned long long)deep, cap, o.sensitivity);
+            else
+                logmsg(2, "No probe K-mer holds a core with more than %u copies: the reference's depth cut (-s%d) cannot fire",
+                       cap, o.sensitivity);
+        }
+    }
 
     // per-loci array H[sum of entry lengths] preset 0xFF (hammings.cpp:2336-2354); loci that the
     // reference's chunk scheduler would not sample stay 0xFF (hammings.cpp:1615-1674 with

@@ -70,6 +70,7 @@ struct NcclApi {
 constexpr int kNcclUint8 = 1;   // ncclUint8 in nccl.h
 constexpr int kNcclUint32 = 3;  // ncclUint32
 constexpr int kNcclMin = 3;     // ncclMin
+constexpr int kNcclMax = 2;     // ncclMax
 
 struct Engine {
     std::vector<int> devs;
@@ -973,6 +974,46 @@ extern "C" int k4b_last_seed_info(uint64_t *occurrences, uint64_t *indexed_cores
 // work, both combining by element-wise minimum of d_best: a RANGE of probe K-mers [q_begin, q_end)
 // against the whole index, or (part, nparts) = a share of the index BUCKETS against all probes -
 // then only 1/nparts of the index is built, which is what scales when the index build matters.
+// Where the reference's answer may differ from the exact one.  CSfxArray::LocateHamming walks at most
+// MaxCoreDepth suffix-array entries per core and gives a core up after MinCoreDepth entries when it has
+// more copies than that (SfxArray.cpp:4480-4494); hammings passes MaxCoreDepth = {10000, 20000, 50000,
+// 5000} for -s 0..3 (hammings.cpp:2366-2386), multiplied by 10 / 8 / 4 / 2 / 1 on the cascade levels
+// Rmax = 1 / 2 / 3 / 4 / >= 5 (SfxArray.cpp:4297-4311).  The seed engine has no such cut; it can flag the
+// probe K-mers that hold a core (of the last cascade level = the index's core length) with more copies.
+static thread_local struct {
+    int sensitivity = 0;          // -s of the host (k4b_set_reference_sensitivity)
+    uint32_t cap = 0;             // device-API watch: entries per bucket above which a probe is flagged
+    uint8_t *d_deep = nullptr;    // device-API watch: one byte per probe position (caller-owned)
+    unsigned long long last_count = 0;  // host-buffer calls: flagged probe K-mers answered below "not found"
+    uint32_t last_cap = 0;
+    bool last_valid = false;
+} g_depth;
+
+static uint32_t reference_depth_cap(int sensitivity, int R) {
+    static const uint32_t max_depth[4] = {10000u, 20000u, 50000u, 5000u};
+    const uint32_t mult = R <= 1 ? 10u : R == 2 ? 8u : R == 3 ? 4u : R == 4 ? 2u : 1u;
+    return mult * max_depth[sensitivity & 3];
+}
+
+extern "C" int k4b_set_reference_sensitivity(int sensitivity) {
+    if (sensitivity < 0 || sensitivity > 3) return fail(K4B_ERR_PARAMS, "sensitivity %d outside 0..3", sensitivity);
+    g_depth.sensitivity = sensitivity;
+    return K4B_OK;
+}
+
+extern "C" int k4b_seed_watch_depth(uint32_t max_copies, uint8_t *d_deep) {
+    g_depth.cap = max_copies;
+    g_depth.d_deep = d_deep;
+    return K4B_OK;
+}
+
+extern "C" int k4b_last_depth_cut(uint64_t *probe_kmers, uint32_t *max_copies) {
+    if (!g_depth.last_valid) return fail(K4B_ERR_PARAMS, "no seed-engine host call recorded on this thread");
+    if (probe_kmers) *probe_kmers = g_depth.last_count;
+    if (max_copies) *max_copies = g_depth.last_cap;
+    return K4B_OK;
+}
+
 static int seed_run(k4b_packed *probes, k4b_packed *targets, int both_strands, uint32_t clamp, uint32_t core_len,
                     uint32_t q_begin, uint32_t q_end, uint32_t part, uint32_t nparts, uint32_t *d_best, void *stream,
                     int *launches) {
@@ -1019,7 +1060,7 @@ static int seed_run(k4b_packed *probes, k4b_packed *targets, int both_strands, u
     if (e == cudaSuccess)
         e = launch_seed_query(probes->view(), crick ? probes->rc_view() : probes->view(), targets->view(), K, core_len,
                               d_off, d_ent, q_begin, q_end, b_lo, b_hi, clamp, crick, targets->has_non_acgt != 0,
-                              probes->has_non_acgt != 0, self, d_best, d_occ, st);
+                              probes->has_non_acgt != 0, self, g_depth.cap, g_depth.d_deep, d_best, d_occ, st);
     if (e == cudaSuccess) e = g_tp.end(st);
     if (e == cudaSuccess && !g_h_seed) e = cudaMallocHost(&g_h_seed, (kSeedOccSlots + 1) * 8);
     if (e == cudaSuccess) e = cudaMemcpyAsync(g_h_seed, d_occ, kSeedOccSlots * 8, cudaMemcpyDeviceToHost, st);
@@ -1345,15 +1386,17 @@ static int run_exhaustive_diag(const uint8_t *concat, uint32_t len, uint32_t K, 
 // POPC engine).  Devices split the index BUCKETS (seed: each builds and joins its share of the
 // index against all probes) or the diagonals (bands); minima meet in one ncclAllReduce(min).
 static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8_t *q_concat, uint32_t q_len,
-                            uint32_t K, int both, uint32_t clamp, uint32_t core_len, bool allow_seed,
+                            uint32_t K, int R, int both, uint32_t clamp, uint32_t core_len, bool allow_seed,
                             bool allow_diag, uint8_t *out_h, int *used) {
     *used = 0;
     RC(ensure_init());
     const int n = (int)g_eng.devs.size();
     PhaseTrace trace;
     std::vector<k4b_packed *> qs, ts;
-    std::vector<DevScratch> bests(n);
-    DevScratch d_out;
+    std::vector<DevScratch> bests(n), deeps(n);
+    DevScratch d_out, d_deep_count;
+    const uint32_t depth_cap = reference_depth_cap(g_depth.sensitivity, R);
+    g_depth.last_valid = false;
     bool use_seed = false;
     int rc = 0;
     do {
@@ -1412,7 +1455,8 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
         {
             cudaError_t e = cudaSetDevice(g_eng.devs[0]);
             if (e == cudaSuccess) e = d_out.alloc((size_t)q_len * 2, g_eng.streams[0]);
-            if (e == cudaSuccess && !(h_out = (uint16_t *)pinned_result(0, (size_t)q_len * 2))) e = cudaErrorMemoryAllocation;
+            // results + (after them, 8-byte aligned) the depth-watch count
+            if (e == cudaSuccess && !(h_out = (uint16_t *)pinned_result(0, (size_t)q_len * 2 + 16))) e = cudaErrorMemoryAllocation;
             if (e != cudaSuccess) {
                 rc = fail(cuda_code(e), "result buffers: %s", cudaGetErrorString(e));
                 break;
@@ -1421,16 +1465,20 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
         for (int i = 0; i < n && !rc; ++i) {
             cudaError_t e = cudaSetDevice(g_eng.devs[i]);
             if (e == cudaSuccess) e = bests[i].alloc((size_t)q_len * 4, g_eng.streams[i]);
+            if (e == cudaSuccess && use_seed) e = deeps[i].alloc(q_len, g_eng.streams[i]);
+            if (e == cudaSuccess && use_seed) e = cudaMemsetAsync(deeps[i].p, 0, q_len, g_eng.streams[i]);
             if (e != cudaSuccess) {
                 rc = fail(cuda_code(e), "minima buffer: %s", cudaGetErrorString(e));
                 break;
             }
             rc = k4b_best_init_device(bests[i].as<uint32_t>(), q_len, K, g_eng.streams[i]);
             if (rc) break;
-            if (use_seed)  // device i: its share of the index buckets, all probes
+            if (use_seed) {  // device i: its share of the index buckets, all probes
+                k4b_seed_watch_depth(depth_cap, deeps[i].as<uint8_t>());
                 rc = seed_run(qs[i], ts[i], both, clamp, core_len, 0, q_len, (uint32_t)i, (uint32_t)n,
                               bests[i].as<uint32_t>(), g_eng.streams[i], nullptr);
-            else
+                k4b_seed_watch_depth(0, nullptr);
+            } else
                 rc = k4b_targeted_diag_device(qs[i], ts[i], both, clamp, (uint32_t)i, (uint32_t)n, bests[i].as<uint32_t>(),
                                               g_eng.streams[i], nullptr);
         }
@@ -1447,13 +1495,28 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
             int nr = g_eng.nccl.GroupStart();
             for (int i = 0; i < n && !nr; ++i)
                 nr = g_eng.nccl.AllReduce(bests[i].p, bests[i].p, q_len, kNcclUint32, kNcclMin, g_eng.comms[i], g_eng.streams[i]);
-            const int nr2 = g_eng.nccl.GroupEnd();
+            int nr2 = g_eng.nccl.GroupEnd();
+            if (!nr && !nr2 && use_seed) {  // the depth flags of the bucket shards: element-wise maximum
+                nr = g_eng.nccl.GroupStart();
+                for (int i = 0; i < n && !nr; ++i)
+                    nr = g_eng.nccl.AllReduce(deeps[i].p, deeps[i].p, q_len, kNcclUint8, kNcclMax, g_eng.comms[i], g_eng.streams[i]);
+                nr2 = g_eng.nccl.GroupEnd();
+            }
             if (nr || nr2) {
-                rc = fail(K4B_ERR_NCCL, "ncclAllReduce(min): %s", g_eng.nccl.GetErrorString(nr ? nr : nr2));
+                rc = fail(K4B_ERR_NCCL, "ncclAllReduce: %s", g_eng.nccl.GetErrorString(nr ? nr : nr2));
                 break;
             }
         }
         cudaError_t e = cudaSetDevice(g_eng.devs[0]);
+        unsigned long long *h_count = (unsigned long long *)((char *)h_out + (((size_t)q_len * 2 + 7) & ~(size_t)7));
+        if (use_seed) {
+            if (e == cudaSuccess) e = d_deep_count.alloc(8, g_eng.streams[0]);
+            if (e == cudaSuccess) e = cudaMemsetAsync(d_deep_count.p, 0, 8, g_eng.streams[0]);
+            if (e == cudaSuccess)
+                e = launch_seed_deep_count(deeps[0].as<uint8_t>(), bests[0].as<uint32_t>(), qs[0]->view(), q_len, clamp,
+                                           d_deep_count.as<unsigned long long>(), g_eng.streams[0]);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(h_count, d_deep_count.p, 8, cudaMemcpyDeviceToHost, g_eng.streams[0]);
+        }
         if ((rc = k4b_targeted_finalize_device(qs[0], bests[0].as<uint32_t>(), clamp, d_out.as<uint16_t>(), g_eng.streams[0]))) break;
         if (use_seed)  // the wildcard probe K-mers the seed engine skipped
             for (size_t k = 0; k < impure.size() && !rc; ++k)
@@ -1474,15 +1537,22 @@ static int run_targeted_big(const uint8_t *t_concat, uint32_t t_len, const uint8
         trace.mark("kernels + D2H");
         for (uint32_t p = 0; p < q_len; ++p)
             if (h_out[p] <= K) out_h[p] = (uint8_t)h_out[p];
+        if (use_seed) {
+            g_depth.last_count = *h_count;
+            g_depth.last_cap = depth_cap;
+            g_depth.last_valid = true;
+        }
     } while (0);
     for (int i = 0; i < n; ++i) {
         cudaSetDevice(g_eng.devs[i]);
         bests[i].release();
+        deeps[i].release();
         if ((size_t)i < qs.size() && qs[i]) k4b_packed_free(qs[i]);
         if ((size_t)i < ts.size() && ts[i] && !((size_t)i < qs.size() && ts[i] == qs[i])) k4b_packed_free(ts[i]);
     }
     cudaSetDevice(g_eng.devs[0]);
     d_out.release();
+    d_deep_count.release();
     trace.mark("free");
     return rc;
 }
@@ -1565,7 +1635,7 @@ extern "C" int k4b_hamm_targeted(const uint8_t *target_concat, uint64_t target_l
         const int eng = engine_setting();
         if (q_begin == 0 && q_end == tl && (eng == 0 || eng == 3) && tl >= 4096) {
             int used = 0;
-            const int rc = run_targeted_big(target_concat, tl, nullptr, 0, K, both_strands, std::min(notfound, 20u), core,
+            const int rc = run_targeted_big(target_concat, tl, nullptr, 0, K, R, both_strands, std::min(notfound, 20u), core,
                                             true, false, out_h, &used);
             if (used || rc) return rc;
         }
@@ -1581,7 +1651,7 @@ extern "C" int k4b_hamm_targeted(const uint8_t *target_concat, uint64_t target_l
         const bool big = (uint64_t)probe_len * target_len >= (1ull << 32);
         if (whole && eng != 1) {
             int used = 0;
-            const int rc = run_targeted_big(target_concat, (uint32_t)target_len, probe_concat, probe_len, K, both_strands,
+            const int rc = run_targeted_big(target_concat, (uint32_t)target_len, probe_concat, probe_len, K, R, both_strands,
                                             notfound, core, eng == 0 || eng == 3, eng == 2 || (eng != 1 && big), out_h,
                                             &used);
             if (used || rc) return rc;

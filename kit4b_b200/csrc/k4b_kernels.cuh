@@ -151,7 +151,13 @@ cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t b_lo, uin
 cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t K, uint32_t core_len,
                               const uint32_t *d_off, const uint4 *d_ent, uint32_t q_begin, uint32_t q_end,
                               uint32_t b_lo, uint32_t b_hi, uint32_t clamp, bool crick, bool three, bool q_impure,
-                              SeedSelfRules self, uint32_t *d_best, unsigned long long *d_occ, cudaStream_t st);
+                              SeedSelfRules self, uint32_t depth_cap, uint8_t *d_deep, uint32_t *d_best,
+                              unsigned long long *d_occ, cudaStream_t st);
+// d_deep (nullable, one byte per probe position, zeroed by the caller): set to 1 where a core of the probe
+// K-mer has more than depth_cap index entries; launch_seed_deep_count adds to *d_count the flagged valid
+// probe K-mers whose minimum lies below clamp
+cudaError_t launch_seed_deep_count(const uint8_t *d_deep, const uint32_t *d_best, ImageView q, uint32_t n, uint32_t clamp,
+                                   unsigned long long *d_count, cudaStream_t st);
 constexpr int kSeedOccSlots = 1024;  // d_occ (nullable): bucket entries streamed, summed over these slots
 cudaError_t launch_microbench(int which, int iters, uint32_t *d_sink, int *blocks, int *threads,
                               int *ops_per_thread_iter, cudaStream_t st);

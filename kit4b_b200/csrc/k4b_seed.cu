@@ -166,6 +166,10 @@ struct SeedCtx {  // launch-wide constants
     ImageView q, rcq, t;
     uint32_t K, core_len, n_cores, bits, clamp;
     uint32_t b_lo, b_hi;  // bucket range this launch answers (the index holds only these buckets)
+    // depth watch (nullable): deep[p] = 1 for every probe position p that holds a core whose bucket has
+    // more than depth_cap entries - where the reference truncates its search (SfxArray.cpp:4487-4494)
+    uint32_t depth_cap;
+    uint8_t *deep;
     int strands, three, q_impure;
     SeedSelfRules self;
 };
@@ -266,6 +270,7 @@ __global__ void __launch_bounds__(256) seed_query_kernel(SeedCtx cx, const uint3
     if (!ok || b < cx.b_lo || b >= cx.b_hi) return;  // !ok cannot happen for pure-ACGT probes; kept for safety
     const uint32_t lo = __ldg(off + b), hi = __ldg(off + b + 1);
     if (occ && lane == 0) atomicAdd(occ + (blockIdx.x & (kSeedOccSlots - 1)), (unsigned long long)(hi - lo));
+    if (cx.deep && lane == 0 && hi - lo > cx.depth_cap) cx.deep[it.p] = 1;
     uint32_t mine = it.cur;
     for (uint32_t i = lo + lane; i < hi && mine; i += 32) {
         const uint4 e = __ldg(ent + i);
@@ -347,6 +352,7 @@ __global__ void __launch_bounds__(256) seed_join_kernel(SeedCtx cx, const uint32
         const uint32_t lo = __ldg(off + key), hi = __ldg(off + key + 1);
         if (occ && tid == 0)
             atomicAdd(occ + (blockIdx.x & (kSeedOccSlots - 1)), (unsigned long long)(hi - lo) * (r_end - r));
+        if (cx.deep && hi - lo > cx.depth_cap && tid < r_end - r) cx.deep[items[r + tid].p] = 1;
         for (uint32_t t0 = lo; t0 < hi; t0 += kJoinTile) {
             const uint32_t n = hi - t0 < (uint32_t)kJoinTile ? hi - t0 : (uint32_t)kJoinTile;
             __syncthreads();  // the previous tile has been consumed
@@ -391,6 +397,23 @@ __global__ void __launch_bounds__(256) seed_join_kernel(SeedCtx cx, const uint32
         atomicMin(best + items[tid].p, s_mine[tid]);
 }
 
+// probe K-mers flagged by the depth watch that were answered below the "not found" value: only there
+// can a truncated search of the reference have missed the hit this engine reports
+__global__ void __launch_bounds__(256) seed_deep_count_kernel(const uint8_t *__restrict__ deep,
+                                                              const uint32_t *__restrict__ best, ImageView q, uint32_t n,
+                                                              uint32_t clamp, unsigned long long *__restrict__ count) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool hit = p < n && deep[p] && best[p] < clamp && ((q.valid()[p >> 5] >> (p & 31)) & 1u);
+    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+}
+cudaError_t launch_seed_deep_count(const uint8_t *d_deep, const uint32_t *d_best, ImageView q, uint32_t n, uint32_t clamp,
+                                   unsigned long long *d_count, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    seed_deep_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_deep, d_best, q, n, clamp, d_count);
+    return cudaGetLastError();
+}
+
 uint32_t seed_bucket_bits(uint32_t core_len) {
     return 2 * core_len < kSeedMaxBits ? 2 * core_len : kSeedMaxBits;
 }
@@ -425,7 +448,8 @@ cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t b_lo, uin
 cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t K, uint32_t core_len,
                               const uint32_t *d_off, const uint4 *d_ent, uint32_t q_begin, uint32_t q_end,
                               uint32_t b_lo, uint32_t b_hi, uint32_t clamp, bool crick, bool three, bool q_impure,
-                              SeedSelfRules self, uint32_t *d_best, unsigned long long *d_occ, cudaStream_t st) {
+                              SeedSelfRules self, uint32_t depth_cap, uint8_t *d_deep, uint32_t *d_best,
+                              unsigned long long *d_occ, cudaStream_t st) {
     if (q_begin >= q_end || t.len < K || q.len < K) return cudaSuccess;
     SeedCtx cx;
     cx.q = q;
@@ -438,6 +462,8 @@ cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t 
     cx.clamp = clamp;
     cx.b_lo = b_lo;
     cx.b_hi = b_hi;
+    cx.depth_cap = depth_cap;
+    cx.deep = d_deep;
     cx.strands = crick ? 2 : 1;
     cx.three = three ? 1 : 0;
     cx.q_impure = q_impure ? 1 : 0;

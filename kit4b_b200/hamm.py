@@ -79,6 +79,9 @@ SIGNATURES = {
     "k4b_targeted_seed_part_device": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32,
                                                      ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
     "k4b_last_seed_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64)] * 2),
+    "k4b_set_reference_sensitivity": (ctypes.c_int, [ctypes.c_int]),
+    "k4b_last_depth_cut": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32)]),
+    "k4b_seed_watch_depth": (ctypes.c_int, [ctypes.c_uint32, _vp]),
     "k4b_hamm_histogram": (ctypes.c_int, [_u16p, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint64)]),
     "k4b_histogram_device": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
     "k4b_targeted_finalize_device": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, _vp]),
@@ -336,6 +339,18 @@ def last_diag_info() -> dict:
 
 def best_finalize_device(g: Packed, d_best_ptr: int, d_out_ptr: int, stream: int = 0) -> None:
     _check(load_lib().k4b_best_finalize_device(g.handle, _vp(d_best_ptr), _vp(d_out_ptr), _vp(stream)))
+
+
+def set_reference_sensitivity(sensitivity: int) -> None:
+    """-s of the reference run the results will be compared with (0 default, 1 more, 2 ultra, 3 less)."""
+    _check(load_lib().k4b_set_reference_sensitivity(sensitivity))
+
+
+def last_depth_cut() -> dict:
+    """Probe K-mers of the last seed-engine targeted() call where the reference's depth cut may fire."""
+    n, cap = ctypes.c_uint64(0), ctypes.c_uint32(0)
+    _check(load_lib().k4b_last_depth_cut(ctypes.byref(n), ctypes.byref(cap)))
+    return {"probe_kmers": int(n.value), "max_copies": int(cap.value)}
 
 
 def histogram(minima, K: int) -> np.ndarray:

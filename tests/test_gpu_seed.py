@@ -254,3 +254,48 @@ def test_seed_engine_bucket_parts_combine_to_the_full_result(oracle, monkeypatch
     finally:
         t.free()
         q.free()
+
+
+def test_exact_where_the_reference_depth_cut_fires(oracle, tmp_path):
+    """Repeat-rich assembly (tests/golden/depth_case.py): the seed engine reports the true minimum where the
+    reference at its default sensitivity truncates its search and reports "not found"; the depth signal
+    (k4b_last_depth_cut, logged by the CLI) counts exactly that K-mer for -s0 / -s3 and none for -s1 / -s2."""
+    import subprocess
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import bench
+    import depth_case
+    from kit4b_b200 import hostlib
+    asm, probes, upos = depth_case.build()
+    target = np.ascontiguousarray(np.concatenate([np.concatenate([c, [7]]) for _, c in asm]).astype(np.uint8))
+    concat, chroms, _ = oracle.concat_entries(probes)
+    K, R = depth_case.K, depth_case.R
+    want = oracle.targeted_brute(target, concat, K, R, True)
+    gold = {s: open(os.path.join(GOLDEN, "depth.K32r3c.s%d.csv" % s), "rb").read() for s in range(4)}
+    caps = {0: 40000, 1: 80000, 2: 200000, 3: 20000}  # 4 x MaxCoreDepth (hammings.cpp:2366-2386, SfxArray.cpp:4303)
+    for join in ("0", "1"):
+        os.environ["K4B_SEED_JOIN"] = join
+        try:
+            for s in range(4):
+                hamm.set_reference_sensitivity(s)
+                got = k4b.targeted(target, concat, K, R, True)
+                assert np.array_equal(got, want) and got[upos] == 3
+                cut = hamm.last_depth_cut()
+                assert cut["max_copies"] == caps[s]
+                assert cut["probe_kmers"] == (1 if s in (0, 3) else 0), (join, s, cut)
+                rep = oracle.restricted_report(chroms, K, R, oracle.restricted_per_loci(chroms, got), 0)
+                assert (rep == gold[s]) == (s in (1, 2))  # differs from the reference exactly where its cut fires
+        finally:
+            os.environ.pop("K4B_SEED_JOIN", None)
+            hamm.set_reference_sensitivity(0)
+    # the CLI: FASTA in, the -s1 golden out, and the log names the K-mer for -s0
+    fa, pfa = str(tmp_path / "asm.fa"), str(tmp_path / "probes.fa")
+    bench.write_fasta(fa, asm)
+    bench.write_fasta(pfa, probes)
+    for s, expect in ((0, "1 probe K-mers answered below the not-found value"), (1, "depth cut (-s1) cannot fire")):
+        out = str(tmp_path / "o.csv")
+        p = subprocess.run([hostlib.cli_path(), "hammings", "-m0", "-K32", "-r3", "-c", "-s%d" % s, "-i", fa, "-I", pfa, "-o", out],
+                           capture_output=True, text=True)
+        assert p.returncode == 0, p.stdout[-1500:]
+        assert open(out, "rb").read() == gold[1]
+        assert expect in p.stdout, p.stdout[-1500:]

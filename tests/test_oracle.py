@@ -137,3 +137,24 @@ def test_merged_node_slices_equal_the_single_node_run(tmp_path):
     merged = open(into).read().split("\n")[1:]
     full = open(os.path.join(GOLDEN, "adversarial.K12c.csv")).read().strip("\n").split("\n")[1:]
     assert merged == full
+
+
+def test_reference_depth_cut_case(oracle):
+    """tests/golden/depth_case.py: at the default sensitivity (and at -s3) the reference gives a core with
+    42000 copies up and reports "not found" (4) for a K-mer whose true minimum is 3; at -s1 / -s2 it finds
+    it.  The oracle is exact: it reproduces the -s1 / -s2 files and differs from -s0 / -s3 in that one K-mer."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import depth_case
+    asm, probes, upos = depth_case.build()
+    target = np.concatenate([np.concatenate([c, [7]]) for _, c in asm]).astype(np.uint8)
+    concat, chroms, _ = oracle.concat_entries(probes)
+    h = oracle.targeted_brute(target, concat, depth_case.K, depth_case.R, True)
+    assert h[upos] == 3
+    rep = oracle.restricted_report(chroms, depth_case.K, depth_case.R, oracle.restricted_per_loci(chroms, h), 0)
+    gold = {s: open(os.path.join(GOLDEN, "depth.K32r3c.s%d.csv" % s), "rb").read() for s in range(4)}
+    assert rep == gold[1] == gold[2]
+    assert gold[0] == gold[3] != rep
+    h4 = h.copy()
+    h4[upos] = 4  # what the truncated search reports
+    assert oracle.restricted_report(chroms, depth_case.K, depth_case.R, oracle.restricted_per_loci(chroms, h4), 0) == gold[0]
