@@ -778,7 +778,7 @@ extern "C" int k4b_diag_slabs_device(k4b_packed *g, int both_strands, uint32_t p
     uint32_t *d_bm = bm_buf.as<uint32_t>();
     CU(cudaMemsetAsync(d_bm + n_blocks, 0, 2 * kMaxSlabs * 4, st));
     const char *rs = getenv("K4B_DIAG_ROWS");
-    const uint32_t rows_per_seg = rs ? (uint32_t)atoi(rs) : 8192u;
+    const uint32_t rows_per_seg = rs ? (uint32_t)atoi(rs) : 8193u;  // 1 warm-up row + 256 whole 32-row blocks: no tail
     DiagParams dp;
     dp.a = g->view();
     dp.va = g->view();
@@ -909,7 +909,7 @@ extern "C" int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets,
     dp.update_cols = 0;
     dp.wild = three ? 1 : 0;
     dp.t_fixed = std::min(clamp, K + 1);
-    dp.rows_per_seg = rs ? (uint32_t)atoi(rs) : 8192u;
+    dp.rows_per_seg = rs ? (uint32_t)atoi(rs) : 8193u;
     dp.n_seg = (uint32_t)(((uint64_t)dp.Mrow + 1 + dp.rows_per_seg - 1) / dp.rows_per_seg);
     dp.best = d_best;
     dp.blockmax = nullptr;

@@ -471,6 +471,223 @@ __global__ void __launch_bounds__(kDiagWarps * 32) diag_min_kernel(const DiagPar
     }
 }
 
+// ---- two diagonal words per thread ---------------------------------------------------------------
+// Same algorithm as the window-table path of diag_min_kernel (two planes, pure ACGT), but a thread owns
+// 64 consecutive diagonals = two counter words, a warp 2048 diagonals and a CTA (4 warps, 128 threads)
+// the same 8192-diagonal group.  The two words share what is per thread rather than per word: the
+// column windows overlap (three aligned words serve both: (a,b) and (b,c)), so the block prologue
+// builds 3 instead of 4 mismatch words per row base and side, ONE LDS.128 per row step and side fetches
+// the windows of both words, the per-row address arithmetic on the uniform datapath is done once, and
+// two independent ripple chains are in flight per thread.  ALU work per word is unchanged
+// (4 SHF + 2*NP+8 LOP3 + 1 ISETP per row pair).
+template <int NP>
+__device__ __forceinline__ void pair_core_fn(uint32_t (&c)[NP], uint32_t &pprev, uint32_t u0, uint32_t u1, uint32_t v0,
+                                             uint32_t v1, uint32_t pn) {
+    const uint32_t b0 = lop3<0x0c>(u0, v0, 0u);       // u - v: borrow out of bit 0 = ~u0 & v0
+    const uint32_t d1 = lop3<0x96>(u1, v1, b0);       // bit 1 of u - v
+    const uint32_t sg = lop3<0x8e>(u1, v1, b0);       // borrow out of bit 1 = sign = maj(~u1, v1, b0)
+    uint32_t old = c[0];
+    c[0] = lop3<0x96>(old, u0, v0);
+    uint32_t carry = lop3<0x60>(old, u0, v0);         // old & (u0 ^ v0)
+    old = c[1];
+    c[1] = lop3<0x96>(old, d1, carry);
+    carry = lop3<0xe8>(old, d1, carry);               // majority
+#pragma unroll
+    for (int b = 2; b < NP; ++b) {
+        old = c[b];
+        c[b] = lop3<0x96>(old, sg, carry);
+        if (b + 1 < NP) carry = lop3<0xe8>(old, sg, carry);
+    }
+    pprev = pn;
+}
+template <int NP>
+__device__ __forceinline__ void pair_step_fn(uint32_t (&c)[NP], uint32_t &pprev, uint32_t e1, uint32_t l1, uint32_t e2,
+                                             uint32_t l2, uint32_t &q2) {
+    const uint32_t pn = lop3<0x30>(e2, l2, 0u);       // e2 & ~l2
+    q2 = lop3<0x30>(l2, e2, 0u);                      // l2 & ~e2
+    pair_core_fn<NP>(c, pprev, lop3<0x3c>(pprev, e1, 0u), lop3<0xc0>(pprev, e1, 0u), lop3<0x3c>(l1, q2, 0u),
+                     lop3<0xc0>(l1, q2, 0u), pn);
+}
+
+constexpr int kDw = 2;                       // diagonal words per thread
+constexpr int kDwWarps = kDiagWarps / kDw;   // 4 warps of 2048 diagonals
+template <int NP>
+__global__ void __launch_bounds__(kDwWarps * 32) diag_min2_kernel(const DiagParams prm) {
+    if (prm.sel) {  // device-side choice between the narrow- and the full-counter instance
+        const uint32_t tg = __ldg(prm.tmax_ptr);
+        const bool narrow = tg <= prm.sel_limit && __ldg(prm.low_ptr) <= prm.low_max;
+        if ((prm.sel == 1) != narrow) return;
+    }
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t grp_local = blockIdx.x / prm.n_seg, seg = blockIdx.x - grp_local * prm.n_seg;
+    const uint32_t l = prm.l_first + grp_local;
+    const long long q = (long long)(l / prm.q_span) * prm.q_period + prm.q_lo + l % prm.q_span;
+    const long long grp = (long long)prm.part + q * prm.nparts;
+    const long long S0cta = prm.s_first + grp * kGroupDiags;
+    const long long S1cta = S0cta + kGroupDiags - 1;
+    const long long Mrow = prm.Mrow, Mcol = prm.Mcol;
+    long long row_lo = S1cta < 0 ? -S1cta : 0;
+    long long row_hi = Mcol - S0cta;
+    if (prm.mode == kDiagCrick) row_hi >>= 1;  // first half of every mirror-symmetric diagonal
+    if (row_hi > Mrow) row_hi = Mrow;
+    const long long r_start = row_lo + (long long)seg * prm.rows_per_seg;
+    if (r_start > row_hi) return;
+    long long r_end = r_start + prm.rows_per_seg;
+    if (r_end > row_hi + 1) r_end = row_hi + 1;
+    constexpr int kBand = kSuperBand * kDw;  // diagonals per warp
+    const long long S0w = S0cta + (long long)warp * kBand;
+    const long long s0 = S0w + lane * (32 * kDw);
+    const uint32_t K = prm.K;
+
+    // ---- threshold: upper bound of every minimum this warp can still lower ----
+    uint32_t tmax = prm.t_fixed;
+    if (prm.mode != kDiagRect) {
+        auto scan = [&](long long lo, long long hi, long long top) {
+            if (lo < 0) lo = 0;
+            if (hi > top) hi = top;
+            if (lo > hi) return;
+            for (long long bk = (lo >> prm.bm_shift) + lane; bk <= (hi >> prm.bm_shift); bk += 32)
+                tmax = max(tmax, __ldg(prm.blockmax + bk));
+        };
+        scan(r_start, r_end - 1, Mrow);
+        const long long c_lo = r_start + S0w, c_hi = r_end - 1 + S0w + kBand - 1;
+        if (!prm.col_flip) scan(c_lo, c_hi, Mcol);
+        else scan(Mcol - c_hi, Mcol - c_lo, Mcol);
+        tmax = __reduce_max_sync(0xffffffffu, tmax);
+    }
+    if (tmax == 0) return;
+    const uint32_t t_floor = (K + 1 > (1u << (NP - 1))) ? K + 1 - (1u << (NP - 1)) : 0u;
+    const uint32_t T = tmax > t_floor ? tmax : t_floor;
+    const uint32_t bias = (1u << (NP - 1)) - T;
+
+    uint32_t c[kDw][NP];
+#pragma unroll
+    for (int w = 0; w < kDw; ++w)
+#pragma unroll
+        for (int b = 0; b < NP; ++b) c[w][b] = ((bias >> b) & 1u) ? 0xffffffffu : 0u;
+
+    FlushCtx fc;
+    fc.valid_row = prm.va.valid();
+    fc.valid_col = prm.vb.valid();
+    fc.best = prm.best;
+    fc.Mrow = Mrow;
+    fc.Mcol = Mcol;
+    fc.row_flip = prm.row_flip;
+    fc.col_flip = prm.col_flip;
+    fc.update_cols = prm.update_cols;
+    auto flush = [&](int w, uint32_t flags, long long row, uint32_t adj0, uint32_t adj1, int rows) {
+        Counters<NP> cs;
+#pragma unroll
+        for (int b = 0; b < NP; ++b) cs.c[b] = c[w][b];
+        diag_flush<NP>(cs, flags, bias, row, s0 + 32 * w, adj0, adj1, rows, fc);
+    };
+
+    // ---- warm-up: the first K bases of the window enter, nothing leaves (word by word) ----
+    {
+        long long e = r_start;
+        uint32_t remaining = K;
+        while (remaining) {
+            const uint32_t n = remaining < 32 ? remaining : 32;
+#pragma unroll
+            for (int w = 0; w < kDw; ++w) {
+                SideWords<2> we;
+                load_side<2>(prm.a, prm.b, e, s0 + 32 * w, we);
+#pragma unroll 1
+                for (uint32_t t = 0; t < n; ++t) {
+                    uint32_t act = mism_word<2, false>(we, t);
+#pragma unroll
+                    for (int b = 0; b < NP; ++b) {  // ripple increment
+                        const uint32_t old = c[w][b];
+                        c[w][b] = old ^ act;
+                        act &= old;
+                    }
+                }
+            }
+            e += n;
+            remaining -= n;
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < kDw; ++w) {
+        const uint32_t f = ~c[w][NP - 1];
+        if (f) flush(w, f, r_start, 0u, 0u, 1);
+    }
+
+    // ---- main: row pairs, the counters of a word hold min(d(r), d(r+1)) (see diag_min_kernel) ----
+    uint32_t pprev[kDw] = {0u, 0u};
+    __shared__ uint4 mtab2[2][4][kDwWarps * 32];  // per thread and side: {Ma, Mb, Mc, -} for the four row bases
+    constexpr uint32_t kBaseStride = kDwWarps * 32 * sizeof(uint4);  // 2048 B: bits 11, 12 select the base
+    constexpr uint32_t kSideStride = 4 * kBaseStride;
+    static_assert(kBaseStride == 2048, "offset extraction below assumes a 2 KB base stride");
+    long long row = r_start + 1;
+    while (row < r_end) {
+        const long long left = r_end - row;
+        if (left >= 32) {
+            uint32_t ce_lo, ce_hi, cl_lo, cl_hi;  // 2-bit base codes of the 32 enter / leave rows (uniform)
+            auto build = [&](long long idx, int side, uint32_t &c_lo, uint32_t &c_hi) {
+                const uint32_t *cw = prm.a.code2() + (idx >> 4);
+                const uint32_t csh = (uint32_t)(idx & 15) * 2u;
+                const uint32_t k0 = __ldg(cw), k1 = __ldg(cw + 1), k2 = __ldg(cw + 2);
+                c_lo = __reduce_or_sync(0xffffffffu, __funnelshift_r(k0, k1, csh));
+                c_hi = __reduce_or_sync(0xffffffffu, __funnelshift_r(k1, k2, csh));
+                const long long wb = idx + s0;
+                const long long wj = wb >> 5;  // floor: may be slightly negative (front pad)
+                const uint32_t ws = (uint32_t)(wb & 31);
+                const uint32_t *b0 = prm.b.plane(0) + wj, *b1 = prm.b.plane(1) + wj;
+                const uint32_t p0 = __ldg(b0), p1 = __ldg(b0 + 1), p2 = __ldg(b0 + 2), p3 = __ldg(b0 + 3);
+                const uint32_t q0 = __ldg(b1), q1 = __ldg(b1 + 1), q2w = __ldg(b1 + 2), q3 = __ldg(b1 + 3);
+                const uint32_t xa = __funnelshift_r(p0, p1, ws), xb = __funnelshift_r(p1, p2, ws), xc = __funnelshift_r(p2, p3, ws);
+                const uint32_t ya = __funnelshift_r(q0, q1, ws), yb = __funnelshift_r(q1, q2w, ws), yc = __funnelshift_r(q2w, q3, ws);
+                // mismatch windows (x ^ b0) | (y ^ b1) for the four row bases, one LOP3 per word
+                mtab2[side][0][threadIdx.x] = make_uint4(lop3<0xfc>(xa, ya, 0u), lop3<0xfc>(xb, yb, 0u), lop3<0xfc>(xc, yc, 0u), 0u);
+                mtab2[side][1][threadIdx.x] = make_uint4(lop3<0xcf>(xa, ya, 0u), lop3<0xcf>(xb, yb, 0u), lop3<0xcf>(xc, yc, 0u), 0u);
+                mtab2[side][2][threadIdx.x] = make_uint4(lop3<0xf3>(xa, ya, 0u), lop3<0xf3>(xb, yb, 0u), lop3<0xf3>(xc, yc, 0u), 0u);
+                mtab2[side][3][threadIdx.x] = make_uint4(lop3<0x3f>(xa, ya, 0u), lop3<0x3f>(xb, yb, 0u), lop3<0x3f>(xc, yc, 0u), 0u);
+            };
+            build(row + K - 1, 0, ce_lo, ce_hi);
+            build(row - 1, 1, cl_lo, cl_hi);
+            const char *slot = reinterpret_cast<const char *>(&mtab2[0][0][threadIdx.x]);
+            auto off = [&](uint32_t c_lo, uint32_t c_hi, uint32_t t) -> uint32_t {
+                const uint32_t wv = t < 16 ? c_lo : c_hi, b = (t & 15u) * 2u;  // the code sits at bits b, b+1 of wv
+                return (b <= 11 ? (wv << (11 - b)) : (wv >> (b - 11))) & 0x1800u;
+            };
+#pragma unroll
+            for (uint32_t t = 0; t < 32; t += 2) {
+                const uint4 E1 = *reinterpret_cast<const uint4 *>(slot + off(ce_lo, ce_hi, t));
+                const uint4 L1 = *reinterpret_cast<const uint4 *>(slot + kSideStride + off(cl_lo, cl_hi, t));
+                const uint4 E2 = *reinterpret_cast<const uint4 *>(slot + off(ce_lo, ce_hi, t + 1));
+                const uint4 L2 = *reinterpret_cast<const uint4 *>(slot + kSideStride + off(cl_lo, cl_hi, t + 1));
+                uint32_t q2a, q2b;
+                pair_step_fn<NP>(c[0], pprev[0], __funnelshift_r(E1.x, E1.y, t), __funnelshift_r(L1.x, L1.y, t),
+                                 __funnelshift_r(E2.x, E2.y, t + 1), __funnelshift_r(L2.x, L2.y, t + 1), q2a);
+                pair_step_fn<NP>(c[1], pprev[1], __funnelshift_r(E1.y, E1.z, t), __funnelshift_r(L1.y, L1.z, t),
+                                 __funnelshift_r(E2.y, E2.z, t + 1), __funnelshift_r(L2.y, L2.z, t + 1), q2b);
+                const uint32_t fa = ~c[0][NP - 1], fb = ~c[1][NP - 1];
+                if (__builtin_expect(fa != 0, 0)) flush(0, fa, row + t, q2a, pprev[0], 2);
+                if (__builtin_expect(fb != 0, 0)) flush(1, fb, row + t, q2b, pprev[1], 2);
+            }
+            row += 32;
+            continue;
+        }
+#pragma unroll
+        for (int w = 0; w < kDw; ++w) {  // fewer than 32 rows left: word by word on the plain path
+            SideWords<2> we, wl;
+            load_side<2>(prm.a, prm.b, row + K - 1, s0 + 32 * w, we);
+            load_side<2>(prm.a, prm.b, row - 1, s0 + 32 * w, wl);
+#pragma unroll 1
+            for (uint32_t t = 0; t < (uint32_t)left; t += 2) {
+                const bool two = t + 1 < (uint32_t)left;
+                uint32_t q2;
+                pair_step_fn<NP>(c[w], pprev[w], mism_word<2, false>(we, t), mism_word<2, false>(wl, t),
+                                 two ? mism_word<2, false>(we, t + 1) : 0u, two ? mism_word<2, false>(wl, t + 1) : 0u, q2);
+                const uint32_t f = ~c[w][NP - 1];
+                if (f) flush(w, f, row + t, q2, pprev[w], two ? 2 : 1);
+            }
+        }
+        row += left;
+    }
+}
+
 cudaError_t launch_blockmax(const uint32_t *d_best, ImageView a, uint32_t n_pos, uint32_t shift,
                             uint32_t *d_blockmax, uint32_t n_blocks, uint32_t *d_tmax, uint32_t low_floor,
                             uint32_t *d_n_low, cudaStream_t st) {
@@ -485,6 +702,26 @@ int diag_planes_for_k(uint32_t K) {
     int b = 0;
     while ((1u << b) < K + 1) ++b;  // 2^b >= K+1 >= any threshold T
     return b + 1;
+}
+
+static cudaError_t launch_diag_dw(const DiagParams &p, int np, dim3 grid, cudaStream_t st) {
+    switch (np) {
+#define K4B_DIAG2_CASE(N) \
+    case N: diag_min2_kernel<N><<<grid, kDwWarps * 32, 0, st>>>(p); break
+        K4B_DIAG2_CASE(5);
+        K4B_DIAG2_CASE(6);
+        K4B_DIAG2_CASE(7);
+        K4B_DIAG2_CASE(8);
+        K4B_DIAG2_CASE(9);
+        K4B_DIAG2_CASE(10);
+        K4B_DIAG2_CASE(11);
+        K4B_DIAG2_CASE(12);
+        K4B_DIAG2_CASE(13);
+        K4B_DIAG2_CASE(14);
+#undef K4B_DIAG2_CASE
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
 }
 
 template <int P, bool WILD, bool EWIN>
@@ -522,6 +759,12 @@ cudaError_t launch_diag(const DiagParams &p, bool three_planes, int np, uint32_t
         // K4B_DIAG_EWIN=0 selects the previous two-plane path (row table + IMAD broadcast XOR)
         const char *e = getenv("K4B_DIAG_EWIN");  // read per launch: tests toggle it
         const int ewin = e ? atoi(e) : 1;
+        // two diagonal words per thread (diag_min2_kernel) when its registers still allow 7-8 CTAs per SM
+        // (NP <= 6: 63-64 registers; at NP = 7, 70 registers, it measured 5 % slower) and the launch is large enough to fill the GPU with 128-thread
+        // CTAs; K4B_DIAG_DW=1|2 forces a variant (tests, profiles)
+        const char *d = getenv("K4B_DIAG_DW");
+        const bool dw2 = d ? atoi(d) == 2 : (np <= 6 && total >= 4736ull);
+        if (ewin && dw2) return launch_diag_dw(p, np, grid, st);
         return ewin ? launch_diag_p<2, false, true>(p, np, grid, st) : launch_diag_p<2, false, false>(p, np, grid, st);
     }
     return p.wild ? launch_diag_p<3, true, false>(p, np, grid, st) : launch_diag_p<3, false, false>(p, np, grid, st);

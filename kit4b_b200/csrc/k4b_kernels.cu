@@ -141,9 +141,29 @@ __global__ void __launch_bounds__(256) valid_kernel(ImageView img, uint32_t *__r
             const uint32_t g = w_abs - kFrontPadWords;
             const uint64_t base = (uint64_t)g << 5;
             if (base < img.len) {
-                // common case: no EOS anywhere in [base, base+31+K) -> all 32 starts are valid
-                uint64_t ne = next_eos(img, base, K + 31);
-                if (ne == kNoEos || ne >= base + 31 + K) {
+                // common case: no EOS anywhere in [base, base+31+K) -> all 32 starts are valid.  For K <= 225
+                // that window is at most 8 words: their loads are issued together (no dependent scan)
+                const uint32_t span = K + 31, nwin = (span + 31) / 32;
+                bool clean = false;
+                uint64_t ne = kNoEos;
+                if (nwin <= 8) {
+                    uint32_t any = 0;
+#pragma unroll
+                    for (uint32_t k = 0; k < 8; ++k) {
+                        if (k < nwin) {
+                            uint32_t e = eos_word(img, g + k);
+                            const uint32_t left = span - 32 * k;  // bits of this word inside the window
+                            if (left < 32) e &= (1u << left) - 1u;
+                            any |= e;
+                        }
+                    }
+                    clean = any == 0;
+                    if (!clean) ne = next_eos(img, base, span);
+                } else {
+                    ne = next_eos(img, base, span);
+                    clean = ne == kNoEos || ne >= base + span;
+                }
+                if (clean) {
                     v = 0xffffffffu;
                 } else {
                     for (int i = 0; i < 32; ++i) {

@@ -187,6 +187,18 @@ struct SeedItem {  // one (probe K-mer, strand, core)
     uint32_t cur;           // running minimum when the item was set up (<= clamp)
 };
 
+// which of the 16 + 16 flank bases of core number c lie inside the K-mer: the LAST nl of the 16 bases before
+// the core (bits 16-nl .. 15) and the FIRST nr of the 16 after it (bits 16 .. 16+nr-1); depends on c only
+__device__ __forceinline__ uint32_t seed_flank_mask(const SeedCtx &cx, uint32_t c) {
+    const uint32_t shift = c * cx.core_len;
+    const uint32_t nl = shift < 16 ? shift : 16u;
+    const uint32_t after = cx.K - shift - cx.core_len;
+    const uint32_t nr = after < 16 ? after : 16u;
+    const uint32_t ml = nl ? (0xffffu << (16 - nl)) & 0xffffu : 0u;
+    const uint32_t mr = nr == 16 ? 0xffffu : ((1u << nr) - 1u);
+    return ml | (mr << 16);
+}
+
 // decodes item `sub` of probe p; false = nothing to do (no K-mer, wildcard K-mer, already at 0)
 __device__ __forceinline__ bool seed_item_setup(const SeedCtx &cx, uint32_t p, uint32_t sub,
                                                 const uint32_t *__restrict__ best, SeedItem &it) {
@@ -208,19 +220,13 @@ __device__ __forceinline__ bool seed_item_setup(const SeedCtx &cx, uint32_t p, u
     it.cur = __ldg(best + p);            // running minimum so far (other cores / strands / launches)
     if (it.cur > cx.clamp) it.cur = cx.clamp;  // only distances below the "not found" value matter
     if (it.cur == 0) return false;
-    const ImageView &img = it.strand ? cx.rcq : cx.q;
     const uint32_t shift = it.c * cx.core_len;
-    // the probe's own flanks of this core, cut to what lies inside the K-mer: nl bases before the
-    // core, nr bases after it
-    const uint32_t nl = shift < 16 ? shift : 16u;
-    const uint32_t after = cx.K - shift - cx.core_len;
-    const uint32_t nr = after < 16 ? after : 16u;
+    // the probe's own flanks of this core, cut to what lies inside the K-mer (masked once here, so that
+    // a test against a pre-masked entry needs no AND)
+    it.m = seed_flank_mask(cx, it.c);
     const uint2 qs = flank_sig(probe_bits(cx, it.strand), it.pp + shift, cx.core_len);
-    it.q0 = qs.x;
-    it.q1 = qs.y;
-    const uint32_t ml = nl ? (0xffffu << (16 - nl)) & 0xffffu : 0u;  // the LAST nl of the 16 bases before the core
-    const uint32_t mr = nr == 16 ? 0xffffu : ((1u << nr) - 1u);      // the FIRST nr of the 16 bases after it
-    it.m = ml | (mr << 16);
+    it.q0 = qs.x & it.m;
+    it.q1 = qs.y & it.m;
     return true;
 }
 
@@ -282,9 +288,9 @@ __global__ void __launch_bounds__(256) seed_query_kernel(SeedCtx cx, const uint3
 
 // ---- query, bucket-major join --------------------------------------------------------------
 // With a few thousand entries per bucket and hundreds of items per bucket, streaming the bucket
-// once per item is HBM-bound (12 B per entry test).  Here the items of a probe chunk are sorted by
+// once per item is HBM-bound (16 B per entry test).  Here the items of a probe chunk are sorted by
 // bucket; a CTA takes 64 consecutive sorted items, stages the bucket of each run of equal-bucket
-// items tile by tile in shared memory and lets its 8 warps test their items against the tile:
+// items tile by tile in shared memory and lets its consumer warps test their items against the tile:
 // one global read of an entry serves up to 64 entry tests.
 constexpr int kJoinItems = 64;    // sorted items per CTA
 constexpr int kJoinTile = 1024;   // index entries staged per tile (12 KB)
@@ -366,27 +372,27 @@ __global__ void __launch_bounds__(256) seed_join_kernel(SeedCtx cx, const uint32
                 uint32_t mine = s_mine[j];
                 if (mine == 0) continue;
                 const SeedItem it = items[j];
-                // 4 entries per lane and round: independent loads and POPCs in flight; whole rounds
-                // run without bounds checks, only the last round of a tile tests e < n
-                const uint32_t n_full = n & ~127u;
+                const uint2 *sig = tile_sig + lane;
+                const uint32_t *tpos = tile_pos + lane;
+                // lower bound of the distance from the flank signature (the item's q0 / q1 are masked at set-up)
+                auto bound = [&](uint2 sg) -> uint32_t { return __popc(((sg.x ^ it.q0) | (sg.y ^ it.q1)) & it.m); };
+                // 8 entries per lane and round: independent loads and POPCs in flight, one branch per round;
+                // whole rounds run without bounds checks, only the tail of a tile tests e < n
                 uint32_t e0 = 0;
-                for (; e0 < n_full && mine; e0 += 128) {
-                    uint32_t lb[4];
+                for (; e0 + 256 <= n && mine; e0 += 256) {
+                    uint32_t lb[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) lb[u] = seed_sig_bound(it, tile_sig[e0 + u * 32 + lane]);
-                    if (min(min(lb[0], lb[1]), min(lb[2], lb[3])) < mine) {  // rare: one branch per 4 entries
+                    for (int u = 0; u < 8; ++u) lb[u] = bound(sig[e0 + u * 32]);
+                    const uint32_t lo4 = min(min(lb[0], lb[1]), min(lb[2], lb[3]));
+                    const uint32_t hi4 = min(min(lb[4], lb[5]), min(lb[6], lb[7]));
+                    if (min(lo4, hi4) < mine) {  // rare
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (lb[u] < mine) seed_verify(cx, it, tile_pos[e0 + u * 32 + lane], mine);
+                        for (int u = 0; u < 8; ++u)
+                            if (lb[u] < mine) seed_verify(cx, it, tpos[e0 + u * 32], mine);
                     }
                 }
-                if (e0 < n && mine) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t e = e0 + u * 32 + lane;
-                        if (e < n && seed_sig_bound(it, tile_sig[e]) < mine) seed_verify(cx, it, tile_pos[e], mine);
-                    }
-                }
+                for (; e0 < n && mine; e0 += 32)
+                    if (e0 + lane < n && bound(sig[e0]) < mine) seed_verify(cx, it, tpos[e0], mine);
                 mine = __reduce_min_sync(0xffffffffu, mine);
                 if (lane == 0) s_mine[j] = mine;
             }

@@ -198,12 +198,13 @@ def test_window_table_path_equals_row_table_path(monkeypatch):
     probes = np.ascontiguousarray(np.concatenate([c[1000:9000], [7], random_genome(961, [5000])]), dtype=np.uint8)
     probes[100] = (probes[100] + 1) % 4
     res = {}
-    for ewin in ("1", "0"):
+    for ewin, dw in (("1", "1"), ("1", "2"), ("0", "1")):  # K4B_DIAG_DW=2: two diagonal words per thread
         for rows in ("8192", "4096"):
             monkeypatch.setenv("K4B_DIAG_EWIN", ewin)
+            monkeypatch.setenv("K4B_DIAG_DW", dw)
             monkeypatch.setenv("K4B_DIAG_ROWS", rows)
-            res[(ewin, rows)] = (k4b.exhaustive(c, 40, True), k4b.targeted(c, probes, 32, 3, True))
-    ref = res[("0", "4096")]
+            res[(ewin, dw, rows)] = (k4b.exhaustive(c, 40, True), k4b.targeted(c, probes, 32, 3, True))
+    ref = res[("0", "1", "4096")]
     for key, (ex, tg) in res.items():
         assert np.array_equal(ex, ref[0]), key
         assert np.array_equal(tg, ref[1]), key
