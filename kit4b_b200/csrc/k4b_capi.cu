@@ -751,6 +751,32 @@ extern "C" int k4b_diag_slab_count(k4b_packed *g, int both_strands, uint32_t npa
     return K4B_OK;
 }
 
+// A second stream per device for the Crick launches of a slab: Watson and Crick kernels of one slab
+// are independent, so the CTAs of one fill the SMs that the draining tail of the other leaves idle
+// (one partial wave per slab instead of two - it matters when a rank's launches are only 10-20 waves).
+namespace {
+struct SideStream {
+    int dev = -1;
+    cudaStream_t st = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaError_t get(int device) {
+        if (dev == device && st) return cudaSuccess;
+        if (st) {
+            cudaStreamDestroy(st);
+            cudaEventDestroy(fork);
+            cudaEventDestroy(join);
+            st = nullptr;
+        }
+        cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+        dev = e == cudaSuccess ? device : -1;
+        return e;
+    }
+};
+thread_local SideStream g_side[16];  // one per device slot a thread drives
+}  // namespace
+
 // Diagonal bands: slabs [slab_begin, slab_end) of part `part` of `nparts` of the pair matrix
 // (interleaved CTA groups of 8192 diagonals), thresholds refreshed per slab.  Parts (and, with a
 // collective between calls, slab ranges) combine by element-wise minimum of d_best.
@@ -807,9 +833,14 @@ extern "C" int k4b_diag_slabs_device(k4b_packed *g, int both_strands, uint32_t p
     const uint32_t low_floor = (np_small && K + 1 > (1u << (np_small - 1))) ? K + 1 - (1u << (np_small - 1)) : 0u;
     RC(g_tp.begin(g->device, slab_begin == 0, st));
     cudaError_t e = cudaSuccess;
+    SideStream &side = g_side[g->device & 15];
+    const bool fork = crick && !getenv("K4B_DIAG_ONE_STREAM");
+    if (fork) e = side.get(g->device);
     for (uint32_t slab = slab_begin; slab < slab_end && e == cudaSuccess; ++slab) {
         uint32_t *d_tmax = d_bm + n_blocks + slab, *d_low = d_bm + n_blocks + kMaxSlabs + slab;
         e = launch_blockmax(d_best, g->view(), M + 1, bm_shift, d_bm, n_blocks, d_tmax, low_floor, d_low, st);
+        if (fork && e == cudaSuccess) e = cudaEventRecord(side.fork, st);
+        if (fork && e == cudaSuccess) e = cudaStreamWaitEvent(side.st, side.fork, 0);
         dp.tmax_ptr = d_tmax;
         dp.sel_limit = np_small ? (1u << (np_small - 1)) : 0u;
         dp.low_ptr = d_low;
@@ -828,24 +859,33 @@ extern "C" int k4b_diag_slabs_device(k4b_packed *g, int both_strands, uint32_t p
             dp.col_flip = strand;
             dp.b = strand ? g->rc_view() : g->view();
             dp.s_first = strand ? -(long long)M : 1;
-            // the 1-D grid is limited to 2^31-1 CTAs: split very large launches by groups
-            const uint32_t max_groups = std::max(1u, 0x7fffffffu / dp.n_seg);
             DiagParams q = dp;
+            // launches of fewer than ~40 waves of CTAs (small inputs, many parts): half-length row segments,
+            // i.e. twice as many CTAs of half the duration - a shorter tail for 0.6 % more warm-up rows
+            if (!rs && ng * dp.n_seg < 47360ull) {
+                q.rows_per_seg = 4097u;
+                q.n_seg = (uint32_t)(((uint64_t)M + 1 + q.rows_per_seg - 1) / q.rows_per_seg);
+            }
+            // the 1-D grid is limited to 2^31-1 CTAs: split very large launches by groups
+            const uint32_t max_groups = std::max(1u, 0x7fffffffu / q.n_seg);
+            cudaStream_t ls = (fork && strand) ? side.st : st;  // Crick launches overlap the Watson ones
             for (uint64_t done = 0; done < ng && e == cudaSuccess; done += max_groups) {
                 q.l_first = (uint32_t)done;
                 const uint32_t now = (uint32_t)std::min<uint64_t>(max_groups, ng - done);
                 if (np_small) {
                     q.sel = 1;
-                    e = launch_diag(q, three, np_small, now, st, nullptr);
+                    e = launch_diag(q, three, np_small, now, ls, nullptr);
                     ++nl;
                     q.sel = 2;
                 } else {
                     q.sel = 0;
                 }
-                if (e == cudaSuccess) e = launch_diag(q, three, np_full, now, st, nullptr);
+                if (e == cudaSuccess) e = launch_diag(q, three, np_full, now, ls, nullptr);
                 ++nl;
             }
         }
+        if (fork && e == cudaSuccess) e = cudaEventRecord(side.join, side.st);
+        if (fork && e == cudaSuccess) e = cudaStreamWaitEvent(st, side.join, 0);
     }
     if (e == cudaSuccess) e = g_tp.end(st);
     if (e == cudaSuccess && !g_h_tmax) e = cudaMallocHost(&g_h_tmax, 2 * kMaxSlabs * sizeof(uint32_t));
