@@ -334,8 +334,9 @@ def cfg4_reference(scale, target_seconds=8.0, parity=True):
         os.replace(os.path.join(d, "asm.sfx.tmp"), sfx)
         os.unlink(os.path.join(d, "asm.fa"))
     pl = (len(probes) - 1) // 2
-    # reference cost measured in round 1: 531.6 s for 2e6 probe K-mers vs 500 Mbp on 16 threads (~0.27 ms each)
-    n_half = int(max(200, min(pl - K, target_seconds * T / 16.0 / 0.27e-3 * min(1.0, 1.0 / max(scale, 1e-3)) / 2)))
+    # reference cost measured on the GPU box: ~2.4 ms per probe K-mer of this sample on 16 threads (the mutated-copy half
+    # descends the whole cascade; round 1's full job averaged 0.27 ms over all probes)
+    n_half = int(max(200, min(pl - K, target_seconds * T / 16.0 / 2.4e-3 * min(1.0, 1.0 / max(scale, 1e-3)) / 2)))
     def probe_files(tag, n):
         fa, seq = os.path.join(d, tag + ".fa"), os.path.join(d, tag + ".seq")
         write_fasta(fa, [("mutated_copy", probes[:n + K - 1]), ("unrelated", probes[pl + 1:pl + 1 + n + K - 1])])
@@ -542,13 +543,15 @@ def bands_roofline(c, workload, res, cmps_per_step, steps, L, three_planes):
     return {"bound": "int_pipe(alu: lop3/shf)", "achieved": achieved, "peak": c.lop3_peak, "unit": "Gop/s",
             "frac": achieved / c.lop3_peak, "traffic": prof.get("dram_bytes_per_launch"),
             "alu_pipe_busy_ncu": prof.get("alu_pipe_busy"), "profile": prof.get("source"),
-            "kernel": "diag_min_kernel<NP=%d|%d,P=%d>: %d of %d slabs ran the narrow-counter instance (all band launches "
-                      "of one step on this rank)" % (info["np_small"], info["np_full"], 3 if three_planes else 2,
-                                                     info["narrow_slabs"], info["slabs"]),
+            "kernel": "%s, NP=%d|%d, %d planes: %d of %d slabs ran the narrow-counter instance (all band launches of one step "
+                      "on this rank)" % ("diag_min2_kernel (two diagonal words per thread) where NP <= 6 and the launch fills the "
+                                         "GPU, else diag_min_kernel (window-table instance)" if not three_planes else
+                                         "diag_min_kernel (row-table instance)", info["np_small"], info["np_full"],
+                                         3 if three_planes else 2, info["narrow_slabs"], info["slabs"]),
             "kernel_ms": k_ms, "kernel_share_of_step": k_ms * steps / res["ms"] if res["ms"] > 0 else None,
             "ops_model": "%.2f ALU-pipe thread-ops per 32-cell row step = the inner loop of the shipped kernel (per row PAIR: "
                          "4 SHF + 2*NP+8 LOP3 + 1 ISETP); cells = valid pairs, each serving 2 comparisons.  NOT counted as "
-                         "useful: the prologue of every 32-row block, the K warm-up rows of each 8192-row segment, cells "
+                         "useful: the prologue of every 32-row block, the K warm-up rows of each 8193-row segment, cells "
                          "outside the triangle in boundary CTAs, the flagged-cell slow path, the bootstrap.  This is the "
                          "builder's instruction model of its own algorithm, not SURVEY 8d's POPC word-compare contract (by "
                          "which this engine sits far above 1: it does O(1) work per pair instead of K/32 POPCs; see the "
@@ -968,7 +971,7 @@ def run_ours(args):
             t0 = time.perf_counter()
             try:
                 if name == "cfg4":
-                    ent = targeted_leg(c, args.scale, 5, 3, 2, not args.no_cpu)
+                    ent = targeted_leg(c, args.scale, 5, 3, 3, not args.no_cpu)
                 elif name == "popc":
                     ent = popc_leg(c, args.workload, 5, 3, args.batch)
                 elif name == "cfg3":

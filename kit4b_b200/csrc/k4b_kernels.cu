@@ -113,8 +113,10 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ c
 // counter).  Also counts the valid K-mers.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t eos_word(const ImageView &img, uint32_t w) {
-    if (w >= img.nwl) return 0xffffffffu;
-    return img.plane(0)[w] & img.plane(1)[w] & img.plane(2)[w];
+    // branch-free (the loads of several words can be in flight together): words past the end are
+    // clamped onto the last word of the back pad, which is EOS-filled like everything after the sequence
+    w = w < img.nwl ? w : img.nwl - 1;
+    return __ldg(img.plane(0) + w) & __ldg(img.plane(1) + w) & __ldg(img.plane(2) + w);
 }
 // first EOS position >= pos found while scanning the words that overlap [pos, pos+K); kNoEos
 // when those words hold none (a hit may lie at or beyond pos+K: callers compare)
@@ -176,10 +178,15 @@ __global__ void __launch_bounds__(256) valid_kernel(ImageView img, uint32_t *__r
         }
         valid_arr[w_abs] = v;
     }
-    uint32_t c = __popc(v);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (unsigned long long)c);
+    // number of valid K-mers: one global atomic per CTA (one per warp made 0.5 M atomics on a single address
+    // the bottleneck of this kernel at 500 Mbp)
+    __shared__ uint32_t s_count;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const uint32_t c = __reduce_add_sync(0xffffffffu, __popc(v));
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_count, c);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_count) atomicAdd(count, (unsigned long long)s_count);
 }
 
 __global__ void fill_u32_kernel(uint32_t *d, uint32_t n, uint32_t v) {
