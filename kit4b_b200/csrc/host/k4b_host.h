@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace k4bhost {
@@ -21,6 +22,7 @@ enum : int {
     kErrCreateFile = -89,
     kErrFileVer = -86,
     kErrFileAccess = -85,
+    kErrFeature = -53,
     kErrParse = -46,
 };
 
@@ -114,7 +116,7 @@ int merge_hamming_csv(const std::string &from, const std::string &into, std::str
 int csv_to_bham(const std::string &csv, const std::string &bham, std::string &err);
 int bham_to_csv(const std::string &bham, const std::string &csv, std::string &err);
 
-// ---- HammingDist (HammingDist/HammingDist.cpp:371-705), region-less mode -----------------------------
+// ---- HammingDist (HammingDist/HammingDist.cpp:371-705), region-less mode; region mode below ------------
 // Distribution file of the reference's downstream tool: header `,"All","Proportion All","Cumulative All"`,
 // then one row `\n<d>,<count>,<proportion %f>,<cumulative %f>` for d = 0 .. max-1 (the reference's loops
 // stop BEFORE the largest value seen, :631-641; kept, so the proportions are over the rows shown).
@@ -126,6 +128,63 @@ int write_hamming_distribution(const std::string &path, const std::vector<uint64
 // Leading header lines and the `G,b,B` descriptor row of -m1 files are skipped.
 int hamming_counts_from_csv(const std::vector<std::string> &files, std::vector<uint64_t> &counts, uint64_t &rows,
                             std::string &err);
+
+// ---- HammingDist region mode: gene / feature annotation (libkit4b/BEDfile.cpp) -------------------------
+// feature bits, BEDfile.h:28-33; the region of a locus is the first set bit in this order, else intergenic
+enum : int {
+    kFeatCDS = 0x01,
+    kFeat5UTR = 0x02,
+    kFeat3UTR = 0x04,
+    kFeatIntrons = 0x08,
+    kFeatUpstream = 0x10,
+    kFeatDnstream = 0x20,
+    kFeatRegionBits = 0x3f,  // cRegionFeatBits (BEDfile.h:48)
+};
+struct Feature {
+    int32_t start = 0, end = 0;  // chromosome offsets, end inclusive
+    int32_t score = 0;
+    char strand = '+';           // '+', '-' or '?'
+    // gene + exons files only: coding range and exon start/end pairs, all relative to `start`
+    int32_t thick_start = 0, thick_end = 0;
+    std::vector<int32_t> exons;
+};
+struct FeatureChrom {
+    std::string name;
+    std::vector<Feature> feats;  // sorted by start, end
+    int32_t max_len = 0;
+};
+struct FeatureSet {
+    bool gene_exons = false;  // features carry exon detail (eBTGeneExons)
+    // false: the file was neither BED nor biobed and short enough (< 100 lines) that the reference's GFF3
+    // fallback reports "no genes" as success (BEDfile.cpp:421-432 returns its zero count as the result
+    // code): the tool then runs with NO chromosome known, which ends every input file at its first row
+    bool available = true;
+    std::vector<FeatureChrom> chroms;
+    std::unordered_map<std::string, int> chrom_index;  // lower-cased name -> index into chroms
+    // index of the chromosome, -1 if absent; case-insensitive, chloroplast/ChrC and mitochondria/ChrM are
+    // aliases of each other (BEDfile.cpp:3070-3095)
+    int chrom_id(const std::string &name) const;
+    // OR of the overlap bits of every feature touching [start-updn, end+updn] (BEDfile.cpp:4279-4311)
+    int feature_bits(int chrom, int start, int end, int want_bits, int updn) const;
+};
+// raw BED text (BED3..BED12, tabs or commas) or the binary biobed container written by `genbiobed`
+int read_features(const std::string &path, FeatureSet &fs, std::string &err);
+
+// Region mode of HammingDist (HammingDist.cpp:371-496, :606-700): every row `"chrom",loci,hamming` is put
+// into the region of loci+ofs_loci (regulatory length reg_len) and the distances are histogrammed per
+// region.  Bit-exact with the reference, its reading rules included: no row is special-cased (the
+// `G,b,B` descriptor row of -m1 output names no chromosome of the feature file, and the FIRST row whose
+// chromosome is unknown ends the reading of that file, :449-453); distances above 200 do not fit its
+// table (:278) and are refused here.
+constexpr int kNumRegions = 7, kMaxRegionHamming = 200;
+struct RegionHistogram {
+    uint32_t counts[kNumRegions][kMaxRegionHamming + 1] = {};
+    int max_hamming = -1;      // largest distance in any file that was read to its end
+    long total_processed = 0;  // rows of those files
+};
+int region_counts_from_csv(const std::vector<std::string> &files, const FeatureSet &fs, int ofs_loci, int reg_len,
+                           RegionHistogram &h, std::string &log, std::string &err);
+int write_region_distribution(const std::string &path, const RegionHistogram &h, std::string &err);
 
 // ---- CLI ----------------------------------------------------------------------------------------
 struct Options {

@@ -139,6 +139,28 @@ int k4bh_hamming_dist(int n, const char **csvs, const char *out) {
     return rc ? set_err(rc, err) : 0;
 }
 
+// HammingDist region mode (-I): per-region distribution file; feats = BED text or biobed container.
+// The region of one locus is available on its own for tests: -1 = chromosome not in the feature file.
+int k4bh_hamming_dist_regions(int n, const char **csvs, const char *feats, int reg_len, int ofs_loci, const char *out) {
+    std::vector<std::string> files(csvs, csvs + n);
+    std::string err, log;
+    FeatureSet fs;
+    int rc = read_features(feats, fs, err);
+    RegionHistogram hist;
+    if (!rc) rc = region_counts_from_csv(files, fs, ofs_loci, reg_len, hist, log, err);
+    if (!rc) rc = write_region_distribution(out, hist, err);
+    return rc ? set_err(rc, err) : 0;
+}
+int k4bh_feature_bits(const char *feats, const char *chrom, int n, const int *loci, int reg_len, int *bits) {
+    std::string err;
+    FeatureSet fs;
+    const int rc = read_features(feats, fs, err);
+    if (rc) return set_err(rc, err);
+    const int id = fs.chrom_id(chrom);
+    for (int i = 0; i < n; ++i) bits[i] = id < 0 ? -1 : fs.feature_bits(id, loci[i], loci[i], kFeatRegionBits, reg_len);
+    return 0;
+}
+
 // parses a command line (argv[0] = program); fills ints[0..15] and strs (4 x 512 chars:
 // in, inseq, out, prefix).  Returns 0, or -1 with k4bh_last_error() set.
 int k4bh_parse_cli(int argc, char **argv, int *ints, char *strs) {

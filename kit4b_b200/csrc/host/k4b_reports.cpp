@@ -674,4 +674,112 @@ int hamming_counts_from_csv(const std::vector<std::string> &files, std::vector<u
     return kOk;
 }
 
+// ---- HammingDist, region mode (HammingDist/HammingDist.cpp:371-496, :606-700) --------------------------
+int region_counts_from_csv(const std::vector<std::string> &files, const FeatureSet &fs, int ofs_loci, int reg_len,
+                           RegionHistogram &h, std::string &log, std::string &err) {
+    std::vector<std::string> fields;
+    std::vector<bool> quoted;
+    for (const std::string &path : files) {
+        std::ifstream in(path);
+        if (!in) {
+            err = "Unable to open file: " + path;
+            return kErrOpnFile;
+        }
+        std::string line, prev_chrom;
+        long processed = 0, lineno = 0;
+        int max_h = -1, chrom = -1;
+        bool complete = true;  // read to its end: only then do its rows and its maximum count (:490-495)
+        while (std::getline(in, line)) {
+            ++lineno;
+            size_t b = 0;
+            while (b < line.size() && (line[b] == ' ' || line[b] == '\t' || line[b] == '\r')) ++b;
+            if (b == line.size() || line[b] == '#') continue;  // blank and comment lines (CSVFile.cpp:655-687)
+            split_csv(line, fields, quoted);
+            if (fields.size() < 3) {
+                log += "Expected 3+ fields in '" + path + "', line " + std::to_string(lineno) + ": reading of this file stops\n";
+                complete = false;
+                break;
+            }
+            if (!processed) {  // CCSVFile::IsLikelyHeaderLine (CSVFile.cpp:757-789)
+                bool header = true;
+                int empty = 0;
+                for (size_t k = 0; k < fields.size() && header; ++k) {
+                    if (quoted[k]) continue;
+                    if (fields[k].empty()) {
+                        if (++empty > 2) header = false;
+                        continue;
+                    }
+                    if (is_number(fields[k])) header = false;
+                }
+                if (header) continue;
+            }
+            ++processed;
+            int loci = atoi(fields[1].c_str());
+            const int hamming = atoi(fields[2].c_str());
+            if (chrom < 0 || fields[0] != prev_chrom) {
+                chrom = fs.chrom_id(fields[0]);
+                if (chrom < 0) {  // the reference leaves the file at the first unknown chromosome (:449-453)
+                    log += "'" + path + "' line " + std::to_string(lineno) + ": chromosome '" + fields[0] +
+                           "' is not in the feature file; as in the reference, reading of this file stops here and its rows do not "
+                           "count towards the totals\n";
+                    complete = false;
+                    break;
+                }
+                prev_chrom = fields[0];
+            }
+            if (hamming < 0 || hamming > kMaxRegionHamming) {
+                err = "Hamming distance " + std::to_string(hamming) + " in '" + path + "', line " + std::to_string(lineno) +
+                      " does not fit the region table (0.." + std::to_string(kMaxRegionHamming) + ")";
+                return kErrParse;
+            }
+            loci += ofs_loci;
+            if (loci < 0) loci = 0;
+            int bits = fs.feature_bits(chrom, loci, loci, kFeatRegionBits, reg_len);
+            int region = 0;
+            for (; region < kNumRegions - 1; ++region, bits >>= 1)
+                if (bits & 1) break;
+            if (max_h < hamming) max_h = hamming;
+            ++h.counts[region][hamming];
+        }
+        if (complete) {
+            h.total_processed += processed;
+            if (h.max_hamming < max_h) h.max_hamming = max_h;
+        }
+    }
+    return kOk;
+}
+
+int write_region_distribution(const std::string &path, const RegionHistogram &h, std::string &err) {
+    static const char *const kNames[kNumRegions] = {"CDS", "UTR5", "UTR3", "Intron", "UP5", "DN3", "Intergenic"};  // :313-338
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) {
+        err = "Unable to create " + path + " - " + strerror(errno);
+        return kErrCreateFile;
+    }
+    if (h.max_hamming >= 0 && h.total_processed > 0) {
+        for (const char *pre : {"", "Proportion ", "Cumulative "})
+            for (int r = 0; r < kNumRegions; ++r) fprintf(f, ",\"%s%s\"", pre, kNames[r]);
+        uint32_t total[kNumRegions] = {};
+        double cumulative[kNumRegions] = {};
+        for (int d = 0; d < h.max_hamming; ++d)  // the largest distance is left out of totals and rows alike (:631, :640)
+            for (int r = 0; r < kNumRegions; ++r) total[r] += h.counts[r][d];
+        for (int d = 0; d < h.max_hamming; ++d) {
+            fprintf(f, "\n%d", d);
+            for (int r = 0; r < kNumRegions; ++r) fprintf(f, ",%d", (int)h.counts[r][d]);
+            for (int r = 0; r < kNumRegions; ++r) fprintf(f, ",%f", total[r] > 0 ? h.counts[r][d] / (double)total[r] : 0.0);
+            for (int r = 0; r < kNumRegions; ++r) {
+                cumulative[r] += total[r] > 0 ? (double)h.counts[r][d] / (double)total[r] : 0.0;
+                fprintf(f, ",%f", cumulative[r]);
+            }
+        }
+    }
+    const bool ok = fflush(f) == 0 && fsync(fileno(f)) == 0;
+    fclose(f);
+    if (!ok) {
+        err = "Error on write to file '" + path + "'";
+        return kErrFileAccess;
+    }
+    return kOk;
+}
+
 }  // namespace k4bhost

@@ -122,6 +122,23 @@ def hamming_dist(csvs: List[str], out: str):
     _check(load().k4bh_hamming_dist(len(csvs), arr, out.encode()))
 
 
+def hamming_dist_regions(csvs: List[str], feats: str, out: str, reg_len: int = 0, ofs_loci: int = 0):
+    """HammingDist, region mode (-I feats [-r reg_len] [-R ofs_loci]): per-region distributions, bit-exact
+    with the reference; feats = BED text or the biobed container of `genbiobed`."""
+    arr = (ctypes.c_char_p * len(csvs))(*[c.encode() for c in csvs])
+    _check(load().k4bh_hamming_dist_regions(len(csvs), arr, feats.encode(), reg_len, ofs_loci, out.encode()))
+
+
+def feature_bits(feats: str, chrom: str, loci: List[int], reg_len: int = 0) -> List[int]:
+    """Region feature bits (CDS 1, 5'UTR 2, 3'UTR 4, intron 8, upstream 16, downstream 32) of single loci;
+    -1 where the chromosome is not in the feature file."""
+    n = len(loci)
+    a = (ctypes.c_int * n)(*loci)
+    b = (ctypes.c_int * n)()
+    _check(load().k4bh_feature_bits(feats.encode(), chrom.encode(), n, a, reg_len, b))
+    return list(b)
+
+
 def bham_to_csv(bham: str, csv: str):
     _check(load().k4bh_bham_to_csv(bham.encode(), csv.encode()))
 

@@ -1,8 +1,8 @@
 // TEST INFRASTRUCTURE ONLY - not part of the product path.
 // Minimal dispatcher that links the UNMODIFIED reference translation units
-// (ngskit4b/hammings.cpp, genbioseq.cpp, kit4bax.cpp) compiled where they lie under
-// /root/reference, so the reference's own `hammings`, `genbioseq` and `index`
-// subprocesses can be run as the parity oracle.  The real ngskit4b/ngskit4b.cpp
+// (ngskit4b/hammings.cpp, genbioseq.cpp, kit4bax.cpp, genbiobed.cpp) compiled where they lie
+// under /root/reference, so the reference's own `hammings`, `genbioseq`, `index` and
+// `genbiobed` subprocesses can be run as the parity oracle.  The real ngskit4b/ngskit4b.cpp
 // dispatcher is not used because it would pull in all 54 subprocesses
 // (ngskit4b/ngskit4b.cpp:136-191); this file only defines the globals those TUs
 // expect (ngskit4b/ngskit4b.h:37-47) and forwards argv.
@@ -15,6 +15,7 @@
 extern int hammings(int argc, char *argv[]);
 extern int genbioseq(int argc, char *argv[]);
 extern int kingsax(int argc, char *argv[]);
+extern int genbiobed(int argc, char *argv[]);
 
 const char *cpszProgVer = "oracle";
 CStopWatch gStopWatch;
@@ -28,6 +29,7 @@ static tsSubProcess gTable[] = {
     {"hammings", "hammings", "hammings", hammings},
     {"genbioseq", "genbioseq", "genbioseq", genbioseq},
     {"index", "index", "index", kingsax},
+    {"genbiobed", "genbiobed", "genbiobed", genbiobed},
 };
 tsSubProcess *gpszSubProcess = &gTable[0];
 
@@ -41,7 +43,7 @@ extern "C" unsigned int sleep(unsigned int) { return 0; }
 int main(int argc, char *argv[]) {
     strcpy(gszProcName, "ngskit4b");
     if (argc < 2) {
-        fprintf(stderr, "usage: %s hammings|genbioseq|index <flags>\n", argv[0]);
+        fprintf(stderr, "usage: %s hammings|genbioseq|index|genbiobed <flags>\n", argv[0]);
         return 2;
     }
     for (auto &e : gTable) {

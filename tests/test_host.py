@@ -220,7 +220,7 @@ def test_hammingdist_distribution_of_exhaustive_csv(tmp_path):
     assert open(out2, "rb").read() == _expected_distribution(values + values)
     assert subprocess.run([exe, "-h"], capture_output=True).returncode == 1
     assert subprocess.run([exe, "-i", src], capture_output=True).returncode == 1           # -o is required
-    assert subprocess.run([exe, "-i", src, "-o", out2, "-I", "genes.bed"], capture_output=True).returncode == 1  # region mode
+    assert subprocess.run([exe, "-i", src, "-o", out2, "-I", str(tmp_path / "nosuch.bed")], capture_output=True).returncode == 1
     bad = str(tmp_path / "bad.csv")
     open(bad, "w").write('"chr1",5\n')
     with pytest.raises(RuntimeError):

@@ -2,7 +2,7 @@
 # round-2 experiment 16 (8 GPUs): the default bench line under torchrun, all configs + the in-process leg
 set -u
 mkdir -p gpurun_out
-( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus 8 --steps 5 --warmup 3 ) > gpurun_out/bench16_n8.json 2> gpurun_out/bench16_n8.err; echo "bench rc=$?"
+( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus 8 --steps 5 --warmup 3 --no-cpu ) > gpurun_out/bench16_n8.json 2> gpurun_out/bench16_n8.err; echo "bench rc=$?"
 tail -6 gpurun_out/bench16_n8.err
 python - <<PY
 import json
