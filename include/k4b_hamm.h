@@ -44,8 +44,9 @@ extern "C" {
 /* ---- lifetime -------------------------------------------------------------------------- */
 
 /* Creates contexts and streams on n_gpus devices (0 = all visible) and, when more than one
- * device is used, a single-process NCCL communicator for the one-off broadcast of the packed
- * target set.  Replaces the reference's pthread pool set-up (hammings.cpp:2752-2780). */
+ * device is used, a single-process NCCL communicator (ncclCommInitAll) for the broadcast of the
+ * packed sets and the all_reduce(min) of the per-device minima.  Replaces the reference's pthread
+ * pool set-up (hammings.cpp:2752-2780). */
 int k4b_gpu_init(int n_gpus, const int *device_ids /* nullable */);
 void k4b_gpu_shutdown(void);
 /* number of devices in use after k4b_gpu_init (0 before) */
@@ -159,8 +160,10 @@ float k4b_last_kernel_ms(void);
 /* Two exact engines produce the exhaustive minima: 1 = POPC all-pairs (queries in registers,
  * XOR / fold / POPC per 32 bases), 2 = diagonal bands (the reference's O(1)-per-pair sliding
  * recurrence, 32 diagonals per thread in bit-sliced counters, every cell serving both K-mers
- * of the pair).  0 = automatic (bands for full sweeps of >= 200 kb, all-pairs otherwise; sweep
- * sub-ranges, query shards and the targeted mode always use all-pairs).  Env: K4B_ENGINE=popc|diag. */
+ * of the pair).  0 = automatic: exhaustive - bands for full sweeps of >= 200 kb, all-pairs for
+ * smaller inputs, sweep sub-ranges (-b/-B, -m2) and query shards; targeted - the seed-and-verify
+ * engine (3) for pure-ACGT probe sets with cores of >= 6 bases, else bands, all-pairs for probe
+ * sub-ranges and wildcard probe K-mers.  Env: K4B_ENGINE=popc|diag|seed. */
 int k4b_set_engine(int engine);
 int k4b_get_engine(void);
 /* d_best: DEVICE uint32[len] running minima.  init fills K+1; k4b_exhaustive_diag_device lowers

@@ -10,8 +10,10 @@ depends on the engine:
                                   the host of rank 0;
   * exhaustive_distributed_bands  diagonal-band engine: the PAIR MATRIX is partitioned (every cell
                                   lowers both K-mers of its pair), every rank keeps a complete
-                                  minima array, thresholds are exchanged between slabs and the
-                                  arrays meet in one all_reduce(MIN) at the end;
+                                  minima array and the arrays meet in all_reduce(MIN) after the
+                                  query-sharded bootstrap and after every slab (asynchronous, one slab
+                                  behind: bands_slabwise), so each rank thresholds against what all
+                                  ranks have found;
   * targeted_distributed          seed-and-verify engine: the index BUCKETS are sharded (each rank
                                   builds 1/world of the index and answers all probes for it), one
                                   all_reduce(MIN) at the end.
