@@ -727,10 +727,11 @@ def targeted_leg(c, scale, steps, warmup, e2e_steps, with_cpu):
         ach = info["occurrences"] / (kms * 1e-3) / 1e9
         roofline = {"bound": "int_pipe(xu: popc)", "achieved": ach, "peak": c.popc_peak, "unit": "Gop/s", "frac": ach / c.popc_peak,
                     "traffic": prof.get("dram_bytes_per_launch"), "profile": prof.get("source"),
-                    "kernel": "seed_join_kernel (+ index build, item keys, radix sort of the items) of one step on this rank",
+                    "kernel": "seed_join_kernel, one pass per core (+ index build, item keys, radix sorts of the items) of one step on this rank",
                     "kernel_ms": kms, "kernel_share_of_step": kms * steps / ms if ms > 0 else None,
-                    "ops_model": "1 POPC per entry test (%d tests: every item against every entry of its core's bucket); "
-                                 "index build, item keys and the radix sort of the items count as overhead" % info["occurrences"],
+                    "ops_model": "1 POPC per entry test (%d tests: every item the phase schedule leaves active against every entry "
+                                 "of its core's bucket); index build, item keys and the radix sorts of the items count as "
+                                 "overhead" % info["occurrences"],
                     "peak_source": "measured live: register-resident POPC microbenchmark (k4b_microbench_intpipe)"}
     else:
         roofline = {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

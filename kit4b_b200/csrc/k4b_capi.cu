@@ -1095,19 +1095,20 @@ static int seed_run(k4b_packed *probes, k4b_packed *targets, int both_strands, u
         self.n_ent = (uint32_t)g_zf.starts.size();
     }
     RC(g_tp.begin(probes->device, true, st));
+    int nq = 0;
     cudaError_t e = launch_seed_index(targets->view(), core_len, b_lo, b_hi, d_cnt, d_off, d_cur, d_ent, tmp_buf.p,
                                       temp_bytes, st);
     if (e == cudaSuccess)
         e = launch_seed_query(probes->view(), crick ? probes->rc_view() : probes->view(), targets->view(), K, core_len,
                               d_off, d_ent, q_begin, q_end, b_lo, b_hi, clamp, crick, targets->has_non_acgt != 0,
-                              probes->has_non_acgt != 0, self, g_depth.cap, g_depth.d_deep, d_best, d_occ, st);
+                              probes->has_non_acgt != 0, self, g_depth.cap, g_depth.d_deep, d_best, d_occ, st, &nq);
     if (e == cudaSuccess) e = g_tp.end(st);
     if (e == cudaSuccess && !g_h_seed) e = cudaMallocHost(&g_h_seed, (kSeedOccSlots + 1) * 8);
     if (e == cudaSuccess) e = cudaMemcpyAsync(g_h_seed, d_occ, kSeedOccSlots * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)  // number of indexed cores = the last bucket offset
         e = cudaMemcpyAsync(g_h_seed + kSeedOccSlots, d_off + nb, 4, cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return fail(cuda_code(e), "seed engine launch: %s", cudaGetErrorString(e));
-    if (launches) *launches = nl + 4;
+    if (launches) *launches = nl + 2 + nq;  // reverse complement of the probes, the two index scans, the query kernels
     return K4B_OK;
 }
 

@@ -152,7 +152,7 @@ cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t 
                               const uint32_t *d_off, const uint4 *d_ent, uint32_t q_begin, uint32_t q_end,
                               uint32_t b_lo, uint32_t b_hi, uint32_t clamp, bool crick, bool three, bool q_impure,
                               SeedSelfRules self, uint32_t depth_cap, uint8_t *d_deep, uint32_t *d_best,
-                              unsigned long long *d_occ, cudaStream_t st);
+                              unsigned long long *d_occ, cudaStream_t st, int *n_launches);
 // d_deep (nullable, one byte per probe position, zeroed by the caller): set to 1 where a core of the probe
 // K-mer has more than depth_cap index entries; launch_seed_deep_count adds to *d_count the flagged valid
 // probe K-mers whose minimum lies below clamp

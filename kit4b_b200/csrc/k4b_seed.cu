@@ -171,6 +171,8 @@ struct SeedCtx {  // launch-wide constants
     uint32_t depth_cap;
     uint8_t *deep;
     int strands, three, q_impure;
+    int core_only;        // >= 0: this pass handles the items of this core only (phase schedule of the join)
+    uint32_t done_below;  // items of probe K-mers whose minimum is <= this are skipped (0 outside the phases)
     SeedSelfRules self;
 };
 struct SeedItem;
@@ -219,7 +221,7 @@ __device__ __forceinline__ bool seed_item_setup(const SeedCtx &cx, uint32_t p, u
     it.pp = it.strand ? (long long)cx.q.len - cx.K - p : p;
     it.cur = __ldg(best + p);            // running minimum so far (other cores / strands / launches)
     if (it.cur > cx.clamp) it.cur = cx.clamp;  // only distances below the "not found" value matter
-    if (it.cur == 0) return false;
+    if (it.cur <= cx.done_below) return false;  // 0: nothing lower exists; phase j: settled, see the join
     const uint32_t shift = it.c * cx.core_len;
     // the probe's own flanks of this core, cut to what lies inside the K-mer (masked once here, so that
     // a test against a pre-masked entry needs no AND)
@@ -289,93 +291,112 @@ __global__ void __launch_bounds__(256) seed_query_kernel(SeedCtx cx, const uint3
 // ---- query, bucket-major join --------------------------------------------------------------
 // With a few thousand entries per bucket and hundreds of items per bucket, streaming the bucket
 // once per item is HBM-bound (16 B per entry test).  Here the items of a probe chunk are sorted by
-// bucket; a CTA takes 64 consecutive sorted items, stages the bucket of each run of equal-bucket
-// items tile by tile in shared memory and lets its consumer warps test their items against the tile:
-// one global read of an entry serves up to 64 entry tests.
-constexpr int kJoinItems = 64;    // sorted items per CTA
-constexpr int kJoinTile = 1024;   // index entries staged per tile (12 KB)
-
-// bucket of every item of the probe chunk [q0, q0+n_probes); inactive items sort to the end
+// bucket; a CTA takes the items of ONE bucket, stages the bucket tile by tile in shared memory and lets
+// its warps test their items against the tile: one global read of an entry serves up to ITEMS entry tests.
+//
+// Phase schedule (whole index on this device): the items of core 0 of every probe K-mer are joined first,
+// then core 1, ...  An alignment with d mismatches leaves at least n_cores - d cores intact, so once
+// cores 0 .. j-1 are done every alignment with fewer than j mismatches has been seen: a probe K-mer whose
+// minimum is <= j needs none of the cores j, j+1, ... any more.  On BASELINE config 4 (half the probes are
+// 3 % mutated copies) that drops a third of the entry tests; on unrelated probes it costs three more small
+// sorts.  With bucket shards (several GPUs) a rank sees only its share of the hits, so the rule does not
+// apply there and all cores go in one pass.
+// bucket of every item of the probe chunk [q0, q0+n_probes); inactive items sort to the end.
+// cx.core_only >= 0 (phase schedule, see launch_seed_query): items of that core only, n_probes * strands of
+// them; an item that is left out only because its probe is already settled for this phase (0 < minimum <=
+// cx.done_below) still reports a deep bucket to the depth watch, as it would have when processed.
 __global__ void __launch_bounds__(256) seed_item_keys_kernel(SeedCtx cx, uint32_t q0, uint32_t n_probes,
                                                              const uint32_t *__restrict__ best,
+                                                             const uint32_t *__restrict__ off,
                                                              uint32_t *__restrict__ keys, uint32_t *__restrict__ ids) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t per_probe = (uint32_t)cx.strands * cx.n_cores;
-    if (i >= n_probes * per_probe) return;
-    const uint32_t pl = i / per_probe;
+    const uint32_t per_pass = cx.core_only >= 0 ? (uint32_t)cx.strands : per_probe;
+    if (i >= n_probes * per_pass) return;
+    const uint32_t pl = i / per_pass;
+    const uint32_t sub = cx.core_only >= 0 ? (i - pl * per_pass) * cx.n_cores + (uint32_t)cx.core_only : i - pl * per_pass;
     SeedItem it;
     uint32_t key = 1u << cx.bits;  // inactive: sorts behind every bucket
-    if (seed_item_setup(cx, q0 + pl, i - pl * per_probe, best, it)) {
+    SeedCtx probe_cx = cx;
+    probe_cx.done_below = 0;  // decode first, the phase rule is applied below
+    if (seed_item_setup(probe_cx, q0 + pl, sub, best, it)) {
         bool ok;
         const uint32_t b = core_bucket(probe_bits(cx, it.strand), it.pp + (long long)it.c * cx.core_len, cx.core_len,
                                        cx.bits, ok);
-        if (ok && b >= cx.b_lo && b < cx.b_hi) key = b;
+        if (ok && b >= cx.b_lo && b < cx.b_hi) {
+            if (it.cur > cx.done_below) key = b;
+            else if (cx.deep && __ldg(off + b + 1) - __ldg(off + b) > cx.depth_cap) cx.deep[it.p] = 1;
+        }
     }
     keys[i] = key;
-    ids[i] = i;
+    ids[i] = pl * per_probe + sub;
 }
 
-__global__ void __launch_bounds__(256) seed_join_kernel(SeedCtx cx, const uint32_t *__restrict__ off,
-                                                        const uint4 *__restrict__ ent, uint32_t q0, uint32_t n_items,
-                                                        const uint32_t *__restrict__ keys,
-                                                        const uint32_t *__restrict__ ids, uint32_t *__restrict__ best,
-                                                        unsigned long long *__restrict__ occ) {
-    __shared__ uint32_t tile_pos[kJoinTile];
-    __shared__ uint2 tile_sig[kJoinTile];
-    __shared__ SeedItem items[kJoinItems];
-    __shared__ uint32_t s_key[kJoinItems], s_mine[kJoinItems];
-    __shared__ uint32_t run_end[kJoinItems];  // run_end[j] = end of the run of equal keys that starts at j
+// ONE BUCKET PER CTA: CTA b finds the items of bucket b_lo + b in the sorted keys (two binary searches), takes
+// them in batches of ITEMS and stages the bucket, TILE entries at a time, once per batch.  (Round 2 first gave
+// every CTA 64 consecutive sorted items whatever their buckets: a bucket's items were then split between CTAs,
+// each staging the whole bucket again and dealing a ragged handful of items to its 8 warps - 53.7 ms on
+// BASELINE config 4 against 33 ms now, 0.67 of the POPC peak.)  With the phase schedule a pass has
+// strands * probes / buckets items per bucket (61 on config 4): one batch, every bucket staged once per pass.
+template <int ITEMS, int TILE>
+__global__ void __launch_bounds__(256, 4) seed_join_kernel(SeedCtx cx, const uint32_t *__restrict__ off,
+                                                                   const uint4 *__restrict__ ent, uint32_t q0,
+                                                                   uint32_t n_items, const uint32_t *__restrict__ keys,
+                                                                   const uint32_t *__restrict__ ids,
+                                                                   uint32_t *__restrict__ best,
+                                                                   unsigned long long *__restrict__ occ) {
+    __shared__ uint32_t tile_pos[TILE];
+    __shared__ uint2 tile_sig[TILE];
+    __shared__ SeedItem items[ITEMS];
+    __shared__ uint32_t s_mine[ITEMS];  // running minimum of the item; 0: nothing (left) to do
+    __shared__ uint32_t s_cur[ITEMS];   // its minimum at set-up; 0: the item is inactive
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t base = blockIdx.x * kJoinItems;
     const uint32_t per_probe = (uint32_t)cx.strands * cx.n_cores;
-    const uint32_t kNone = 1u << cx.bits;
-    if (tid < kJoinItems) {
-        uint32_t key = kNone;
-        s_mine[tid] = 0;
-        if (base + tid < n_items) {
-            key = __ldg(keys + base + tid);
-            if (key < kNone) {
-                const uint32_t id = __ldg(ids + base + tid);
-                const uint32_t pl = id / per_probe;
-                // the item was active when the keys were made; its minimum may have dropped since
-                if (!seed_item_setup(cx, q0 + pl, id - pl * per_probe, best, items[tid])) key = kNone;
-                else s_mine[tid] = items[tid].cur;
-            }
+    const uint32_t key = cx.b_lo + blockIdx.x;
+    const uint32_t lo = __ldg(off + key), hi = __ldg(off + key + 1);
+    if (lo == hi) return;
+    auto first_at_least = [&](uint32_t k) -> uint32_t {  // first sorted item whose key is >= k
+        uint32_t a = 0, b = n_items;
+        while (a < b) {
+            const uint32_t mid = a + ((b - a) >> 1);
+            if (__ldg(keys + mid) < k) a = mid + 1;
+            else b = mid;
         }
-        s_key[tid] = key;
-    }
-    __syncthreads();
-    if (tid < kJoinItems) {  // run boundaries (sorted keys; an item deactivated above splits its run)
-        uint32_t e = tid + 1;
-        while (e < kJoinItems && s_key[e] == s_key[tid]) ++e;
-        run_end[tid] = e;
-    }
-    __syncthreads();
-    for (uint32_t r = 0; r < kJoinItems; r = run_end[r]) {
-        const uint32_t key = s_key[r];
-        if (key >= kNone) continue;
-        const uint32_t r_end = run_end[r];
-        const uint32_t lo = __ldg(off + key), hi = __ldg(off + key + 1);
-        if (occ && tid == 0)
-            atomicAdd(occ + (blockIdx.x & (kSeedOccSlots - 1)), (unsigned long long)(hi - lo) * (r_end - r));
-        if (cx.deep && hi - lo > cx.depth_cap && tid < r_end - r) cx.deep[items[r + tid].p] = 1;
-        for (uint32_t t0 = lo; t0 < hi; t0 += kJoinTile) {
-            const uint32_t n = hi - t0 < (uint32_t)kJoinTile ? hi - t0 : (uint32_t)kJoinTile;
-            __syncthreads();  // the previous tile has been consumed
+        return a;
+    };
+    const uint32_t i_lo = first_at_least(key), i_hi = first_at_least(key + 1);
+    for (uint32_t ib = i_lo; ib < i_hi; ib += ITEMS) {
+        const uint32_t n_it = i_hi - ib < (uint32_t)ITEMS ? i_hi - ib : (uint32_t)ITEMS;
+        __syncthreads();  // the previous batch has been written back
+        if (tid < n_it) {
+            const uint32_t id = __ldg(ids + ib + tid);
+            const uint32_t pl = id / per_probe;
+            // the item was active when the keys were made; its minimum may have dropped since
+            s_cur[tid] = seed_item_setup(cx, q0 + pl, id - pl * per_probe, best, items[tid]) ? items[tid].cur : 0u;
+            s_mine[tid] = s_cur[tid];
+            if (cx.deep && hi - lo > cx.depth_cap && s_cur[tid]) cx.deep[items[tid].p] = 1;
+        }
+        if (occ && tid == 0) atomicAdd(occ + (blockIdx.x & (kSeedOccSlots - 1)), (unsigned long long)(hi - lo) * n_it);
+        for (uint32_t t0 = lo; t0 < hi; t0 += TILE) {
+            const uint32_t n = hi - t0 < (uint32_t)TILE ? hi - t0 : (uint32_t)TILE;
+            __syncthreads();  // the items are set up / the previous tile has been consumed
             for (uint32_t e = tid; e < n; e += 256) {
                 const uint4 v = __ldg(ent + t0 + e);  // one 16-byte entry: position + flank signature
                 tile_pos[e] = v.x;
                 tile_sig[e] = make_uint2(v.y, v.z);
             }
             __syncthreads();
-            for (uint32_t j = r + warp; j < r_end; j += 8) {
+            for (uint32_t j = warp; j < n_it; j += 8) {
                 uint32_t mine = s_mine[j];
                 if (mine == 0) continue;
-                const SeedItem it = items[j];
+                // the item stays in shared memory (the out-of-line verification takes it by reference: a per-thread
+                // copy would be written to local memory for every item and tile); the hot fields go to registers
+                const SeedItem &it = items[j];
+                const uint32_t iq0 = it.q0, iq1 = it.q1, im = it.m;
                 const uint2 *sig = tile_sig + lane;
                 const uint32_t *tpos = tile_pos + lane;
                 // lower bound of the distance from the flank signature (the item's q0 / q1 are masked at set-up)
-                auto bound = [&](uint2 sg) -> uint32_t { return __popc(((sg.x ^ it.q0) | (sg.y ^ it.q1)) & it.m); };
+                auto bound = [&](uint2 sg) -> uint32_t { return __popc(((sg.x ^ iq0) | (sg.y ^ iq1)) & im); };
                 // 8 entries per lane and round: independent loads and POPCs in flight, one branch per round;
                 // whole rounds run without bounds checks, only the tail of a tile tests e < n
                 uint32_t e0 = 0;
@@ -397,10 +418,9 @@ __global__ void __launch_bounds__(256) seed_join_kernel(SeedCtx cx, const uint32
                 if (lane == 0) s_mine[j] = mine;
             }
         }
+        __syncthreads();
+        if (tid < n_it && s_mine[tid] < s_cur[tid]) atomicMin(best + items[tid].p, s_mine[tid]);
     }
-    __syncthreads();
-    if (tid < kJoinItems && s_key[tid] < kNone && s_mine[tid] < items[tid].cur)
-        atomicMin(best + items[tid].p, s_mine[tid]);
 }
 
 // probe K-mers flagged by the depth watch that were answered below the "not found" value: only there
@@ -451,11 +471,31 @@ cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t b_lo, uin
     return cudaGetLastError();
 }
 
+// kernel shapes of the join: {items per batch, entries per tile}; K4B_SEED_JOIN_VARIANT picks one (tests, measurements)
+constexpr int kJoinDefaultVariant = 0;
+static cudaError_t join_launch(int variant, const SeedCtx &cx, const uint32_t *d_off, const uint4 *d_ent, uint32_t q0,
+                               uint32_t n_items, const uint32_t *keys, const uint32_t *ids, uint32_t *d_best,
+                               unsigned long long *d_occ, cudaStream_t st) {
+    const uint32_t grid = cx.b_hi - cx.b_lo;  // one CTA per bucket of this launch's share
+    switch (variant) {
+        case 0: seed_join_kernel<128, 3072><<<grid, 256, 0, st>>>(cx, d_off, d_ent, q0, n_items, keys, ids, d_best, d_occ); break;
+        case 1: seed_join_kernel<64, 2048><<<grid, 256, 0, st>>>(cx, d_off, d_ent, q0, n_items, keys, ids, d_best, d_occ); break;
+        case 2: seed_join_kernel<128, 1024><<<grid, 256, 0, st>>>(cx, d_off, d_ent, q0, n_items, keys, ids, d_best, d_occ); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t K, uint32_t core_len,
                               const uint32_t *d_off, const uint4 *d_ent, uint32_t q_begin, uint32_t q_end,
                               uint32_t b_lo, uint32_t b_hi, uint32_t clamp, bool crick, bool three, bool q_impure,
                               SeedSelfRules self, uint32_t depth_cap, uint8_t *d_deep, uint32_t *d_best,
-                              unsigned long long *d_occ, cudaStream_t st) {
+                              unsigned long long *d_occ, cudaStream_t st, int *n_launches) {
+    int own = 0;  // kernels of this file enqueued (the library sort launches are not counted)
+    struct Report {
+        int *dst, &n;
+        ~Report() { if (dst) *dst = n; }
+    } report{n_launches, own};
     if (q_begin >= q_end || t.len < K || q.len < K) return cudaSuccess;
     SeedCtx cx;
     cx.q = q;
@@ -473,6 +513,8 @@ cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t 
     cx.strands = crick ? 2 : 1;
     cx.three = three ? 1 : 0;
     cx.q_impure = q_impure ? 1 : 0;
+    cx.core_only = -1;
+    cx.done_below = 0;
     cx.self = self;
     const uint32_t per_probe = (uint32_t)cx.strands * cx.n_cores;
     // bucket-major join when buckets are long enough to be worth staging (short cores on long
@@ -487,13 +529,19 @@ cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t 
             const uint32_t e = (q_end - b > max_probes) ? b + max_probes : q_end;
             const unsigned long long w = (unsigned long long)(e - b) * per_probe;
             seed_query_kernel<<<(unsigned)((w + 7) / 8), 256, 0, st>>>(cx, d_off, d_ent, b, e, d_best, d_occ);
+            ++own;
             const cudaError_t err = cudaGetLastError();
             if (err != cudaSuccess) return err;
             b = e;
         }
         return cudaSuccess;
     }
-    // probe chunks of at most 2^25 items: keys -> radix sort by bucket -> join
+    // probe chunks of at most 2^25 items: keys -> radix sort by bucket -> join, core by core when this
+    // device holds the whole index (phase schedule, see above; K4B_SEED_PHASES=0 joins all cores in one pass)
+    const char *ph = getenv("K4B_SEED_PHASES");
+    const bool phases = (ph ? atoi(ph) != 0 : true) && cx.n_cores > 1 && b_lo == 0 && b_hi == (1u << cx.bits);
+    const char *jv = getenv("K4B_SEED_JOIN_VARIANT");  // kernel shape, for measurements (see join_launch)
+    const int variant = jv ? atoi(jv) : kJoinDefaultVariant;
     const uint32_t chunk_probes = std::max(1u, (1u << 25) / per_probe);
     const uint32_t max_items = std::min<unsigned long long>((unsigned long long)chunk_probes,
                                                             (unsigned long long)(q_end - q_begin)) * per_probe;
@@ -511,16 +559,17 @@ cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t 
     uint32_t *k_in = d_buf, *k_out = d_buf + max_items, *i_in = k_out + max_items, *i_out = i_in + max_items;
     for (uint32_t b = q_begin; b < q_end && err == cudaSuccess;) {
         const uint32_t e = (q_end - b > chunk_probes) ? b + chunk_probes : q_end;
-        const uint32_t n_items = (e - b) * per_probe;
-        seed_item_keys_kernel<<<(n_items + 255) / 256, 256, 0, st>>>(cx, b, e - b, d_best, k_in, i_in);
-        err = cudaGetLastError();
-        if (err == cudaSuccess)
-            err = cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, k_in, k_out, i_in, i_out, (int)n_items, 0,
-                                                  (int)cx.bits + 1, st);
-        if (err == cudaSuccess) {
-            seed_join_kernel<<<(n_items + kJoinItems - 1) / kJoinItems, 256, 0, st>>>(cx, d_off, d_ent, b, n_items, k_out,
-                                                                                    i_out, d_best, d_occ);
+        for (uint32_t pass = 0; pass < (phases ? cx.n_cores : 1u) && err == cudaSuccess; ++pass) {
+            cx.core_only = phases ? (int)pass : -1;
+            cx.done_below = phases ? pass : 0u;
+            const uint32_t n_items = (e - b) * (phases ? (uint32_t)cx.strands : per_probe);
+            seed_item_keys_kernel<<<(n_items + 255) / 256, 256, 0, st>>>(cx, b, e - b, d_best, d_off, k_in, i_in);
             err = cudaGetLastError();
+            if (err == cudaSuccess)
+                err = cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, k_in, k_out, i_in, i_out, (int)n_items, 0,
+                                                      (int)cx.bits + 1, st);
+            if (err == cudaSuccess) err = join_launch(variant, cx, d_off, d_ent, b, n_items, k_out, i_out, d_best, d_occ, st);
+            own += 2;  // item keys + join
         }
         b = e;
     }

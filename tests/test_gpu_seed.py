@@ -80,6 +80,24 @@ def test_seed_engine_bucket_major_join_matches_oracle(oracle, monkeypatch, K, R,
                           oracle.targeted_self_brute(target, K, R, both, 2))
 
 
+@pytest.mark.parametrize("phases", ["0", "1"])
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
+def test_seed_join_shapes_and_phase_schedule(oracle, monkeypatch, variant, phases):
+    """every shape of the join kernel (items per CTA, tile size: K4B_SEED_JOIN_VARIANT) with and without the
+    core-by-core phase schedule
+    (K4B_SEED_PHASES) equals the oracle - probes with hits at every distance, both strands, and the
+    assembly against itself with the -z filter"""
+    monkeypatch.setenv("K4B_SEED_JOIN", "1")
+    monkeypatch.setenv("K4B_SEED_JOIN_VARIANT", variant)
+    monkeypatch.setenv("K4B_SEED_PHASES", phases)
+    for K, R, both in ((32, 3, True), (25, 2, False), (100, 4, True)):
+        target, probes = _planted(5600 + K, [6000, 3000, 2500])
+        assert np.array_equal(k4b.targeted(target, probes, K, R, both), oracle.targeted_brute(target, probes, K, R, both)), (K, R)
+    target, _ = _planted(5700, [5000, 2500])
+    assert np.array_equal(k4b.targeted(target, None, 32, 3, True, intra_inter_both=1),
+                          oracle.targeted_self_brute(target, 32, 3, True, 1))
+
+
 def test_seed_engine_targets_with_non_acgt(oracle):
     target, probes = _planted(4100, [5000, 4000], alpha_t=5)  # N in the targets, probes stay ACGT
     target[1000:1010] = 4
