@@ -1095,9 +1095,19 @@ static int seed_run(k4b_packed *probes, k4b_packed *targets, int both_strands, u
         self.n_ent = (uint32_t)g_zf.starts.size();
     }
     RC(g_tp.begin(probes->device, true, st));
-    int nq = 0;
-    cudaError_t e = launch_seed_index(targets->view(), core_len, b_lo, b_hi, d_cnt, d_off, d_cur, d_ent, tmp_buf.p,
-                                      temp_bytes, st);
+    int nq = 0, ni = 0;
+    // index build: entries placed one by one, or (default; K4B_SEED_INDEX=0 turns it off; buckets of <= 16 bits) by two partition
+    // passes through a scratch array as large as the index; without room for it the first build is used
+    DevScratch part_buf;
+    const char *ix = getenv("K4B_SEED_INDEX");
+    const int part_mode = ix ? atoi(ix) : kSeedIndexDefault;
+    if (part_mode != 0 && seed_index_can_partition(core_len) && part_buf.alloc(ent_bytes, st) != cudaSuccess) {
+        part_buf.p = nullptr;
+        cudaGetLastError();  // out of memory is no error here
+    }
+    cudaError_t e = launch_seed_index(targets->view(), core_len, b_lo, b_hi, d_cnt, d_off, d_cur, d_ent,
+                                      part_buf.as<uint4>(), part_mode, tmp_buf.p, temp_bytes, st, &ni);
+    part_buf.release();  // stream-ordered: the join's sort buffers may take its place
     if (e == cudaSuccess)
         e = launch_seed_query(probes->view(), crick ? probes->rc_view() : probes->view(), targets->view(), K, core_len,
                               d_off, d_ent, q_begin, q_end, b_lo, b_hi, clamp, crick, targets->has_non_acgt != 0,
@@ -1108,7 +1118,7 @@ static int seed_run(k4b_packed *probes, k4b_packed *targets, int both_strands, u
     if (e == cudaSuccess)  // number of indexed cores = the last bucket offset
         e = cudaMemcpyAsync(g_h_seed + kSeedOccSlots, d_off + nb, 4, cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return fail(cuda_code(e), "seed engine launch: %s", cudaGetErrorString(e));
-    if (launches) *launches = nl + 2 + nq;  // reverse complement of the probes, the two index scans, the query kernels
+    if (launches) *launches = nl + ni + nq;  // reverse complement of the probes, the index passes, the query kernels
     return K4B_OK;
 }
 

@@ -145,9 +145,12 @@ struct SeedSelfRules {          // probes drawn from the indexed assembly itself
 uint32_t seed_bucket_bits(uint32_t core_len);
 size_t seed_scan_temp_bytes(uint32_t n_buckets);
 // only cores whose bucket lies in [b_lo, b_hi) are indexed / answered (bucket shards of a multi-GPU run)
+// d_part: nullptr = entries placed one by one; else t.len entries of scratch for the two partition passes
+// (only when seed_index_can_partition(core_len)); *n_launches = kernels of k4b_seed.cu enqueued
+bool seed_index_can_partition(uint32_t core_len);
 cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t b_lo, uint32_t b_hi, uint32_t *d_cnt,
-                              uint32_t *d_off, uint32_t *d_cursor, uint4 *d_ent, void *d_temp, size_t temp_bytes,
-                              cudaStream_t st);
+                              uint32_t *d_off, uint32_t *d_cursor, uint4 *d_ent, uint4 *d_part, int part_mode, void *d_temp,
+                              size_t temp_bytes, cudaStream_t st, int *n_launches);
 cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t K, uint32_t core_len,
                               const uint32_t *d_off, const uint4 *d_ent, uint32_t q_begin, uint32_t q_end,
                               uint32_t b_lo, uint32_t b_hi, uint32_t clamp, bool crick, bool three, bool q_impure,
@@ -158,6 +161,12 @@ cudaError_t launch_seed_query(ImageView q, ImageView rcq, ImageView t, uint32_t 
 // probe K-mers whose minimum lies below clamp
 cudaError_t launch_seed_deep_count(const uint8_t *d_deep, const uint32_t *d_best, ImageView q, uint32_t n, uint32_t clamp,
                                    unsigned long long *d_count, cudaStream_t st);
+// index build, K4B_SEED_INDEX overrides: 0 = entries placed one by one; else partition passes (flag 1) with
+// tiles of 4096 instead of 2048 entries (2), the counters of the count pass in shared memory (4), the three-word
+// field extraction in pass A (8), the persistent pass B (16; tiles of 2048 only)
+constexpr int kSeedIndexPartition = 1, kSeedIndexTile4096 = 2, kSeedIndexSmemCount = 4, kSeedIndexFastA = 8,
+              kSeedIndexPersistB = 16;
+constexpr int kSeedIndexDefault = kSeedIndexPartition | kSeedIndexSmemCount | kSeedIndexFastA | kSeedIndexPersistB;
 constexpr int kSeedOccSlots = 1024;  // d_occ (nullable): bucket entries streamed, summed over these slots
 cudaError_t launch_microbench(int which, int iters, uint32_t *d_sink, int *blocks, int *threads,
                               int *ops_per_thread_iter, cudaStream_t st);

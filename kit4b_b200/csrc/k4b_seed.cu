@@ -136,6 +136,324 @@ __global__ void __launch_bounds__(256) seed_scan_kernel(ImageView t, uint32_t n_
     }
 }
 
+// ---- index by two partition passes (buckets of at most 16 bits) ------------------------------
+// The fill above costs one returning L2 atomic and one scattered 16-byte store PER ENTRY.  Here the
+// entries are moved twice, but in runs: pass A cuts them out of the planes exactly as the fill does and
+// groups them by the TOP 8 bits of the bucket into a scratch array laid out like the index (coarse
+// partition p starts at off[p << nlow]); pass B reads a coarse partition in tiles and groups by the
+// remaining nlow = bits - 8 bits into the final bucket runs.  A CTA groups its tile of 2048 entries in
+// shared memory (ranks from a shared-memory histogram), reserves ONE run per digit with one global atomic
+// (a warp's 32 cursors share a line: 8 atomic requests per CTA instead of 2048) and copies the grouped
+// tile out with consecutive lanes on consecutive slots.  3x the bytes of the fill, all of them coalesced.
+// Order inside a bucket is arbitrary in both builds (the queries take minima).
+constexpr int kPartPer = 8;  // entries per thread: a tile is THREADS * 8 entries (2048 or 4096)
+
+// exclusive prefix sums over the first 256 threads of the CTA (one value each); every thread calls
+__device__ __forceinline__ uint32_t cta_excl_scan_256(uint32_t v, uint32_t *ws, uint32_t &total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += n;
+    }
+    if (warp < 8 && lane == 31) ws[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 8; ++w) {
+        const uint32_t s = ws[w];
+        all += s;
+        if (w < warp) before += s;
+    }
+    total = all;
+    __syncthreads();  // ws is free again
+    return before + inc - v;
+}
+
+struct PartShared {
+    uint32_t hist[256], start[256], gbase[256], ws[8];
+};
+
+// groups the entries the CTA's threads hold (e[u].w = bucket < 2^16, bit u of `live` = e[u] is an entry) by
+// digit_of(bucket) < 256 in `out` (a tile of entries) and reserves one run per group: reserve(digit, size) is the
+// slot of its first entry.  Returns the number of entries; e is dead afterwards.  part_copy_out then writes the
+// groups to their runs, consecutive lanes on consecutive slots.
+template <class DigitOf, class Reserve>
+__device__ __forceinline__ uint32_t part_group(uint4 (&e)[kPartPer], uint32_t live, DigitOf digit_of, Reserve reserve,
+                                               uint4 *out, PartShared &sh) {
+    const uint32_t tid = threadIdx.x;
+    if (tid < 256) sh.hist[tid] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kPartPer; ++u)
+        if ((live >> u) & 1u) e[u].w |= atomicAdd(&sh.hist[digit_of(e[u].w)], 1u) << 16;  // rank inside the group, < 4096
+    __syncthreads();
+    uint32_t total;
+    const uint32_t h = tid < 256 ? sh.hist[tid] : 0u;
+    const uint32_t ex = cta_excl_scan_256(h, sh.ws, total);
+    if (tid < 256) {
+        sh.start[tid] = ex;
+        sh.gbase[tid] = h ? reserve(tid, h) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kPartPer; ++u)
+        if ((live >> u) & 1u) {
+            const uint32_t b = e[u].w & 0xffffu;
+            out[sh.start[digit_of(b)] + (e[u].w >> 16)] = make_uint4(e[u].x, e[u].y, e[u].z, b);
+        }
+    return total;
+}
+template <int THREADS, class DigitOf>
+__device__ __forceinline__ void part_copy_out(uint32_t total, DigitOf digit_of, uint4 *__restrict__ dst, const uint4 *out,
+                                              const PartShared &sh) {
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < total; i += THREADS) {
+        const uint4 v = out[i];
+        const uint32_t d = digit_of(v.w);
+        dst[sh.gbase[d] + (i - sh.start[d])] = v;
+    }
+}
+template <int THREADS, class DigitOf, class Reserve>
+__device__ __forceinline__ void part_tile_out(uint4 (&e)[kPartPer], uint32_t live, DigitOf digit_of, Reserve reserve,
+                                              uint4 *__restrict__ dst, uint4 *out, PartShared &sh) {
+    part_copy_out<THREADS>(part_group(e, live, digit_of, reserve, out, sh), digit_of, dst, out, sh);
+}
+
+extern __shared__ uint4 part_out[];  // THREADS * 8 entries
+
+// pass A: positions -> entries grouped by the top 8 bits of the bucket.  cur_a: 256 zeroed counters.
+// FAST: bucket and flank signature cut out of three staged words per plane (the 16 + core + 16 bases of a core of at
+// most 8 bases span 40 bits) instead of one two-word window per field
+template <int THREADS, bool FAST>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) seed_part_a_kernel(ImageView t, uint32_t n_pos, uint32_t core_len,
+                                                                              uint32_t bits, uint32_t b_lo, uint32_t b_hi,
+                                                                              const uint32_t *__restrict__ off,
+                                                                              uint32_t *__restrict__ cur_a,
+                                                                              uint4 *__restrict__ tmp) {
+    constexpr int kTile = THREADS * kPartPer;
+    constexpr int kStage = kTile / 32 + 1 + kSeedHalo + 1;  // words per plane, as in seed_scan_kernel
+    __shared__ uint32_t stage[3][kStage];
+    __shared__ PartShared sh;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t base = blockIdx.x * (uint32_t)kTile;
+    const long long w0 = (long long)(base >> 5) - 1;
+    for (uint32_t i = tid; i < 3u * kStage; i += THREADS) {
+        const uint32_t p = i / kStage, w = i - p * kStage;
+        stage[p][w] = __ldg(t.plane((int)p) + w0 + w);
+    }
+    __syncthreads();
+    SmemBits src;
+    src.pl[0] = stage[0];
+    src.pl[1] = stage[1];
+    src.pl[2] = stage[2];
+    src.origin = w0 * 32;
+    uint4 e[kPartPer];
+    uint32_t live = 0;
+#pragma unroll
+    for (int j = 0; j < kPartPer; ++j) {
+        const uint32_t pos = base + (uint32_t)j * THREADS + tid;
+        e[j] = make_uint4(0, 0, 0, 0);
+        if (FAST) {
+            if (pos < n_pos) {
+                const uint32_t lb = pos - base + 16;  // bit of base pos - 16 in the staged copy (which starts at base - 32)
+                const uint32_t wi = lb >> 5, sh5 = lb & 31u, m = (1u << core_len) - 1u;
+                // per plane: first word = bases pos-16 .. pos+15, second = bases pos+16 .. pos+47
+                const uint32_t a0 = __funnelshift_r(stage[0][wi], stage[0][wi + 1], sh5);
+                const uint32_t a1 = __funnelshift_r(stage[0][wi + 1], stage[0][wi + 2], sh5);
+                const uint32_t c0 = __funnelshift_r(stage[1][wi], stage[1][wi + 1], sh5);
+                const uint32_t c1 = __funnelshift_r(stage[1][wi + 1], stage[1][wi + 2], sh5);
+                const uint32_t n0 = __funnelshift_r(stage[2][wi], stage[2][wi + 1], sh5);
+                const uint32_t n1 = __funnelshift_r(stage[2][wi + 1], stage[2][wi + 2], sh5);
+                const uint32_t k0 = __funnelshift_r(a0, a1, 16) & m, k1 = __funnelshift_r(c0, c1, 16) & m;
+                const uint32_t b = k0 | (k1 << core_len);
+                if ((__funnelshift_r(n0, n1, 16) & m) == 0 && b >= b_lo && b < b_hi) {
+                    e[j] = make_uint4(pos, (a0 & 0xffffu) | (__funnelshift_r(a0, a1, 16 + core_len) << 16),
+                                      (c0 & 0xffffu) | (__funnelshift_r(c0, c1, 16 + core_len) << 16), b);
+                    live |= 1u << j;
+                }
+            }
+        } else if (pos < n_pos) {
+            bool ok;
+            const uint32_t b = core_bucket(src, pos, core_len, bits, ok);
+            if (ok && b >= b_lo && b < b_hi) {
+                const uint2 sg = flank_sig(src, pos, core_len);
+                e[j] = make_uint4(pos, sg.x, sg.y, b);
+                live |= 1u << j;
+            }
+        }
+    }
+    const uint32_t nlow = bits - 8;
+    part_tile_out<THREADS>(
+        e, live, [nlow](uint32_t b) { return b >> nlow; },
+        [&](uint32_t d, uint32_t n) { return __ldg(off + ((size_t)d << nlow)) + atomicAdd(cur_a + d, n); }, tmp, part_out,
+        sh);
+}
+
+// pass B: tile `blockIdx.x` of the coarse partitions (tiles are numbered partition by partition; every CTA
+// derives the numbering from the 257 partition bounds) -> final bucket runs.  cur: a copy of off.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) seed_part_b_kernel(uint32_t bits, const uint32_t *__restrict__ off,
+                                                                              uint32_t *__restrict__ cur,
+                                                                              const uint4 *__restrict__ tmp,
+                                                                              uint4 *__restrict__ ent) {
+    constexpr uint32_t kTile = THREADS * kPartPer;
+    __shared__ PartShared sh;
+    __shared__ uint32_t s_part, s_first, s_n;
+    const uint32_t tid = threadIdx.x, nlow = bits - 8;
+    uint32_t lo = 0, hi = 0;
+    if (tid < 256) {
+        lo = __ldg(off + ((size_t)tid << nlow));
+        hi = __ldg(off + ((size_t)(tid + 1) << nlow));
+    }
+    const uint32_t tiles = (hi - lo + kTile - 1) / kTile;
+    uint32_t total;
+    const uint32_t ex = cta_excl_scan_256(tiles, sh.ws, total);
+    if (blockIdx.x >= total) return;  // the grid is an upper bound
+    if (blockIdx.x >= ex && blockIdx.x < ex + tiles) {  // tiles = 0 outside the first 256 threads
+        const uint32_t first = lo + (blockIdx.x - ex) * kTile;
+        s_part = tid;
+        s_first = first;
+        s_n = hi - first < kTile ? hi - first : kTile;
+    }
+    __syncthreads();
+    const uint32_t part = s_part, first = s_first, n = s_n;
+    uint4 e[kPartPer];
+    uint32_t live = 0;
+#pragma unroll
+    for (int j = 0; j < kPartPer; ++j) {
+        const uint32_t i = (uint32_t)j * THREADS + tid;
+        e[j] = make_uint4(0, 0, 0, 0);
+        if (i < n) {
+            e[j] = __ldg(tmp + first + i);
+            live |= 1u << j;
+        }
+    }
+    const uint32_t low_mask = (1u << nlow) - 1u;
+    uint32_t *cur_p = cur + ((size_t)part << nlow);
+    part_tile_out<THREADS>(
+        e, live, [low_mask](uint32_t b) { return b & low_mask; },
+        [&](uint32_t d, uint32_t m) { return atomicAdd(cur_p + d, m); }, ent, part_out, sh);
+}
+
+// count pass with the counters in shared memory: one persistent CTA per SM keeps ALL buckets (at most 2^16) as
+// 16-bit halves of 2^15 words and counts its chunks of 8192 positions with shared-memory atomics; the global
+// counters see one add per bucket and CTA at the end instead of one per position (the one-per-position pass runs
+// at the rate of the L2 atomics: 500 M in 3.5 ms).  A half that reaches 2^15 hands 2^15 on to the global counter
+// at once (the thread that sees 0x7fff -> 0x8000 subtracts it again), so no half can carry into its neighbour.
+// The planes of the next chunk are fetched (one word per thread) while the current one is counted.
+constexpr int kCountChunk = 8192, kCountThreads = 1024;
+constexpr int kCountStage = kCountChunk / 32 + 2;
+extern __shared__ uint32_t count_half[];
+__global__ void __launch_bounds__(kCountThreads, 1) seed_count_smem_kernel(ImageView t, uint32_t n_pos, uint32_t core_len,
+                                                                           uint32_t bits, uint32_t b_lo, uint32_t b_hi,
+                                                                           uint32_t *__restrict__ cnt) {
+    static_assert(3 * kCountStage <= kCountThreads, "one staging word per thread");
+    __shared__ uint32_t stage[3][kCountStage];
+    const uint32_t tid = threadIdx.x, words = 1u << (bits - 1), m = (1u << core_len) - 1u;
+    for (uint32_t i = tid; i < words; i += kCountThreads) count_half[i] = 0;
+    const uint32_t n_chunks = (n_pos + kCountChunk - 1) / kCountChunk;
+    const bool loader = tid < 3 * kCountStage;
+    const uint32_t lp = tid / kCountStage, lw = tid - lp * kCountStage;
+    uint32_t chunk = blockIdx.x, nxt = 0;
+    if (loader && chunk < n_chunks) nxt = __ldg(t.plane((int)lp) + (size_t)chunk * (kCountChunk / 32) + lw);
+    while (chunk < n_chunks) {
+        __syncthreads();  // the previous chunk has been counted (first round: the counters are zeroed)
+        if (loader) stage[lp][lw] = nxt;
+        __syncthreads();
+        const uint32_t next = chunk + gridDim.x;
+        if (loader && next < n_chunks) nxt = __ldg(t.plane((int)lp) + (size_t)next * (kCountChunk / 32) + lw);
+        const uint32_t base = chunk * (uint32_t)kCountChunk;
+#pragma unroll
+        for (int j = 0; j < kCountChunk / kCountThreads; ++j) {
+            const uint32_t lb = (uint32_t)j * kCountThreads + tid;
+            if (base + lb < n_pos) {
+                const uint32_t wi = lb >> 5, sh5 = lb & 31u;
+                const uint32_t k0 = __funnelshift_r(stage[0][wi], stage[0][wi + 1], sh5) & m;
+                const uint32_t k1 = __funnelshift_r(stage[1][wi], stage[1][wi + 1], sh5) & m;
+                const uint32_t bad = __funnelshift_r(stage[2][wi], stage[2][wi + 1], sh5) & m;
+                const uint32_t b = k0 | (k1 << core_len);
+                if (bad == 0 && b >= b_lo && b < b_hi) {
+                    const uint32_t hs = (b & 1u) << 4;
+                    const uint32_t old = atomicAdd(&count_half[b >> 1], 1u << hs);
+                    if (((old >> hs) & 0xffffu) == 0x7fffu) {
+                        atomicSub(&count_half[b >> 1], 0x8000u << hs);
+                        atomicAdd(cnt + b, 0x8000u);
+                    }
+                }
+            }
+        }
+        chunk = next;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < words; i += kCountThreads) {
+        const uint32_t w = count_half[i];
+        if (w & 0xffffu) atomicAdd(cnt + 2 * i, w & 0xffffu);
+        if (w >> 16) atomicAdd(cnt + 2 * i + 1, w >> 16);
+    }
+}
+
+// pass B, persistent: 4 CTAs per SM walk the tiles with a stride of the grid; the loads of a CTA's next tile are
+// issued as soon as the current one is grouped in shared memory, so they overlap its copy-out (ncu of the
+// one-tile-per-CTA kernel: 23 of 33 stall cycles per issue wait for the tile's loads, issue slots 21 % busy).
+__global__ void __launch_bounds__(256, 4) seed_part_b_persistent_kernel(uint32_t bits, const uint32_t *__restrict__ off,
+                                                                        uint32_t *__restrict__ cur,
+                                                                        const uint4 *__restrict__ tmp,
+                                                                        uint4 *__restrict__ ent) {
+    constexpr uint32_t kTile = 256 * kPartPer;
+    __shared__ PartShared sh;
+    __shared__ uint32_t s_ts[257], s_lo[257];  // first tile number and first entry of every coarse partition
+    const uint32_t tid = threadIdx.x, nlow = bits - 8, low_mask = (1u << nlow) - 1u;
+    uint32_t n_tiles;
+    {
+        const uint32_t lo = __ldg(off + ((size_t)tid << nlow)), hi = __ldg(off + ((size_t)(tid + 1) << nlow));
+        const uint32_t ex = cta_excl_scan_256((hi - lo + kTile - 1) / kTile, sh.ws, n_tiles);
+        s_ts[tid] = ex;
+        s_lo[tid] = lo;
+        if (tid == 255) {
+            s_ts[256] = n_tiles;
+            s_lo[256] = hi;
+        }
+    }
+    __syncthreads();
+    uint4 e[kPartPer];
+    uint32_t live, part;
+    auto fetch = [&](uint32_t tile) {  // partition of the tile (the last one that starts at or before it), its entries
+        uint32_t a = 0, b = 256;
+        while (b - a > 1) {
+            const uint32_t mid = (a + b) >> 1;
+            if (s_ts[mid] <= tile) a = mid;
+            else b = mid;
+        }
+        const uint32_t first = s_lo[a] + (tile - s_ts[a]) * kTile, left = s_lo[a + 1] - first;
+        const uint32_t n = left < kTile ? left : kTile;
+        part = a;
+        live = 0;
+#pragma unroll
+        for (int j = 0; j < kPartPer; ++j) {
+            const uint32_t i = (uint32_t)j * 256 + tid;
+            e[j] = make_uint4(0, 0, 0, 0);
+            if (i < n) {
+                e[j] = __ldg(tmp + first + i);
+                live |= 1u << j;
+            }
+        }
+    };
+    auto digit_of = [low_mask](uint32_t b) { return b & low_mask; };
+    uint32_t tile = blockIdx.x;
+    if (tile < n_tiles) fetch(tile);
+    while (tile < n_tiles) {
+        uint32_t *cur_p = cur + ((size_t)part << nlow);
+        const uint32_t total = part_group(e, live, digit_of, [&](uint32_t d, uint32_t m) { return atomicAdd(cur_p + d, m); },
+                                          part_out, sh);
+        tile += gridDim.x;
+        if (tile < n_tiles) fetch(tile);  // in flight during the copy-out
+        part_copy_out<256>(total, digit_of, ent, part_out, sh);
+        __syncthreads();  // the tile and its tables are free again
+    }
+}
+
 // mismatches between the K-mer of `a` at pa and the K-mer of `b` at pb (b may hold non-ACGT
 // symbols, a is pure ACGT inside the window); stops counting once `limit` is reached
 __device__ __forceinline__ uint32_t kmer_mismatches(const ImageView &a, long long pa, const ImageView &b,
@@ -450,28 +768,101 @@ size_t seed_scan_temp_bytes(uint32_t n_buckets) {
     return bytes;
 }
 
+// partition passes.  FAST_A: three-word field extraction in pass A; PERSIST_B: persistent pass B with the next tile's
+// loads in flight during the copy-out (256 threads only)
+template <int THREADS, bool FAST_A, bool PERSIST_B>
+static cudaError_t part_launch(ImageView t, uint32_t n_pos, uint32_t core_len, uint32_t bits, uint32_t b_lo, uint32_t b_hi,
+                               const uint32_t *d_off, uint32_t *d_cur_a, uint32_t *d_cursor, uint4 *d_part, uint4 *d_ent,
+                               cudaStream_t st) {
+    constexpr uint32_t kTile = THREADS * kPartPer;
+    constexpr size_t kSmem = (size_t)kTile * sizeof(uint4);
+    static_assert(!PERSIST_B || THREADS == 256, "the persistent pass B has 256 threads");
+    if (kSmem > 48 * 1024) {  // opt-in, per device
+        cudaError_t e = cudaFuncSetAttribute(seed_part_a_kernel<THREADS, FAST_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(seed_part_b_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+        if (e != cudaSuccess) return e;
+    }
+    seed_part_a_kernel<THREADS, FAST_A><<<(n_pos + kTile - 1) / kTile, THREADS, kSmem, st>>>(t, n_pos, core_len, bits, b_lo, b_hi,
+                                                                                           d_off, d_cur_a, d_part);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // tiles of all coarse partitions: at most entries / tile + one ragged tile per partition
+    const uint32_t max_tiles = n_pos / kTile + 257;
+    if (!PERSIST_B) {
+        seed_part_b_kernel<THREADS><<<max_tiles, THREADS, kSmem, st>>>(bits, d_off, d_cursor, d_part, d_ent);
+    } else {
+        int dev = 0, sms = 0;
+        e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        const uint32_t grid = std::min<uint32_t>(max_tiles, (uint32_t)sms * 4u);
+        seed_part_b_persistent_kernel<<<grid, 256, kSmem, st>>>(bits, d_off, d_cursor, d_part, d_ent);
+    }
+    return cudaGetLastError();
+}
+
+bool seed_index_can_partition(uint32_t core_len) {
+    const uint32_t bits = seed_bucket_bits(core_len);
+    return bits >= 9 && bits <= 16;
+}
+
 // d_cnt: n_buckets+1 counters (zeroed by the caller), turned into bucket offsets d_off
 // (n_buckets+1 entries, d_off[n_buckets] = number of indexed cores); d_cursor: n_buckets+1
 // scratch; d_ent: t.len entries.  Only cores whose bucket lies in [b_lo, b_hi) are indexed.
+// d_part: nullptr = the entries are placed one by one (atomic cursor + scattered store), else t.len
+// entries of scratch for the two partition passes (seed_index_can_partition(core_len) must hold), in tiles
+// of 2048 entries; part_mode is a set of kSeedIndex* flags (k4b_kernels.cuh) that select the kernel variants.
 cudaError_t launch_seed_index(ImageView t, uint32_t core_len, uint32_t b_lo, uint32_t b_hi, uint32_t *d_cnt,
-                              uint32_t *d_off, uint32_t *d_cursor, uint4 *d_ent, void *d_temp, size_t temp_bytes,
-                              cudaStream_t st) {
+                              uint32_t *d_off, uint32_t *d_cursor, uint4 *d_ent, uint4 *d_part, int part_mode, void *d_temp,
+                              size_t temp_bytes, cudaStream_t st, int *n_launches) {
+    if (n_launches) *n_launches = 0;
     if (t.len < core_len) return cudaSuccess;
     const uint32_t bits = seed_bucket_bits(core_len), nb = 1u << bits;
     const uint32_t n_pos = t.len - core_len + 1;
     const uint32_t grid = (n_pos + kSeedChunk - 1) / kSeedChunk;
-    seed_scan_kernel<false><<<grid, 256, 0, st>>>(t, n_pos, core_len, bits, b_lo, b_hi, d_cnt, nullptr);
-    cudaError_t e = cudaGetLastError();
+    if (d_part && !seed_index_can_partition(core_len)) return cudaErrorInvalidValue;
+    cudaError_t e;
+    if (d_part && (part_mode & kSeedIndexSmemCount)) {
+        int dev = 0, sms = 0;
+        const size_t smem = (size_t)nb * 2;  // 16 bits per bucket
+        e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(seed_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const uint32_t n_chunks = (n_pos + kCountChunk - 1) / kCountChunk;
+        seed_count_smem_kernel<<<std::min<uint32_t>(n_chunks, (uint32_t)sms), kCountThreads, smem, st>>>(t, n_pos, core_len, bits,
+                                                                                                       b_lo, b_hi, d_cnt);
+    } else {
+        seed_scan_kernel<false><<<grid, 256, 0, st>>>(t, n_pos, core_len, bits, b_lo, b_hi, d_cnt, nullptr);
+    }
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     e = cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_cnt, d_off, (int)nb + 1, st);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyAsync(d_cursor, d_off, ((size_t)nb + 1) * 4, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return e;
-    seed_scan_kernel<true><<<grid, 256, 0, st>>>(t, n_pos, core_len, bits, b_lo, b_hi, d_cursor, d_ent);
-    return cudaGetLastError();
+    if (!d_part) {
+        seed_scan_kernel<true><<<grid, 256, 0, st>>>(t, n_pos, core_len, bits, b_lo, b_hi, d_cursor, d_ent);
+        if (n_launches) *n_launches = 2;
+        return cudaGetLastError();
+    }
+    e = cudaMemsetAsync(d_cnt, 0, 256 * 4, st);  // the counts are spent: 256 coarse cursors for pass A
+    if (e != cudaSuccess) return e;
+    if (n_launches) *n_launches = 3;
+#define K4B_PART(T, FA, PB) part_launch<T, FA, PB>(t, n_pos, core_len, bits, b_lo, b_hi, d_off, d_cnt, d_cursor, d_part, d_ent, st)
+    const bool fast_a = (part_mode & kSeedIndexFastA) != 0, persist_b = (part_mode & kSeedIndexPersistB) != 0;
+    if (part_mode & kSeedIndexTile4096) return fast_a ? K4B_PART(512, true, false) : K4B_PART(512, false, false);
+    if (persist_b) return fast_a ? K4B_PART(256, true, true) : K4B_PART(256, false, true);
+    return fast_a ? K4B_PART(256, true, false) : K4B_PART(256, false, false);
+#undef K4B_PART
 }
 
-// kernel shapes of the join: {items per batch, entries per tile}; K4B_SEED_JOIN_VARIANT picks one (tests, measurements)
+// kernel shapes of the join: {items per batch, entries per tile}; K4B_SEED_JOIN_VARIANT picks one (tests, measurements).
+// Also measured and dropped (profiles/r02_join_variants_cfg4_5ctas.jsonl): 5 CTAs per SM (register cap 51: 55 ms against
+// 41 ms for config 4) and batches of 256 items (45.4 ms).
 constexpr int kJoinDefaultVariant = 0;
 static cudaError_t join_launch(int variant, const SeedCtx &cx, const uint32_t *d_off, const uint4 *d_ent, uint32_t q0,
                                uint32_t n_items, const uint32_t *keys, const uint32_t *ids, uint32_t *d_best,

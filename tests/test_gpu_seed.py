@@ -274,6 +274,106 @@ def test_seed_engine_bucket_parts_combine_to_the_full_result(oracle, monkeypatch
         q.free()
 
 
+@pytest.mark.parametrize("join", ["0", "1"])
+@pytest.mark.parametrize("build", ["1", "2", "14", "29"])
+def test_seed_index_by_partition_passes_matches_oracle(oracle, monkeypatch, join, build):
+    """K4B_SEED_INDEX != 0: the index built by two partition passes (flags, k4b_kernels.cuh: 1 plain, 2 tiles of 4096
+    entries, 4 count pass with shared-memory counters, 8 three-word field extraction, 16 persistent second pass;
+    cores of 6, 7 and 8 bases: buckets of 12, 14 and 16 bits; longer cores keep the one-by-one build) answers like
+    the oracle in both query schedules: planted probes, targets with N, the assembly against itself with -z, and
+    bucket shards."""
+    import torch
+    monkeypatch.setenv("K4B_SEED_INDEX", build)
+    monkeypatch.setenv("K4B_SEED_JOIN", join)
+    for K, R, both in ((32, 3, True), (25, 3, False), (28, 3, True), (48, 5, True), (20, 1, True), (64, 7, True)):
+        target, probes = _planted(6100 + K, [6000, 3000, 2500])
+        assert np.array_equal(k4b.targeted(target, probes, K, R, both), oracle.targeted_brute(target, probes, K, R, both)), (K, R)
+    target, probes = _planted(6200, [5000, 4000], alpha_t=5)
+    target[1000:1010] = 4
+    assert np.array_equal(k4b.targeted(target, probes, 32, 3, True), oracle.targeted_brute(target, probes, 32, 3, True))
+    target, _ = _planted(6300, [5000, 2500])
+    assert np.array_equal(k4b.targeted(target, None, 32, 3, True, intra_inter_both=1),
+                          oracle.targeted_self_brute(target, 32, 3, True, 1))
+    # bucket shards: three parts of the index, minima combined
+    K, R, both, nparts = 32, 3, True, 3
+    target, probes = _planted(6400, [7000, 2500, 3000])
+    want = oracle.targeted_brute(target, probes, K, R, both)
+    t, q = hamm.Packed.from_host(target, K), hamm.Packed.from_host(probes, K)
+    try:
+        L = len(probes)
+        total = torch.empty(L, dtype=torch.int32, device="cuda")
+        hamm.best_init_device(total.data_ptr(), L, K)
+        for part in range(nparts):
+            best = torch.empty(L, dtype=torch.int32, device="cuda")
+            hamm.best_init_device(best.data_ptr(), L, K)
+            assert hamm.targeted_seed_part_device(q, t, both, 4, 8, part, nparts, best.data_ptr()) > 0
+            total = torch.minimum(total, best)
+        out = torch.empty(L, dtype=torch.int16, device="cuda")
+        hamm.targeted_finalize_device(q, total.data_ptr(), 4, out.data_ptr())
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().view(np.uint16)
+        res = np.full(L, 0xFF, dtype=np.uint8)
+        res[got <= K] = got[got <= K].astype(np.uint8)
+        assert np.array_equal(res, want)
+    finally:
+        t.free()
+        q.free()
+
+
+def test_seed_index_partition_equals_one_by_one_at_3Mbp(monkeypatch):
+    """all index builds give the same minima and index the same number of cores on a 3 Mbp assembly whose coarse
+    partitions span several tiles, with a 150 kbp poly-A run and a 60 kbp (AC)n run (one bucket of 150 k entries:
+    a digit that fills whole tiles) and an entry shorter than a tile"""
+    rng = np.random.default_rng(6500)
+    ents = [rng.integers(0, 4, size=n, dtype=np.uint8) for n in (1_700_000, 900, 1_300_000)]
+    ents[0][400_000:550_000] = 0
+    ents[2][100_000:160_000] = np.tile(np.array([0, 1], np.uint8), 30_000)
+    ents[2][700_000:700_020] = 4
+    target = np.ascontiguousarray(np.concatenate([np.concatenate([e, [7]]) for e in ents]).astype(np.uint8))
+    cpl = np.array([3, 2, 1, 0, 4, 5, 6, 7], np.uint8)
+    parts = []
+    for start, n, rc in ((399_900, 400, False), (1_000_000, 3000, False), (2_000_000, 3000, True), (1_800_950, 200, False)):
+        seg = target[start:start + n].copy()
+        seg = seg[seg < 4]
+        idx = rng.choice(len(seg), size=len(seg) // 30, replace=False)
+        seg[idx] = (seg[idx] + 1 + rng.integers(0, 3, size=len(idx))) % 4
+        parts += [cpl[seg[::-1]] if rc else seg, np.array([7], np.uint8)]
+    parts.append(rng.integers(0, 4, size=2000, dtype=np.uint8))
+    probes = np.ascontiguousarray(np.concatenate(parts), dtype=np.uint8)
+    res = {}
+    for K, R in ((32, 3), (24, 3), (28, 3)):
+        for join in ("0", "1"):
+            for build in ("0", "1", "2", "5", "9", "17", "14", "29"):
+                monkeypatch.setenv("K4B_SEED_JOIN", join)
+                monkeypatch.setenv("K4B_SEED_INDEX", build)
+                res[build] = (k4b.targeted(target, probes, K, R, True), hamm.last_seed_info()["indexed_cores"])
+                assert res[build][1] == res["0"][1] > 2_900_000, (K, R, join, build)
+                assert np.array_equal(res["0"][0], res[build][0]), (K, R, join, build)
+            assert (res["1"][0] < K // (K // (R + 1))).sum() > 4000  # the planted copies are found
+
+
+def test_seed_index_partition_with_one_huge_bucket(monkeypatch):
+    """8 Mbp of poly-A beside 1 Mbp of random sequence: one bucket with 8 M entries - a shared-memory counter that
+    hands on 2^15 several times, thousands of tiles with a single digit in both passes - gives the same index size
+    and the same minima in every build"""
+    rng = np.random.default_rng(6600)
+    rnd = rng.integers(0, 4, size=1_000_000, dtype=np.uint8)
+    target = np.ascontiguousarray(np.concatenate([rnd[:400_000], [7], np.zeros(8_000_000, np.uint8), [7], rnd[400_000:], [7]]), dtype=np.uint8)
+    seg = rnd[700_000:703_000].copy()
+    idx = rng.choice(len(seg), size=100, replace=False)
+    seg[idx] = (seg[idx] + 1 + rng.integers(0, 3, size=len(idx))) % 4
+    tail = np.concatenate([rnd[399_990:400_000], np.zeros(40, np.uint8)])  # no K-mer of the assembly: crosses an entry end
+    probes = np.ascontiguousarray(np.concatenate([seg, [7], tail, [7], rng.integers(0, 4, size=1000, dtype=np.uint8)]), dtype=np.uint8)
+    res = {}
+    monkeypatch.setenv("K4B_SEED_JOIN", "1")
+    for build in ("0", "1", "5", "29", "14"):
+        monkeypatch.setenv("K4B_SEED_INDEX", build)
+        res[build] = (k4b.targeted(target, probes, 32, 3, True), hamm.last_seed_info()["indexed_cores"])
+        assert res[build][1] == res["0"][1] > 8_900_000, build
+        assert np.array_equal(res["0"][0], res[build][0]), build
+    assert (res["0"][0][:2900] < 4).sum() > 2500
+
+
 def test_exact_where_the_reference_depth_cut_fires(oracle, tmp_path):
     """Repeat-rich assembly (tests/golden/depth_case.py): the seed engine reports the true minimum where the
     reference at its default sensitivity truncates its search and reports "not found"; the depth signal
