@@ -192,9 +192,10 @@ __device__ __forceinline__ uint32_t part_group(uint4 (&e)[kPartPer], uint32_t li
     uint32_t total;
     const uint32_t h = tid < 256 ? sh.hist[tid] : 0u;
     const uint32_t ex = cta_excl_scan_256(h, sh.ws, total);
+    uint32_t g = 0;
     if (tid < 256) {
         sh.start[tid] = ex;
-        sh.gbase[tid] = h ? reserve(tid, h) : 0u;
+        if (h) g = reserve(tid, h);  // the returning atomic is in flight while the tile is grouped
     }
     __syncthreads();
 #pragma unroll
@@ -203,6 +204,7 @@ __device__ __forceinline__ uint32_t part_group(uint4 (&e)[kPartPer], uint32_t li
             const uint32_t b = e[u].w & 0xffffu;
             out[sh.start[digit_of(b)] + (e[u].w >> 16)] = make_uint4(e[u].x, e[u].y, e[u].z, b);
         }
+    if (tid < 256) sh.gbase[tid] = g;  // read after the barrier of part_copy_out
     return total;
 }
 template <int THREADS, class DigitOf>
@@ -224,6 +226,24 @@ __device__ __forceinline__ void part_tile_out(uint4 (&e)[kPartPer], uint32_t liv
 extern __shared__ uint4 part_out[];  // THREADS * 8 entries
 
 // pass A: positions -> entries grouped by the top 8 bits of the bucket.  cur_a: 256 zeroed counters.
+// entry of the core at tile offset lt (position pos) cut out of a staged copy of the planes that starts 32 bases
+// before the tile: three words per plane hold the 16 + core + 16 bases of a core of at most 8 bases.  false: the
+// core holds a non-ACGT symbol or its bucket lies outside [b_lo, b_hi)
+__device__ __forceinline__ bool part_fast_entry(const uint32_t *s0, const uint32_t *s1, const uint32_t *s2, uint32_t lt,
+                                                uint32_t pos, uint32_t core_len, uint32_t b_lo, uint32_t b_hi, uint4 &e) {
+    const uint32_t lb = lt + 16;  // bit of base pos - 16 in the staged copy
+    const uint32_t wi = lb >> 5, sh5 = lb & 31u, m = (1u << core_len) - 1u;
+    // per plane: first word = bases pos-16 .. pos+15, second = bases pos+16 .. pos+47
+    const uint32_t a0 = __funnelshift_r(s0[wi], s0[wi + 1], sh5), a1 = __funnelshift_r(s0[wi + 1], s0[wi + 2], sh5);
+    const uint32_t c0 = __funnelshift_r(s1[wi], s1[wi + 1], sh5), c1 = __funnelshift_r(s1[wi + 1], s1[wi + 2], sh5);
+    const uint32_t n0 = __funnelshift_r(s2[wi], s2[wi + 1], sh5), n1 = __funnelshift_r(s2[wi + 1], s2[wi + 2], sh5);
+    const uint32_t b = (__funnelshift_r(a0, a1, 16) & m) | ((__funnelshift_r(c0, c1, 16) & m) << core_len);
+    if ((__funnelshift_r(n0, n1, 16) & m) != 0 || b < b_lo || b >= b_hi) return false;
+    e = make_uint4(pos, (a0 & 0xffffu) | (__funnelshift_r(a0, a1, 16 + core_len) << 16),
+                   (c0 & 0xffffu) | (__funnelshift_r(c0, c1, 16 + core_len) << 16), b);
+    return true;
+}
+
 // FAST: bucket and flank signature cut out of three staged words per plane (the 16 + core + 16 bases of a core of at
 // most 8 bases span 40 bits) instead of one two-word window per field
 template <int THREADS, bool FAST>
@@ -256,24 +276,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) seed_part_a_kernel(Im
         const uint32_t pos = base + (uint32_t)j * THREADS + tid;
         e[j] = make_uint4(0, 0, 0, 0);
         if (FAST) {
-            if (pos < n_pos) {
-                const uint32_t lb = pos - base + 16;  // bit of base pos - 16 in the staged copy (which starts at base - 32)
-                const uint32_t wi = lb >> 5, sh5 = lb & 31u, m = (1u << core_len) - 1u;
-                // per plane: first word = bases pos-16 .. pos+15, second = bases pos+16 .. pos+47
-                const uint32_t a0 = __funnelshift_r(stage[0][wi], stage[0][wi + 1], sh5);
-                const uint32_t a1 = __funnelshift_r(stage[0][wi + 1], stage[0][wi + 2], sh5);
-                const uint32_t c0 = __funnelshift_r(stage[1][wi], stage[1][wi + 1], sh5);
-                const uint32_t c1 = __funnelshift_r(stage[1][wi + 1], stage[1][wi + 2], sh5);
-                const uint32_t n0 = __funnelshift_r(stage[2][wi], stage[2][wi + 1], sh5);
-                const uint32_t n1 = __funnelshift_r(stage[2][wi + 1], stage[2][wi + 2], sh5);
-                const uint32_t k0 = __funnelshift_r(a0, a1, 16) & m, k1 = __funnelshift_r(c0, c1, 16) & m;
-                const uint32_t b = k0 | (k1 << core_len);
-                if ((__funnelshift_r(n0, n1, 16) & m) == 0 && b >= b_lo && b < b_hi) {
-                    e[j] = make_uint4(pos, (a0 & 0xffffu) | (__funnelshift_r(a0, a1, 16 + core_len) << 16),
-                                      (c0 & 0xffffu) | (__funnelshift_r(c0, c1, 16 + core_len) << 16), b);
-                    live |= 1u << j;
-                }
-            }
+            if (pos < n_pos && part_fast_entry(stage[0], stage[1], stage[2], pos - base, pos, core_len, b_lo, b_hi, e[j])) live |= 1u << j;
         } else if (pos < n_pos) {
             bool ok;
             const uint32_t b = core_bucket(src, pos, core_len, bits, ok);
@@ -768,7 +771,8 @@ size_t seed_scan_temp_bytes(uint32_t n_buckets) {
     return bytes;
 }
 
-// partition passes.  FAST_A: three-word field extraction in pass A; PERSIST_B: persistent pass B with the next tile's
+// partition passes.  FAST_A: three-word field extraction in pass A (a persistent pass A with the next tile's plane
+// words prefetched was measured too: 0.2 ms slower, profiles/r02_index_build_variants_cfg4.jsonl); PERSIST_B: persistent pass B with the next tile's
 // loads in flight during the copy-out (256 threads only)
 template <int THREADS, bool FAST_A, bool PERSIST_B>
 static cudaError_t part_launch(ImageView t, uint32_t n_pos, uint32_t core_len, uint32_t bits, uint32_t b_lo, uint32_t b_hi,
@@ -784,19 +788,19 @@ static cudaError_t part_launch(ImageView t, uint32_t n_pos, uint32_t core_len, u
             e = cudaFuncSetAttribute(seed_part_b_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
         if (e != cudaSuccess) return e;
     }
-    seed_part_a_kernel<THREADS, FAST_A><<<(n_pos + kTile - 1) / kTile, THREADS, kSmem, st>>>(t, n_pos, core_len, bits, b_lo, b_hi,
-                                                                                           d_off, d_cur_a, d_part);
-    cudaError_t e = cudaGetLastError();
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    const uint32_t a_tiles = (n_pos + kTile - 1) / kTile;
+    seed_part_a_kernel<THREADS, FAST_A><<<a_tiles, THREADS, kSmem, st>>>(t, n_pos, core_len, bits, b_lo, b_hi, d_off, d_cur_a, d_part);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // tiles of all coarse partitions: at most entries / tile + one ragged tile per partition
     const uint32_t max_tiles = n_pos / kTile + 257;
     if (!PERSIST_B) {
         seed_part_b_kernel<THREADS><<<max_tiles, THREADS, kSmem, st>>>(bits, d_off, d_cursor, d_part, d_ent);
     } else {
-        int dev = 0, sms = 0;
-        e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
         const uint32_t grid = std::min<uint32_t>(max_tiles, (uint32_t)sms * 4u);
         seed_part_b_persistent_kernel<<<grid, 256, kSmem, st>>>(bits, d_off, d_cursor, d_part, d_ent);
     }
