@@ -741,6 +741,36 @@ def targeted_leg(c, scale, steps, warmup, e2e_steps, with_cpu):
                     "bytes_model": "16 B per bucket entry streamed by the query kernel (%d entries) + index build: planes read "
                                    "twice, 16 B written per indexed core (%d cores)" % (info["occurrences"], info["indexed_cores"]),
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if c.peaks else "fallback 6552.3 GB/s (MEASURED_PEAKS.json absent)"}
+    # the HBM-bound part of the job on its own: the index build, timed as a call that joins ONE probe K-mer
+    index_build = None
+    if c.world == 1:
+        try:
+            scratch = torch.empty(L, dtype=torch.int32, device=c.dev)
+            i_ms = []
+            for _ in range(3):
+                hamm.best_init_device(scratch.data_ptr(), L, K, c.stream.cuda_stream)
+                hamm.targeted_seed_device(q_img, t_img, both, clamp, core, 0, 1, scratch.data_ptr(), c.stream.cuda_stream)
+                c.stream.synchronize()
+                i_ms.append(hamm.last_kernel_ms())
+            cores = hamm.last_seed_info()["indexed_cores"]
+            partition = os.environ.get("K4B_SEED_INDEX", "1") != "0" and bits <= 16
+            i_bytes = (48.0 if partition else 16.0) * cores + 0.75 * len(target)
+            i_s = min(i_ms) * 1e-3
+            index_build = {"bound": "hbm", "ms": min(i_ms), "achieved": i_bytes / i_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": i_bytes / i_s / 1e9 / hbm_peak, "indexed_cores": cores,
+                           "kernel": ("seed_count_smem_kernel + seed_part_a_kernel + seed_part_b_persistent_kernel" if partition
+                                      else "seed_scan_kernel<count> + seed_scan_kernel<fill>"),
+                           "bytes_model": ("planes read twice (3/8 B per base each) + per indexed core 16 B written by the first "
+                                           "partition pass, 16 B read + 16 B written by the second" if partition else
+                                           "planes read twice + 16 B written per indexed core"),
+                           "timed": "engine's own CUDA events around a call that builds the whole index and joins one probe "
+                                    "K-mer (includes ~1 ms of fixed launches: probe reverse complement, item keys, sort, join); "
+                                    "best of 3",
+                           "profile": "profiles/r02_ncu_full_seed_index_partition_v29_summary.json" if partition else
+                                      "profiles/r02_ncu_full_seed_scan_summary.json",
+                           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if c.peaks else "fallback 6552.3 GB/s"}
+        except Exception as ex:  # a diagnostic: never lose the leg over it
+            index_build = {"error": repr(ex)}
     # parity: sampled probe K-mers by the POPC all-pairs kernel (targeted rules) and a NumPy brute force
     parity = None
     if c.rank == 0:
@@ -809,8 +839,8 @@ def targeted_leg(c, scale, steps, warmup, e2e_steps, with_cpu):
             "engine": "seed-and-verify (pigeonhole cores of %d bases, bucket index with flank signatures, %s)"
                       % (core, "bucket-major join" if join else "warp per item"),
             "parallelism": "index-bucket shards x%d (each rank builds 1/%d of the index, answers all probes) + all_reduce(MIN)" % (c.world, c.world),
-            "e2e": e2e, "roofline": roofline, "result_checksum": checksum, "parity": parity, "cpu_baseline": cpu,
-            "gpu_launches": launches, "clocks": clocks}
+            "e2e": e2e, "roofline": roofline, "index_build": index_build, "result_checksum": checksum, "parity": parity,
+            "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks}
 
 
 # ------------------------------------------------------------------------------------------
@@ -940,8 +970,8 @@ def run_ours(args):
                     "config": {"workload": leg["workload"], "K": leg["K"], "R": leg["R"], "engine": leg["engine"],
                                "parallelism": leg["parallelism"], "l2": "256 MB flush write between timed steps",
                                "result_checksum": leg["result_checksum"]},
-                    "roofline": leg["roofline"], "cpu_baseline": leg["cpu_baseline"], "e2e": leg["e2e"], "parity": leg["parity"],
-                    "gpu_launches": leg["gpu_launches"], "clocks": leg["clocks"]}
+                    "roofline": leg["roofline"], "index_build": leg["index_build"], "cpu_baseline": leg["cpu_baseline"],
+                    "e2e": leg["e2e"], "parity": leg["parity"], "gpu_launches": leg["gpu_launches"], "clocks": leg["clocks"]}
     elif args.engine == "popc":
         leg = popc_leg(c, args.workload, args.steps, args.warmup, args.batch)
         if c.rank == 0:
