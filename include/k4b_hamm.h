@@ -208,7 +208,11 @@ int k4b_targeted_diag_device(k4b_packed *probes, k4b_packed *targets, int both_s
  * bucket index of the target's cores and each occurrence is verified over the full K bases.
  * Exact for distances < clamp, which needs clamp <= K/core_len.  Probe K-mers that hold N / InDel
  * (wildcards) are skipped - k4b_hamm_targeted answers those with k4b_allpairs_min_device.  Probe
- * K-mers starting in [q_begin, q_end); d_best as above. */
+ * K-mers starting in [q_begin, q_end); d_best as above.
+ * Device memory (stream-ordered pool, released when the call's work is done): 16 bytes per target
+ * base for the index, and as much again while it is built when core_len <= 8 (two partition passes
+ * through a scratch array; without room for it, or with K4B_SEED_INDEX=0, the entries are placed
+ * one by one instead: slower, same index). */
 int k4b_targeted_seed_device(k4b_packed *probes, k4b_packed *targets, int both_strands, uint32_t clamp,
                              uint32_t core_len, uint32_t q_begin, uint32_t q_end, uint32_t *d_best,
                              void *stream, int *launches);
