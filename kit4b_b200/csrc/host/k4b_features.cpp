@@ -9,7 +9,8 @@
 //   * the raw BED reader (BEDfile.cpp:1172-1337 ProcessBedFile, :1794-2072 AddFeature): tab or comma
 //     separated, BED3..BED12, the file becomes a "gene + exons" file at the first line that carries
 //     thickStart..blockStarts; and the preprocessed binary 'bios' type-7 container that `genbiobed`
-//     writes (BEDfile.h:141-163 header, :105-137 records; BEDfile.cpp:2255-2470 LoadFeatures);
+//     writes (BEDfile.h:141-163 header, :105-137 records; BEDfile.cpp:2255-2470 LoadFeatures); and GFF3
+//     gene models, which the reference tries when the BED reader gives up (BEDfile.cpp:757-1131);
 //   * chromosome lookup, case-insensitive, with the chloroplast/ChrC and mitochondria/ChrM aliases
 //     (BEDfile.cpp:3070-3095);
 //   * the per-feature overlap rules (BEDfile.cpp:4011-4170 GetFeatureOverlaps) - including that ANY
@@ -197,6 +198,227 @@ int read_bed_text(const std::string &path, FeatureSet &fs, std::string &err) {
     return kOk;
 }
 
+// ---- GFF3 gene models (BEDfile.cpp:757-1131) ---------------------------------------------------
+// What the reference makes of a GFF3 file when the BED reader has given up on it: gene (and "orphan"
+// mRNA) lines open a gene, exon / CDS / UTR lines paint a 2-bit map of the gene, and when the next gene
+// opens the map is turned into ONE BED12-style feature (exon blocks = maximal painted runs).  Kept with
+// its reading rules, because they decide which loci count as exonic:
+//   * the gene's name is its Name= attribute; a gene without one is dropped (AddFeature refuses the
+//     empty name and the caller ignores that, :734);
+//   * an mRNA line directly after a gene line is ignored, any LATER mRNA line (second isoform) opens a
+//     new "gene" under the mRNA's name (:1042-1046: the flag is cleared by the first exon / CDS / UTR);
+//   * coordinates stay 1-based: start = GFF start, end = GFF end (:734), blocks relative to the start;
+//   * thickStart / thickEnd are written RELATIVE to the gene (:697-725) but read back as absolute;
+//     a gene without painted loci gets one block of end - start bases and absolute thick values;
+//   * of a gene's blocks only the first two survive: the writer repeats the second for all later ones.
+enum GffType { kGffGene = 1, kGffMrna, kGffExon, kGffIntron, kGffCds, kGffUtr3, kGffUtr5 };
+constexpr int kGffAttrLen = 200;  // BEDfile.h:86
+
+struct GffLine {
+    char chrom[82], name[kGffAttrLen + 2];
+    int start, end, score;
+    char strand;
+};
+
+// ParseGFFline (:757-957): > 0 the feature type, 0 a type of no interest, < 0 not a feature line
+int parse_gff_line(const char *line, GffLine &g) {
+    char source[82], feature[52], score_s[52], strand = 0, frame = 0;
+    int attr_at = 0;
+    g.chrom[0] = g.name[0] = '\0';
+    const int n = sscanf(line, " %80s %80s %50s %d %d %50s %c %c %n", g.chrom, source, feature, &g.start, &g.end, score_s, &strand,
+                         &frame, &attr_at);
+    if (n < 8) return -1;
+    if (score_s[0] == '.') g.score = 0;
+    else g.score = std::min(999, std::max(0, (int)atof(score_s)));
+    g.strand = strand == '-' ? '-' : '+';
+    static const char *const kTypes[] = {"gene", "mRNA", "exon", "intron", "CDS", "three_prime_UTR", "five_prime_UTR"};
+    int type = 0;
+    for (; type < 7; ++type)
+        if (!strcasecmp(feature, kTypes[type])) break;
+    if (type == 7) return 0;
+    // attributes: ID=, Parent= and Name= are recognised wherever they start while no value is being read (also
+    // inside other keys and values); a value ends at ';', white space inside it is dropped
+    static const char *const kAttrs[] = {"ID", "Parent", "Name"};
+    char values[3][kGffAttrLen + 2];
+    memset(values, 0, sizeof(values));
+    char *val = nullptr;
+    int val_len = 0, state = 0;
+    const char *txt = line + attr_at;
+    const int len = (int)strlen(txt);
+    for (int i = 0; i < len; ++i, ++txt) {
+        const char c = *txt;
+        if (state == 0) {
+            if (c == ';' || c == '=') continue;
+            int a = 0, ident = 0;
+            for (; a < 3; ++a) {
+                ident = (int)strlen(kAttrs[a]);
+                if (!strncmp(txt, kAttrs[a], (size_t)ident)) break;
+            }
+            if (a == 3 || txt[ident] != '=') continue;
+            val = values[a];
+            memset(val, 0, kGffAttrLen + 2);
+            val_len = 0;
+            i += ident;  // the loop step skips the '='
+            txt += ident;
+            state = 1;
+            continue;
+        }
+        if (isspace((unsigned char)c)) continue;
+        if (c == ';') {
+            state = 0;
+            continue;
+        }
+        if (val_len < kGffAttrLen) val[val_len++] = c;
+    }
+    strcpy(g.name, values[2]);
+    return type + 1;
+}
+
+// AddFeatExonsBitmap (:565-631): 2 bits per gene locus; 0 none, 1 exon, 2 CDS, 3 UTR; CDS wins, UTR beats exon
+bool gff_paint(int type, int f_start, int f_end, int g_start, int g_end, std::vector<uint8_t> &map) {
+    if (f_start > f_end) std::swap(f_start, f_end);
+    if (f_start < g_start || f_end > g_end) return false;
+    const uint32_t want = type == kGffExon ? 1u : type == kGffCds ? 2u : 3u;
+    for (int rel = f_start - g_start; rel <= f_end - g_start; ++rel) {
+        const uint32_t sh = 2u * ((uint32_t)rel & 3u);
+        const uint32_t cur = (map[(size_t)rel >> 2] >> sh) & 3u;
+        uint32_t now = want;
+        if (cur == 2) now = 2;
+        else if (cur == 3 && want == 1) now = 3;
+        map[(size_t)rel >> 2] = (uint8_t)((map[(size_t)rel >> 2] & ~(3u << sh)) | (now << sh));
+    }
+    return true;
+}
+
+// AddGFF3Gene2BED (:636-737) + AddFeature: the painted map as one gene feature
+void gff_flush_gene(FeatureSet &fs, const GffLine &gene, const std::vector<uint8_t> &map) {
+    std::vector<int> rel_start, size;
+    int min_cds = -1, max_cds = -1;
+    uint32_t prev = 0;
+    const int span = 1 + gene.end - gene.start;
+    for (int rel = 0; rel < span; ++rel) {
+        uint32_t cur = (map[(size_t)rel >> 2] >> (2u * ((uint32_t)rel & 3u))) & 3u;
+        if (cur == 3) cur = 1;  // UTRs are exonic
+        if (cur == 0) {
+            prev = 0;
+            continue;
+        }
+        if (prev == 0) {
+            rel_start.push_back(rel);
+            size.push_back(1);
+            if (cur == 2 && min_cds == -1) min_cds = max_cds = rel;
+            prev = cur;
+            continue;
+        }
+        if (prev != 2 && cur == 2) {
+            if (min_cds == -1) min_cds = max_cds = rel;
+        } else if (prev == 2 && cur == 2) {
+            max_cds = rel;
+        }
+        // (prev keeps the type the block began with, as in the reference: a CDS that follows a UTR inside one
+        // block never extends max_cds beyond its first base)
+        size.back() += 1;
+    }
+    if (rel_start.empty()) {
+        rel_start.push_back(0);
+        size.push_back(gene.end - gene.start);
+        min_cds = gene.start;
+        max_cds = gene.end + 1;
+    }
+    if (min_cds == -1) min_cds = gene.start;
+    if (max_cds == -1) max_cds = gene.end + 1;
+    // AddFeature's own checks (:1822-1830); its refusal is ignored by the caller
+    const int start = gene.start, end = gene.end + 1;
+    if (!gene.name[0] || !gene.chrom[0] || start < 0 || end < start || strlen(gene.name) > (size_t)kMaxFeatName - 1 ||
+        strlen(gene.chrom) > (size_t)kMaxChromName - 1 || rel_start.size() > (size_t)kMaxExons)
+        return;
+    std::string supp = std::to_string(min_cds) + " " + std::to_string(max_cds) + " 0 " + std::to_string(rel_start.size()) + " ";
+    // the reference's writer never advances past the SECOND block (:727-735): blocks 3.. repeat block 2, so a
+    // gene keeps its first two exons only and everything after the second one is outside every exon
+    for (size_t i = 0; i < size.size(); ++i) supp += (i ? "," : "") + std::to_string(size[std::min<size_t>(i, 1)]);
+    supp += ", ";
+    for (size_t i = 0; i < rel_start.size(); ++i) supp += (i ? "," : "") + std::to_string(rel_start[std::min<size_t>(i, 1)]);
+    Feature f;
+    f.start = start;
+    f.end = end - 1;
+    f.score = gene.score;
+    f.strand = gene.strand;
+    if (!parse_gene_detail(supp.c_str(), start, end, f)) return;
+    fs.chroms[(size_t)chrom_slot(fs, gene.chrom)].feats.push_back(std::move(f));
+}
+
+// ParseGFF3FileGFFFeats (:965-1131).  > 0: number of genes opened; 0: none (the caller treats that as
+// "no features available"); < 0: error
+int read_gff3_text(const std::string &path, FeatureSet &fs, std::string &err) {
+    FILE *in = fopen(path.c_str(), "r");
+    if (!in) {
+        err = "Error accessing GFF file " + path + " - " + strerror(errno);
+        return kErrOpnFile;
+    }
+    fs.gene_exons = true;
+    std::vector<char> buf(128 + kMaxExons * 8);
+    std::vector<uint8_t> map;
+    GffLine gene, line;
+    memset(&gene, 0, sizeof(gene));
+    int line_no = 0, n_genes = 0, n_feats = 0, rc = kOk;
+    bool fresh_gene = false, have_gene = false;
+    while (fgets(buf.data(), (int)buf.size() - 1, in)) {
+        ++line_no;
+        for (const char *p = buf.data(); *p; ++p)
+            if ((unsigned char)*p > 127) {
+                err = "Errors whilst parsing - " + path + " - non-ascii chars at line " + std::to_string(line_no);
+                rc = kErrParse;
+                break;
+            }
+        if (rc) break;
+        if (n_genes < 1 && n_feats == 0 && line_no >= 100) {  // no gene within the first 100 lines: not GFF3
+            err = path + " is neither a BED nor a GFF3 file (no gene feature in its first 100 lines)";
+            rc = kErrFileType;
+            break;
+        }
+        char *txt = buf.data();
+        while (*txt && isspace((unsigned char)*txt)) ++txt;
+        size_t len = strlen(txt);
+        while (len && isspace((unsigned char)txt[len - 1])) txt[--len] = '\0';
+        if (!*txt || *txt == '#') continue;
+        const int type = parse_gff_line(txt, line);
+        if (type <= 0 || type == kGffIntron) continue;
+        if (type == kGffMrna && fresh_gene) continue;  // the gene's own transcript
+        if (type == kGffGene || type == kGffMrna) {
+            if (n_feats) gff_flush_gene(fs, gene, map);
+            gene = line;
+            if (gene.end < gene.start) {  // the reference sizes its map from end - start as an unsigned number
+                err = "Errors whilst parsing - " + path + " - at line " + std::to_string(line_no) + ", gene ends before it starts";
+                rc = kErrParse;
+                break;
+            }
+            map.assign((size_t)(1 + (1 + gene.end - gene.start) / 4), 0);
+            n_feats = 0;
+            ++n_genes;
+            fresh_gene = have_gene = true;
+        } else {
+            // (before any gene line the reference compares with uninitialised bounds; refused here)
+            if (!have_gene || line.start < gene.start || line.end > gene.end) {
+                err = "Errors whilst parsing - " + path + " - at line " + std::to_string(line_no) +
+                      ", feature start/end are outside range of gene start/end";
+                rc = kErrParse;
+                break;
+            }
+            if (!gff_paint(type, line.start, line.end, gene.start, gene.end, map)) {
+                err = "Errors generating packed bitmap of gene exons whilst parsing - " + path + " - at line " + std::to_string(line_no);
+                rc = kErrParse;
+                break;
+            }
+            fresh_gene = false;
+        }
+        ++n_feats;
+    }
+    fclose(in);
+    if (rc) return rc;
+    if (n_feats) gff_flush_gene(fs, gene, map);
+    return n_genes;
+}
+
 template <class T>
 bool rd(const std::vector<uint8_t> &img, size_t ofs, T &v) {
     if (ofs + sizeof(T) > img.size()) return false;
@@ -303,27 +525,28 @@ int read_features(const std::string &path, FeatureSet &fs, std::string &err) {
     const bool bios = tolower(magic[0]) == 'b' && tolower(magic[1]) == 'i' && tolower(magic[2]) == 'o' && tolower(magic[3]) == 's';
     int rc = bios ? read_biobed(path, fs, err) : read_bed_text(path, fs, err);
     if (!bios && (rc == kErrFileType || rc == kErrParse)) {
-        // Not BED: the reference tries GFF3 next (BEDfile.cpp:415-432).  GFF3 gene models are not read by
-        // this drop-in; a file without GFF3 gene lines fails there only once it has 100 lines (:1031-1035),
-        // a shorter one "succeeds" with no features available.
-        bool gff = false;
-        long lines = 0;
-        std::ifstream in(path);
-        std::string line;
-        while (std::getline(in, line)) {
-            ++lines;
-            size_t tabs = 0;
-            for (char c : line) tabs += c == '\t';
-            if (tabs >= 8 && line[0] != '#') gff = true;
-        }
-        if (gff) {
-            err = path + " looks like GFF; this drop-in reads BED (BED3..BED12) and biobed feature files only - convert it first";
-            return kErrFileType;
-        }
-        if (lines >= 100) return rc;
+        // Not BED: the reference tries GFF3 next (BEDfile.cpp:415-432).  A file without GFF3 gene lines fails
+        // there only once it has 100 lines (:1031-1035); a shorter one "succeeds" with no features available
+        // (the zero gene count is returned as the result code).
         fs = FeatureSet();
-        fs.available = false;
-        return kOk;
+        std::string gff_err;
+        const int genes = read_gff3_text(path, fs, gff_err);
+        if (genes < 0) {
+            err = gff_err;
+            return genes;
+        }
+        if (genes == 0) {
+            fs = FeatureSet();
+            fs.available = false;
+            return kOk;
+        }
+        size_t kept = 0;
+        for (const FeatureChrom &c : fs.chroms) kept += c.feats.size();
+        if (!kept) {  // genes without a Name= attribute are dropped one by one: SortFeatures then finds nothing (:1530)
+            err = "Unable to load any features from '" + path + "'";
+            return kErrNoFeatures;
+        }
+        rc = kOk;
     }
     if (rc) return rc;
     finish(fs);

@@ -22,6 +22,7 @@ enum : int {
     kErrCreateFile = -89,
     kErrFileVer = -86,
     kErrFileAccess = -85,
+    kErrNoFeatures = -60,
     kErrFeature = -53,
     kErrParse = -46,
 };
@@ -167,7 +168,8 @@ struct FeatureSet {
     // OR of the overlap bits of every feature touching [start-updn, end+updn] (BEDfile.cpp:4279-4311)
     int feature_bits(int chrom, int start, int end, int want_bits, int updn) const;
 };
-// raw BED text (BED3..BED12, tabs or commas) or the binary biobed container written by `genbiobed`
+// raw BED text (BED3..BED12, tabs or commas), the binary biobed container written by `genbiobed`, or GFF3
+// gene models (tried, as in the reference, when the text is no BED)
 int read_features(const std::string &path, FeatureSet &fs, std::string &err);
 
 // Region mode of HammingDist (HammingDist.cpp:371-496, :606-700): every row `"chrom",loci,hamming` is put

@@ -1,8 +1,8 @@
 """Region mode of the HammingDist drop-in (k4b_hammingdist -I) against
 golden files written by the UNMODIFIED reference tool (HammingDist/HammingDist.cpp through
 oracle/_ref/hammingdist_ref; tests/golden/make_hammingdist_golden.py made them): BED12 gene models,
-BED6, the binary biobed container of `genbiobed`, -r / -R, chromosome aliases and the reference's
-reading rules (descriptor row, unknown chromosome mid-file, a feature file it cannot parse)."""
+BED6, the binary biobed container of `genbiobed`, GFF3 gene models, -r / -R, chromosome aliases and the
+reference's reading rules (descriptor row, unknown chromosome mid-file, a feature file it cannot parse)."""
 import json
 import os
 import subprocess
@@ -74,6 +74,29 @@ def test_feature_bits_by_hand(tmp_path):
     assert hostlib.feature_bits(str(bed), "chrZ", [5], 0) == [-1]
 
 
+def test_gff3_gene_models_by_hand(tmp_path):
+    """the reference's GFF3 reading rules (BEDfile.cpp:757-1131): 1-based coordinates kept as they are, exon blocks
+    = painted runs, only the first two blocks of a gene survive its writer, a later mRNA line opens a new gene, an
+    mRNA directly after its gene is ignored, a gene without Name= is dropped, one without exons is one block"""
+    gff = tmp_path / "g.gff3"
+    gff.write_text("##gff-version 3\n"
+                   "chrA\tsrc\tgene\t101\t900\t.\t+\t.\tID=g1;Name=geneP\n"
+                   "chrA\tsrc\tmRNA\t101\t900\t.\t+\t.\tID=m1;Parent=g1;Name=mP\n"
+                   "chrA\tsrc\texon\t101\t250\t.\t+\t.\tParent=m1\n"
+                   "chrA\tsrc\tCDS\t200\t250\t.\t+\t0\tParent=m1\n"
+                   "chrA\tsrc\texon\t401\t600\t.\t+\t.\tParent=m1\n"
+                   "chrA\tsrc\texon\t651\t900\t.\t+\t.\tParent=m1\n"
+                   "chrA\tsrc\tmRNA\t1001\t1100\t.\t-\t.\tID=m2;Parent=g1;Name=isoform2\n"
+                   "chrA\tsrc\texon\t1001\t1050\t.\t-\t.\tParent=m2\n"
+                   "chrA\tsrc\tgene\t1301\t1400\t.\t+\t.\tID=g3\n"
+                   "chrA\tsrc\texon\t1301\t1400\t.\t+\t.\tParent=g3\n"
+                   "chrA\tsrc\tgene\t1501\t1600\t.\t.\t.\tID=g4;Name=lonely\n")
+    exon, intron = 7, 8
+    loci = [100, 101, 250, 251, 400, 401, 600, 601, 651, 900, 1000, 1001, 1050, 1051, 1100, 1101, 1301, 1400, 1500, 1501, 1599, 1600, 1601]
+    want = [0, exon, exon, intron, intron, exon, exon, 0, 0, 0, 0, exon, exon, 0, 0, 0, 0, 0, 0, exon, exon, 0, 0]
+    assert hostlib.feature_bits(str(gff), "chrA", loci, 0) == want
+
+
 def test_region_mode_errors(tmp_path):
     csv = tmp_path / "h.csv"
     csv.write_text('"chrA",5,3\n"chrA",6,250\n')
@@ -86,9 +109,12 @@ def test_region_mode_errors(tmp_path):
     bad.write_text("chrA\t100\t900\tg\t0\t+\t100\t900\t255,0,0\t1\t800,\t0,\n")  # itemRgb triple: reference cannot read it
     with pytest.raises(RuntimeError, match="malformed"):
         hostlib.hamming_dist_regions([str(csv)], str(bad), out)
-    gff = tmp_path / "g.gff3"
-    gff.write_text("##gff-version 3\nchrA\tsrc\tgene\t100\t900\t.\t+\t.\tID=g1\n")
-    with pytest.raises(RuntimeError, match="GFF"):
+    gff = tmp_path / "g.gff3"  # a feature outside its gene is fatal in the reference's GFF3 reader too
+    gff.write_text("##gff-version 3\nchrA\tsrc\tgene\t100\t900\t.\t+\t.\tID=g1;Name=g\nchrA\tsrc\texon\t90\t200\t.\t+\t.\tParent=g1\n")
+    with pytest.raises(RuntimeError, match="outside range of gene"):
+        hostlib.hamming_dist_regions([str(csv)], str(gff), out)
+    gff.write_text("##gff-version 3\nchrA\tsrc\tgene\t100\t900\t.\t+\t.\tID=g1\n")  # no Name=: the gene is dropped
+    with pytest.raises(RuntimeError, match="Unable to load any features"):
         hostlib.hamming_dist_regions([str(csv)], str(gff), out)
     for flag in (["-r", "1000001"], ["-R", "201"], ["-m", "1"], ["-s", "3"]):
         p = subprocess.run([EXE, "-i", str(csv), "-I", str(bed), "-o", out] + flag, capture_output=True)
