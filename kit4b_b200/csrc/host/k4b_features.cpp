@@ -387,7 +387,7 @@ int read_gff3_text(const std::string &path, FeatureSet &fs, std::string &err) {
         if (type == kGffGene || type == kGffMrna) {
             if (n_feats) gff_flush_gene(fs, gene, map);
             gene = line;
-            if (gene.end < gene.start) {  // the reference sizes its map from end - start as an unsigned number
+            if (gene.end < gene.start || (long long)gene.end - gene.start >= 0x7fffffffLL) {  // the reference sizes its map from end - start as an unsigned number
                 err = "Errors whilst parsing - " + path + " - at line " + std::to_string(line_no) + ", gene ends before it starts";
                 rc = kErrParse;
                 break;
